@@ -1,0 +1,620 @@
+// capi.cu — implementation of the C-ABI declared in include/bfq_gpumatch.h (forward index + match).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bfq_gpumatch.h"
+#include "codec.h"
+#include "index_builder.h"
+#include "match_kernels.cuh"
+
+using namespace bfq;
+
+namespace {
+
+thread_local std::string g_err;
+int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(BFQ_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+// growable device / pinned-host buffers
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct bfq_result {
+    bfq_index* owner = nullptr;
+    int64_t n_topics = 0, n_ranges = 0, n_throttled = 0;
+    const uint32_t *span_begin = nullptr, *span_count = nullptr, *route_count = nullptr;
+    const bfq_range* ranges = nullptr;
+    const bfq_throttled* throttled = nullptr;
+    double ms[4] = {0, 0, 0, 0};
+};
+
+struct bfq_index {
+    int device = 0;
+    std::mutex mu;
+    Staging staging;
+    FlatIndex flat;          // host copy of the committed snapshot (segs / tenant map / stats are used on the host)
+    KVBlob committed;        // committed KV (for bfq_route_lookup)
+    bool have_snapshot = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evk[2] = {nullptr, nullptr};
+    double last_kernel_ms = 0;
+    // snapshot on device
+    DevBuf<Slot> d_slots, d_roots;
+    DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
+    DevBuf<uint8_t> d_rkind;
+    // per-call workspace
+    DevBuf<uint8_t> d_topics;
+    DevBuf<int64_t> d_topic_off;
+    DevBuf<int32_t> d_topic_tenant, d_tenant_tab;   // tenant_tab = root | maxP | maxG, 3 x n_tenants
+    DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept;
+    DevBuf<uint2> d_ranges, d_scratch;
+    DevBuf<uint3> d_throttled;
+    DevBuf<unsigned long long> d_counters;
+    PinBuf<unsigned long long> h_counters;
+    PinBuf<int32_t> h_tenant_tab;
+    // pinned result buffers (leased to the bfq_result of the latest bfq_match)
+    PinBuf<uint32_t> h_span_begin, h_span_count, h_route_count;
+    PinBuf<uint2> h_ranges;
+    PinBuf<uint3> h_throttled;
+    // statistics
+    int64_t launches = 0, overflow_topics = 0, flagged_topics = 0;
+    // last device result (for bfq_expand_device)
+    int64_t last_n_topics = 0;
+
+    ~bfq_index() {
+        cudaSetDevice(device);
+        d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release();
+        d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
+        d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
+        d_flagged.release(); d_kept.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
+        d_counters.release(); h_counters.release(); h_tenant_tab.release();
+        h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : evk) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// Shared core of bfq_match / bfq_match_device: topics are on the device; runs tier 1, tier 2 and caps.
+struct CoreOut {
+    int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0;
+};
+
+int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                        const int32_t* max_p, const int32_t* max_g, cudaStream_t stream) {
+    if (n_tenants < 0) return fail(BFQ_E_INVALID, "n_tenants < 0");
+    const size_t nt = (size_t) std::max(n_tenants, 1);
+    CUDA_TRY(h->h_tenant_tab.reserve(3 * nt));
+    CUDA_TRY(h->d_tenant_tab.reserve(3 * nt));
+    for (int32_t i = 0; i < n_tenants; i++) {
+        std::string t((const char*) tenants + tenant_off[i], (size_t) (tenant_off[i + 1] - tenant_off[i]));
+        auto it = h->flat.tenant_ordinal.find(t);
+        h->h_tenant_tab.p[i] = it == h->flat.tenant_ordinal.end() ? -1 : (int32_t) it->second;
+        h->h_tenant_tab.p[nt + i] = max_p ? max_p[i] : 0x7FFFFFFF;
+        h->h_tenant_tab.p[2 * nt + i] = max_g ? max_g[i] : 0x7FFFFFFF;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_tenant_tab.p, h->h_tenant_tab.p, 3 * nt * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    return BFQ_OK;
+}
+
+int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
+                   int64_t n, int32_t n_tenants, cudaStream_t stream, CoreOut* out) {
+    const size_t nn = (size_t) std::max<int64_t>(n, 1);
+    const size_t nt = (size_t) std::max(n_tenants, 1);
+    if (n >= (int64_t) 0x3FFFFFFF) return fail(BFQ_E_INVALID, "too many topics in one batch");
+    CUDA_TRY(h->d_span_begin.reserve(nn));
+    CUDA_TRY(h->d_span_count.reserve(nn));
+    CUDA_TRY(h->d_route_count.reserve(nn));
+    CUDA_TRY(h->d_overflow.reserve(nn));
+    CUDA_TRY(h->d_flagged.reserve(nn));
+    CUDA_TRY(h->d_kept.reserve(nn));
+    CUDA_TRY(h->d_counters.reserve(CTR_COUNT));
+    CUDA_TRY(h->h_counters.reserve(CTR_COUNT));
+    if (h->d_ranges.cap == 0) CUDA_TRY(h->d_ranges.reserve(std::max<size_t>(1 << 20, 4 * nn)));
+    if (h->d_throttled.cap == 0) CUDA_TRY(h->d_throttled.reserve(1 << 16));
+
+    MatchParams p{};
+    p.slots = h->d_slots.p;
+    p.roots = h->d_roots.p;
+    p.n_slots = h->flat.n_slots;
+    p.topics = d_topics;
+    p.topic_off = d_topic_off;
+    p.topic_tenant = d_topic_tenant;
+    p.tenant_root = h->d_tenant_tab.p;
+    p.max_pfanout = h->d_tenant_tab.p + nt;
+    p.max_gfanout = h->d_tenant_tab.p + 2 * nt;
+    p.n_topics = n;
+    p.span_begin = h->d_span_begin.p;
+    p.span_count = h->d_span_count.p;
+    p.route_count = h->d_route_count.p;
+    p.overflow_list = h->d_overflow.p;
+    p.flagged_list = h->d_flagged.p;
+    p.counters = h->d_counters.p;
+
+    unsigned long long* hc = h->h_counters.p;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        p.ranges = h->d_ranges.p;
+        p.ranges_cap = h->d_ranges.cap;
+        CUDA_TRY(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), stream));
+        p.work_list = nullptr;
+        p.n_work = 0;
+        if (n > 0) {
+            CUDA_TRY(cudaEventRecord(h->evk[0], stream));
+            launch_match(p, false, 0, stream);
+            CUDA_TRY(cudaEventRecord(h->evk[1], stream));
+            out->n_launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        out->n_overflow = (int64_t) hc[CTR_OVERFLOW];
+        if (n > 0) {
+            float kms = 0;
+            cudaEventElapsedTime(&kms, h->evk[0], h->evk[1]);
+            h->last_kernel_ms = kms;
+        }
+        if (hc[CTR_OVERFLOW] > 0) {
+            // ---- tier 2: per-warp global scratch sized from the index statistics (exact upper bounds)
+            const uint64_t capF = (uint64_t) h->flat.max_nodes_per_depth + 2;
+            const uint64_t capR = 2 * ((uint64_t) h->flat.max_tenant_nodes + 2) + 2;
+            const uint64_t per_warp = 2 * capF + capR;
+            uint64_t warps = std::min<uint64_t>(hc[CTR_OVERFLOW], std::max<uint64_t>(8, (1ull << 31) / (per_warp * sizeof(uint2))));
+            warps = std::min<uint64_t>(warps, 148 * 8);
+            warps = (warps + 7) / 8 * 8;
+            CUDA_TRY(h->d_scratch.reserve((size_t) (warps * per_warp)));
+            p.scratch = h->d_scratch.p;
+            p.scratch_frontier_cap = capF;
+            p.scratch_ranges_cap = capR;
+            p.work_list = h->d_overflow.p;
+            p.n_work = (int64_t) hc[CTR_OVERFLOW];
+            launch_match(p, true, (int) warps, stream);
+            out->n_launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (hc[CTR_ERROR] != 0) return fail(BFQ_E_STATE, "tier-2 scratch exhausted (index statistics inconsistent)");
+        }
+        if (hc[CTR_RANGES] <= h->d_ranges.cap) break;
+        // the range buffer was too small: grow and redo the batch
+        const size_t want = (size_t) (hc[CTR_RANGES] + hc[CTR_RANGES] / 4 + 1024);
+        if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
+        CUDA_TRY(h->d_ranges.reserve(want));
+        if (attempt == 7) return fail(BFQ_E_STATE, "range buffer sizing did not converge");
+    }
+    out->n_ranges = (int64_t) hc[CTR_RANGES];
+    out->n_flagged = (int64_t) hc[CTR_FLAGGED];
+    out->n_throttled = 0;
+    if (hc[CTR_FLAGGED] > 0) {
+        CapsParams c{};
+        c.flagged_list = h->d_flagged.p;
+        c.n_flagged = (int64_t) hc[CTR_FLAGGED];
+        c.topic_tenant = d_topic_tenant;
+        c.max_pfanout = h->d_tenant_tab.p + nt;
+        c.max_gfanout = h->d_tenant_tab.p + 2 * nt;
+        c.span_begin = h->d_span_begin.p;
+        c.span_count = h->d_span_count.p;
+        c.ranges = h->d_ranges.p;
+        c.segs = h->d_segs.p;
+        c.rkind = h->d_rkind.p;
+        c.pfx_persistent = h->d_pfxP.p;
+        c.pfx_group = h->d_pfxG.p;
+        c.kept_count = h->d_kept.p;
+        c.counters = h->d_counters.p;
+        for (int attempt = 0; attempt < 4; attempt++) {
+            c.throttled = h->d_throttled.p;
+            c.throttled_cap = h->d_throttled.cap;
+            CUDA_TRY(cudaMemsetAsync(h->d_counters.p + CTR_THROTTLED, 0, sizeof(unsigned long long), stream));
+            launch_caps(c, stream);
+            out->n_launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (hc[CTR_THROTTLED] <= h->d_throttled.cap) break;
+            CUDA_TRY(h->d_throttled.reserve((size_t) (hc[CTR_THROTTLED] + hc[CTR_THROTTLED] / 4 + 1024)));
+        }
+        out->n_throttled = (int64_t) hc[CTR_THROTTLED];
+    }
+    h->launches += out->n_launches;
+    h->overflow_topics += out->n_overflow;
+    h->flagged_topics += out->n_flagged;
+    h->last_n_topics = n;
+    return BFQ_OK;
+}
+
+int64_t emit_bytes(const std::string& s, uint8_t* out, int64_t cap) {
+    if (out && (int64_t) s.size() <= cap) memcpy(out, s.data(), s.size());
+    return (int64_t) s.size();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bfq_last_error(void) { return g_err.c_str(); }
+
+int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
+    if (!out) return fail(BFQ_E_INVALID, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BFQ_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= count) return fail(BFQ_E_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    auto* h = new bfq_index();
+    h->device = device_ordinal;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (auto& ev : h->ev)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto& ev : h->evk)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(BFQ_E_CUDA, cudaGetErrorString(e));
+    }
+    *out = h;
+    return BFQ_OK;
+}
+
+void bfq_index_destroy(bfq_index* h) { delete h; }
+
+int32_t bfq_index_reset(bfq_index* h) {
+    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->staging.reset();
+    return BFQ_OK;
+}
+
+int32_t bfq_index_load(bfq_index* h, const uint8_t* keys, const int64_t* key_off, const uint8_t* vals,
+                       const int64_t* val_off, int64_t n) {
+    if (!h || n < 0 || (n > 0 && (!keys || !key_off || !vals || !val_off))) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    std::string err;
+    if (!h->staging.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
+    return BFQ_OK;
+}
+
+int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* add_key_off, const uint8_t* add_vals,
+                        const int64_t* add_val_off, int64_t n_add, const uint8_t* del_keys, const int64_t* del_key_off,
+                        int64_t n_del) {
+    if (!h || n_add < 0 || n_del < 0) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    for (int64_t i = 0; i < n_add; i++) {
+        sv k((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i]));
+        DecodedKey d;
+        if (!decode_route_key(k, &d)) return fail(BFQ_E_INVALID, "undecodable route key in add set");
+        h->staging.upsert(k, sv((const char*) add_vals + add_val_off[i], (size_t) (add_val_off[i + 1] - add_val_off[i])));
+    }
+    for (int64_t i = 0; i < n_del; i++)
+        h->staging.erase(sv((const char*) del_keys + del_key_off[i], (size_t) (del_key_off[i + 1] - del_key_off[i])));
+    return BFQ_OK;
+}
+
+int32_t bfq_index_commit(bfq_index* h) {
+    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const KVBlob& kv = h->staging.materialize();
+    FlatIndex flat;
+    std::string err;
+    if (!build_flat_index(kv, &flat, &err)) return fail(BFQ_E_INVALID, err);
+    // upload the new snapshot, then swap (matches are serialised by the handle mutex)
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h->d_slots.reserve(flat.slots.size()));
+    CUDA_TRY(h->d_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
+    CUDA_TRY(h->d_segs.reserve(flat.segs.size()));
+    CUDA_TRY(h->d_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
+    CUDA_TRY(h->d_pfxP.reserve(flat.pfx_persistent.size()));
+    CUDA_TRY(h->d_pfxG.reserve(flat.pfx_group.size()));
+    CUDA_TRY(cudaMemcpy(h->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    if (!flat.roots.empty())
+        CUDA_TRY(cudaMemcpy(h->d_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!flat.rkind.empty())
+        CUDA_TRY(cudaMemcpy(h->d_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // the host keeps only what it needs after the upload
+    flat.slots.clear();
+    flat.slots.shrink_to_fit();
+    flat.roots.clear();
+    flat.pfx_persistent.clear();
+    flat.pfx_persistent.shrink_to_fit();
+    flat.pfx_group.clear();
+    flat.pfx_group.shrink_to_fit();
+    h->flat = std::move(flat);
+    h->committed = kv;
+    h->have_snapshot = true;
+    return BFQ_OK;
+}
+
+int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
+    if (!h || !stats) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    const int64_t dev_bytes = (int64_t) (h->d_slots.bytes() + h->d_roots.bytes() + h->d_segs.bytes() + h->d_rkind.bytes() +
+                                         h->d_pfxP.bytes() + h->d_pfxG.bytes());
+    const int64_t v[11] = {h->flat.n_routes, (int64_t) h->flat.tenant_ordinal.size(), h->flat.n_nodes, (int64_t) h->flat.n_slots,
+                           dev_bytes, h->flat.max_nodes_per_depth, h->launches, h->overflow_topics, h->flagged_topics,
+                           h->flat.n_multi, h->flat.n_cont_chunks};
+    for (int32_t i = 0; i < n && i < 11; i++) stats[i] = v[i];
+    return BFQ_OK;
+}
+
+int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms) {
+    if (!h || !ms) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *ms = h->last_kernel_ms;
+    return BFQ_OK;
+}
+
+int32_t bfq_route_lookup(bfq_index* h, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
+                         uint8_t* val_out, int64_t val_cap, int64_t* val_len) {
+    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
+    if (rank < 0 || rank >= h->committed.n()) return fail(BFQ_E_RANGE, "rank out of range");
+    sv k = h->committed.key(rank), v = h->committed.val(rank);
+    if (key_len) *key_len = (int64_t) k.size();
+    if (val_len) *val_len = (int64_t) v.size();
+    if (key_out && (int64_t) k.size() <= key_cap) memcpy(key_out, k.data(), k.size());
+    if (val_out && (int64_t) v.size() <= val_cap) memcpy(val_out, v.data(), v.size());
+    return BFQ_OK;
+}
+
+int32_t bfq_route_kind(bfq_index* h, int64_t rank, int32_t* kind) {
+    if (!h || !kind) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
+    if (rank < 0 || rank >= (int64_t) h->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
+    *kind = h->flat.rkind[(size_t) rank];
+    return BFQ_OK;
+}
+
+int32_t bfq_route_kinds(bfq_index* h, const int64_t* ranks, int64_t n, uint8_t* kinds_out) {
+    if (!h || n < 0 || (n > 0 && (!ranks || !kinds_out))) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
+    for (int64_t i = 0; i < n; i++) {
+        if (ranks[i] < 0 || ranks[i] >= (int64_t) h->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
+        kinds_out[i] = h->flat.rkind[(size_t) ranks[i]];
+    }
+    return BFQ_OK;
+}
+
+int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                  const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n,
+                  const int32_t* max_pfanout, const int32_t* max_gfanout, bfq_result** out) {
+    if (!h || !out || n < 0 || n_tenants < 0) return fail(BFQ_E_INVALID, "bad argument");
+    if (n > 0 && (!topics || !topic_off || !topic_tenant || !tenants || !tenant_off)) return fail(BFQ_E_INVALID, "NULL input");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot) return fail(BFQ_E_STATE, "bfq_match before the first bfq_index_commit");
+    for (int64_t i = 0; i < n; i++)
+        if (topic_tenant[i] < 0 || topic_tenant[i] >= n_tenants) return fail(BFQ_E_RANGE, "topic_tenant out of range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    auto t0 = std::chrono::steady_clock::now();
+    const size_t nn = (size_t) std::max<int64_t>(n, 1);
+    const int64_t blob_b = n ? topic_off[0] : 0, blob_e = n ? topic_off[n] : 0;
+    CUDA_TRY(h->d_topics.reserve((size_t) std::max<int64_t>(blob_e, 1)));
+    CUDA_TRY(h->d_topic_off.reserve(nn + 1));
+    CUDA_TRY(h->d_topic_tenant.reserve(nn));
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_topics.p + blob_b, topics + blob_b, (size_t) (blob_e - blob_b), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_topic_off.p, topic_off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_topic_tenant.p, topic_tenant, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    int32_t rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
+    if (rc != BFQ_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    CoreOut co;
+    rc = match_core(h, h->d_topics.p, h->d_topic_off.p, h->d_topic_tenant.p, n, n_tenants, st, &co);
+    if (rc != BFQ_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    // ---- D2H into the pinned result buffers
+    CUDA_TRY(h->h_span_begin.reserve(nn));
+    CUDA_TRY(h->h_span_count.reserve(nn));
+    CUDA_TRY(h->h_route_count.reserve(nn));
+    CUDA_TRY(h->h_ranges.reserve((size_t) std::max<int64_t>(co.n_ranges, 1)));
+    CUDA_TRY(h->h_throttled.reserve((size_t) std::max<int64_t>(co.n_throttled, 1)));
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p, h->d_span_begin.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->h_span_count.p, h->d_span_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->h_route_count.p, h->d_route_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (co.n_ranges > 0)
+        CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p, h->d_ranges.p, (size_t) co.n_ranges * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+    if (co.n_throttled > 0)
+        CUDA_TRY(cudaMemcpyAsync(h->h_throttled.p, h->d_throttled.p, (size_t) co.n_throttled * sizeof(uint3), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // resolve multi-segment ranges? they are kept as-is; bfq_result_expand resolves them through the host segs copy.
+    // strip internal flag bits from the span counts
+    for (int64_t i = 0; i < n; i++) h->h_span_count.p[i] &= SPAN_COUNT_MASK;
+    if (co.n_throttled > 1) {
+        uint3* th = h->h_throttled.p;
+        std::sort(th, th + co.n_throttled, [](const uint3& a, const uint3& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    }
+    auto* r = new bfq_result();
+    r->owner = h;
+    r->n_topics = n;
+    r->n_ranges = co.n_ranges;
+    r->n_throttled = co.n_throttled;
+    r->span_begin = h->h_span_begin.p;
+    r->span_count = h->h_span_count.p;
+    r->route_count = h->h_route_count.p;
+    r->ranges = reinterpret_cast<const bfq_range*>(h->h_ranges.p);
+    r->throttled = reinterpret_cast<const bfq_throttled*>(h->h_throttled.p);
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
+    r->ms[0] = a;
+    r->ms[1] = b;
+    r->ms[2] = c;
+    r->ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = r;
+    return BFQ_OK;
+}
+
+int64_t bfq_result_num_topics(const bfq_result* r) { return r ? r->n_topics : 0; }
+const uint32_t* bfq_result_span_begin(const bfq_result* r) { return r->span_begin; }
+const uint32_t* bfq_result_span_count(const bfq_result* r) { return r->span_count; }
+const uint32_t* bfq_result_route_count(const bfq_result* r) { return r->route_count; }
+const bfq_range* bfq_result_ranges(const bfq_result* r, int64_t* n_ranges) {
+    if (n_ranges) *n_ranges = r->n_ranges;
+    return r->ranges;
+}
+const bfq_throttled* bfq_result_throttled(const bfq_result* r, int64_t* n_throttled) {
+    if (n_throttled) *n_throttled = r->n_throttled;
+    return r->throttled;
+}
+
+int64_t bfq_result_expand(const bfq_result* r, int64_t* offsets, int64_t* ranks, int64_t rank_cap) {
+    if (!r || !offsets) return BFQ_E_INVALID;
+    const std::vector<uint32_t>& segs = r->owner->flat.segs;
+    int64_t total = 0;
+    int64_t ti = 0;  // cursor into the (topic, rank)-sorted throttled list
+    std::vector<int64_t> tmp;
+    for (int64_t t = 0; t < r->n_topics; t++) {
+        offsets[t] = total;
+        tmp.clear();
+        const uint32_t b = r->span_begin[t], c = r->span_count[t];
+        for (uint32_t j = 0; j < c; j++) {
+            const bfq_range rg = r->ranges[b + j];
+            if (rg.count & RANGE_MULTI) {
+                const uint32_t nseg = segs[2 * (size_t) rg.first];
+                for (uint32_t s = 0; s < nseg; s++) {
+                    const uint32_t f = segs[2 * ((size_t) rg.first + 1 + s)], n = segs[2 * ((size_t) rg.first + 1 + s) + 1];
+                    for (uint32_t x = 0; x < n; x++) tmp.push_back((int64_t) f + x);
+                }
+            } else {
+                for (uint32_t x = 0; x < rg.count; x++) tmp.push_back((int64_t) rg.first + x);
+            }
+        }
+        std::sort(tmp.begin(), tmp.end());
+        while (ti < r->n_throttled && r->throttled[ti].topic < (uint32_t) t) ti++;
+        for (int64_t x : tmp) {
+            while (ti < r->n_throttled && r->throttled[ti].topic == (uint32_t) t && (int64_t) r->throttled[ti].rank < x) ti++;
+            if (ti < r->n_throttled && r->throttled[ti].topic == (uint32_t) t && (int64_t) r->throttled[ti].rank == x) continue;
+            if (ranks && total < rank_cap) ranks[total] = x;
+            total++;
+        }
+    }
+    offsets[r->n_topics] = total;
+    return total;
+}
+
+int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n) {
+    if (!r || !ms) return fail(BFQ_E_INVALID, "bad argument");
+    for (int32_t i = 0; i < n && i < 4; i++) ms[i] = r->ms[i];
+    return BFQ_OK;
+}
+void bfq_result_free(bfq_result* r) { delete r; }
+
+int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                         const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant, int64_t n,
+                         const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream, bfq_device_result* out) {
+    if (!h || !out || n < 0 || n_tenants < 0) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot) return fail(BFQ_E_STATE, "bfq_match_device before the first bfq_index_commit");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    int32_t rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
+    if (rc != BFQ_OK) return rc;
+    CoreOut co;
+    rc = match_core(h, d_topics, d_topic_off, d_topic_tenant, n, n_tenants, st, &co);
+    if (rc != BFQ_OK) return rc;
+    out->d_span_begin = h->d_span_begin.p;
+    out->d_span_count = h->d_span_count.p;
+    out->d_route_count = h->d_route_count.p;
+    out->d_ranges = reinterpret_cast<const bfq_range*>(h->d_ranges.p);
+    out->d_throttled = reinterpret_cast<const bfq_throttled*>(h->d_throttled.p);
+    out->n_ranges = co.n_ranges;
+    out->n_throttled = co.n_throttled;
+    out->n_routes = -1;
+    out->n_overflow_topics = co.n_overflow;
+    out->n_flagged_topics = co.n_flagged;
+    out->n_launches = co.n_launches;
+    return BFQ_OK;
+}
+
+int32_t bfq_expand_device(bfq_index*, int64_t, int64_t*, int64_t*, int64_t, void*, int64_t*) {
+    return fail(BFQ_E_STATE, "bfq_expand_device: not available in this build");
+}
+
+// ---------------------------------------------------------------- codec exports
+int64_t bfq_receiver_url(int32_t sub_broker_id, const uint8_t* receiver_id, int64_t rn, const uint8_t* deliverer_key,
+                         int64_t dn, uint8_t* out, int64_t cap) {
+    return emit_bytes(make_receiver_url(sub_broker_id, sv((const char*) receiver_id, (size_t) rn), sv((const char*) deliverer_key, (size_t) dn)), out, cap);
+}
+int64_t bfq_route_key(const uint8_t* tenant, int64_t tn, const uint8_t* tf, int64_t fn, const uint8_t* url, int64_t un,
+                      uint8_t* out, int64_t cap) {
+    return emit_bytes(make_route_key(sv((const char*) tenant, (size_t) tn), sv((const char*) tf, (size_t) fn), sv((const char*) url, (size_t) un)), out, cap);
+}
+int64_t bfq_tenant_begin_key(const uint8_t* tenant, int64_t tn, uint8_t* out, int64_t cap) {
+    return emit_bytes(make_tenant_begin_key(sv((const char*) tenant, (size_t) tn)), out, cap);
+}
+int32_t bfq_is_valid_topic(const uint8_t* topic, int64_t n, int32_t a, int32_t b, int32_t c) {
+    return is_valid_topic(sv((const char*) topic, (size_t) n), a, b, c) ? 1 : 0;
+}
+int32_t bfq_is_valid_topic_filter(const uint8_t* tf, int64_t n, int32_t a, int32_t b, int32_t c) {
+    return is_valid_topic_filter(sv((const char*) tf, (size_t) n), a, b, c) ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// match_kernels.cuh — launch parameters of the forward-match kernels (see match_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trie_layout.h"
+
+namespace bfq {
+
+// device counters, one block of uint64
+enum : int {
+    CTR_RANGES = 0,      // cursor into out_ranges (total ranges requested, may exceed capacity)
+    CTR_OVERFLOW = 1,    // topics deferred to the tier-2 kernel
+    CTR_FLAGGED = 2,     // topics whose matched persistent / group route counts may exceed their caps
+    CTR_THROTTLED = 3,   // cursor into the throttled list
+    CTR_ROUTES = 4,      // total matched routes (before caps)
+    CTR_ERROR = 5,       // tier-2 scratch exhausted (cannot happen with correctly sized scratch)
+    CTR_COUNT = 8,
+};
+
+constexpr uint32_t SPAN_FLAGGED = 0x80000000u;   // in span_count: caps must be applied to this topic
+constexpr uint32_t SPAN_OVERFLOW = 0x40000000u;  // in span_count: deferred to tier 2 (never visible to callers)
+constexpr uint32_t SPAN_COUNT_MASK = 0x3FFFFFFFu;
+
+struct MatchParams {
+    // index snapshot
+    const Slot* slots;
+    const Slot* roots;
+    uint32_t n_slots;
+    // topic batch
+    const uint8_t* topics;          // blob
+    const int64_t* topic_off;       // [n+1]
+    const int32_t* topic_tenant;    // [n] index into the per-call tenant tables
+    const int32_t* tenant_root;     // [n_tenants] root ordinal or -1 (tenant has no routes)
+    const int32_t* max_pfanout;     // [n_tenants]
+    const int32_t* max_gfanout;     // [n_tenants]
+    int64_t n_topics;
+    // tier 2: list of topic indices to process (nullptr => all topics 0..n_topics)
+    const uint32_t* work_list;
+    int64_t n_work;
+    // outputs
+    uint32_t* span_begin;           // [n]
+    uint32_t* span_count;           // [n]  count | SPAN_FLAGGED
+    uint32_t* route_count;          // [n]
+    uint2* ranges;                  // [ranges_cap] {first, count | RANGE_MULTI}
+    uint64_t ranges_cap;
+    uint32_t* overflow_list;        // [n] topic indices deferred to tier 2
+    uint32_t* flagged_list;         // [n] topic indices needing caps
+    unsigned long long* counters;   // [CTR_COUNT]
+    // tier-2 scratch (global memory frontier / range staging), per warp
+    uint2* scratch;
+    uint64_t scratch_frontier_cap;  // entries per frontier buffer
+    uint64_t scratch_ranges_cap;    // entries of range staging
+};
+
+struct CapsParams {
+    const uint32_t* flagged_list;
+    int64_t n_flagged;
+    const int32_t* topic_tenant;
+    const int32_t* max_pfanout;
+    const int32_t* max_gfanout;
+    const uint32_t* span_begin;
+    const uint32_t* span_count;
+    const uint2* ranges;
+    const uint32_t* segs;
+    const uint8_t* rkind;
+    const uint32_t* pfx_persistent;
+    const uint32_t* pfx_group;
+    uint3* throttled;               // {topic, rank, kind}
+    uint64_t throttled_cap;
+    uint32_t* kept_count;           // [n] (optional) routes surviving per flagged topic
+    unsigned long long* counters;
+};
+
+struct ExpandParams {
+    int64_t n_topics;
+    const uint32_t* span_begin;
+    const uint32_t* span_count;
+    const uint2* ranges;
+    const uint32_t* segs;
+    const int64_t* offsets;         // [n+1] exclusive scan of kept counts
+    int64_t* ranks;
+    int64_t rank_cap;
+    // throttled routes sorted by (topic, rank) for removal
+    const uint3* throttled;
+    int64_t n_throttled;
+    const uint32_t* thr_topic_begin; // [n+1] index into throttled per topic (only valid if n_throttled > 0)
+};
+
+void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStream_t stream);
+void launch_caps(const CapsParams& p, cudaStream_t stream);
+int match_kernel_smem_bytes();
+
+}  // namespace bfq

@@ -1,0 +1,78 @@
+// trie_layout.h — HBM layout of the forward index, shared by the host builder and the kernels.
+//
+// The per-tenant filter tries are flattened into ONE open-addressing hash table of 64-byte slots,
+// keyed by (parent node id, level token). A slot is the child NODE RECORD itself, so following an
+// exact edge costs a single 64 B (one DRAM burst, two 32 B sectors) random access and no separate
+// node fetch. Node id == slot index; tenant roots live in a small side array (id = ROOT_BASE + ordinal).
+//
+//   word  0      parent node id              (EMPTY_PARENT = free slot)
+//   word  1      token length in bytes       (LEN_PLUS for the '+' child, LEN_CONT|j for the j-th
+//                                             24-byte continuation chunk of a token longer than 24 B)
+//   words 2..7   token bytes, zero padded    (exact compare: no hash collisions by construction)
+//   word  8      slot of the '+' child       (NONE if absent)
+//   word  9      flags                       (HAS_EXACT: node has >= 1 exact child; *_MULTI see below)
+//   words 10,11  own routes  [first rank, count)   routes of the filter ending at this node
+//   words 12,13  '#' routes  [first rank, count)   routes of the filter "<this node>/#" ('#' is always the
+//                                                   last level, so the '#' child is inlined into its parent)
+//   word  14     own  caps counters: lo16 persistent (subBrokerId==1) routes, hi16 group routes, saturating
+//   word  15     '#'  caps counters, same packing
+//
+// A rank is the position of a route in the committed KV order (the reference's RocksDB order), so a
+// filter's routes are one contiguous run [first, first+count) — except in the rare interleaving case
+// (filters with an empty level after a common prefix) where the run is split; then the
+// *_MULTI flag is set, `count` still holds the total number of routes and `first` indexes the segment
+// table: segs[first] = {n_segments, total}, followed by n_segments {first rank, count} pairs.
+#pragma once
+#include <stdint.h>
+
+namespace bfq {
+
+struct alignas(64) Slot {
+    uint32_t w[16];
+};
+static_assert(sizeof(Slot) == 64, "slot must be one 64-byte burst");
+
+enum : uint32_t {
+    W_PARENT = 0, W_LEN = 1, W_TOK = 2, W_PLUS = 8, W_FLAGS = 9,
+    W_OWN_FIRST = 10, W_OWN_COUNT = 11, W_HASH_FIRST = 12, W_HASH_COUNT = 13, W_OWN_CAPS = 14, W_HASH_CAPS = 15,
+};
+constexpr uint32_t EMPTY_PARENT = 0xFFFFFFFFu;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t LEN_PLUS = 0xFFFFFFFFu;
+constexpr uint32_t LEN_CONT = 0x80000000u;       // | chunk index
+constexpr uint32_t ROOT_BASE = 0x80000000u;      // node id of tenant root = ROOT_BASE + tenant ordinal
+constexpr uint32_t FLAG_HAS_EXACT = 1u, FLAG_OWN_MULTI = 2u, FLAG_HASH_MULTI = 4u;
+constexpr uint32_t TOKEN_WORDS = 6;              // 24 inline token bytes per edge
+constexpr uint32_t TOKEN_BYTES = 24;
+constexpr uint32_t RANGE_MULTI = 0x80000000u;    // marker in an emitted range's count word
+
+// Hash of an edge key. tokh covers (length word, 6 token words); the parent id is mixed in afterwards so
+// the per-level token hash is computed once per topic level and reused for every frontier node.
+#if defined(__CUDACC__)
+#define BFQ_HD __host__ __device__ __forceinline__
+#else
+#define BFQ_HD inline
+#endif
+
+BFQ_HD uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+BFQ_HD uint64_t token_hash(uint32_t lenw, const uint32_t* k /*[6]*/) {
+    uint64_t h = (uint64_t) lenw * 0x9E3779B97F4A7C15ull;
+    h += (uint64_t) k[0] * 0xA24BAED4963EE407ull;
+    h += (uint64_t) k[1] * 0x9FB21C651E98DF25ull;
+    h += (uint64_t) k[2] * 0xD6E8FEB86659FD93ull;
+    h += (uint64_t) k[3] * 0xCA5A826395121157ull;
+    h += (uint64_t) k[4] * 0x8CB92BA72F3D8DD7ull;
+    h += (uint64_t) k[5] * 0xE7037ED1A0B428DBull;
+    return h;
+}
+BFQ_HD uint32_t home_slot(uint64_t tokh, uint32_t parent, uint32_t n_slots) {
+    uint64_t h = fmix64(tokh + (uint64_t) parent * 0xC2B2AE3D27D4EB4Full);
+    return (uint32_t) (((h >> 32) * (uint64_t) n_slots) >> 32);
+}
+
+}  // namespace bfq

@@ -1,0 +1,194 @@
+/* bfq_gpumatch.h — C-ABI of the B200 topic-filter matcher (libbfq_gpumatch.so).
+ *
+ * This is the drop-in boundary: everything a JNI shim needs to put the CUDA matcher behind
+ * apache/bifromq's dist-worker / retain-store co-processors without touching their Java API.
+ * Nothing native exists in the reference today (it is 100% Java), so each entry point cites the
+ * Java interface or call site it replaces. Paths are relative to the reference root; DW/ =
+ * bifromq-dist/bifromq-dist-worker/src/main/java/org/apache/bifromq/dist/worker/, DWS/ =
+ * bifromq-dist/bifromq-dist-worker-schema/src/main/java/org/apache/bifromq/dist/worker/schema/,
+ * RS/ = bifromq-retain/bifromq-retain-store/src/main/java/org/apache/bifromq/retain/store/,
+ * U/ = bifromq-util/src/main/java/org/apache/bifromq/util/.
+ *
+ * Conventions: every function returns 0 (BFQ_OK) or a negative BFQ_E_* code; bfq_last_error()
+ * gives the text. All buffers are caller-owned plain memory (host unless the name says device);
+ * strings are (blob, int64 offsets[n+1]) pairs, never NUL-terminated. A handle may be used from
+ * several threads, calls are serialised internally. There is no CPU fallback: every match runs
+ * on the GPU and the library fails (BFQ_E_CUDA) if no device is usable.
+ */
+#ifndef BFQ_GPUMATCH_H
+#define BFQ_GPUMATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFQ_OK 0
+#define BFQ_E_INVALID (-1)   /* bad argument (unsorted keys, undecodable route key, ...) */
+#define BFQ_E_CUDA (-2)      /* CUDA runtime / device error */
+#define BFQ_E_NOMEM (-3)
+#define BFQ_E_STATE (-4)     /* e.g. match before the first commit */
+#define BFQ_E_RANGE (-5)     /* index out of range */
+
+typedef struct bfq_index bfq_index;     /* forward index: topic filters (routes) of many tenants  */
+typedef struct bfq_result bfq_result;   /* result of one bfq_match call                            */
+typedef struct bfq_rindex bfq_rindex;   /* inverse index: topics, matched BY filters (retain)      */
+typedef struct bfq_rresult bfq_rresult;
+
+/* text of the last error raised on this thread */
+const char* bfq_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward index life cycle. One bfq_index per dist-worker KV range == one DistWorkerCoProc
+ * (DW/DistWorkerCoProc.java:105-125). It replaces the per-tenant TenantRouteMatcher instances
+ * (DW/cache/TenantRouteCacheFactory.java:67-71) and their RocksDB merge-join.
+ * ---------------------------------------------------------------------------------------------- */
+int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out);
+void bfq_index_destroy(bfq_index* h);
+
+/* Drop all staged routes. Called from DistWorkerCoProc.reset(Boundary) (DW/DistWorkerCoProc.java:283-291)
+ * before re-loading the range. */
+int32_t bfq_index_reset(bfq_index* h);
+
+/* Bulk-stage raw KV pairs exactly as stored by the reference: key = route key
+ * (DWS/KVSchemaUtil.java:91-130), value = 8-byte BE incarnation (normal) or RouteGroup proto (shared).
+ * Keys must be strictly ascending in unsigned byte order (a KV range scan is). Decoding is native
+ * (replaces DWS/cache/RouteDetailCache.java:53-109 on the load path). */
+int32_t bfq_index_load(bfq_index* h, const uint8_t* keys, const int64_t* key_off, const uint8_t* vals,
+                       const int64_t* val_off, int64_t n);
+
+/* Incremental feed from the post-persist Supplier of DistWorkerCoProc.mutate
+ * (DW/DistWorkerCoProc.java:188-209; batchAddRoute :304-413, batchRemoveRoute :415-513):
+ * upsert n_add pairs, delete n_del keys (any order). */
+int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* add_key_off, const uint8_t* add_vals,
+                        const int64_t* add_val_off, int64_t n_add, const uint8_t* del_keys, const int64_t* del_key_off,
+                        int64_t n_del);
+
+/* Publish the staged state as a new immutable device snapshot (matches always see a whole snapshot). */
+int32_t bfq_index_commit(bfq_index* h);
+
+/* stats[k], k < n: 0 routes, 1 tenants, 2 trie nodes, 3 hash-table slots, 4 device bytes, 5 max nodes per
+ * depth, 6 kernel launches so far, 7 overflow (tier-2) topics so far, 8 cap-flagged topics so far,
+ * 9 multi-segment filters, 10 long-token chunks */
+int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n);
+/* device time of the tier-1 match kernel of the latest match call on this handle, measured with CUDA events
+ * recorded on the launching stream around the launch (for roofline accounting) */
+int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms);
+
+/* Map a route rank (position in the committed KV order) back to its stored key/value so the Java side
+ * re-hydrates Matching objects with its own KVSchemaUtil.buildMatchRoute (DWS/KVSchemaUtil.java:73-79).
+ * Lengths are returned even if the capacities are too small (nothing is copied then). */
+int32_t bfq_route_lookup(bfq_index* h, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
+                         uint8_t* val_out, int64_t val_cap, int64_t* val_len);
+/* per-rank route kind: 0 normal, 1 normal persistent (subBrokerId == 1), 2 group (shared subscription) */
+int32_t bfq_route_kind(bfq_index* h, int64_t rank, int32_t* kind);
+int32_t bfq_route_kinds(bfq_index* h, const int64_t* ranks, int64_t n, uint8_t* kinds_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward match == ITenantRouteMatcher.matchAll(Set<String> topics, int maxPersistentFanout,
+ * int maxGroupFanout) (DW/cache/ITenantRouteMatcher.java:28-38; implementation replaced:
+ * DW/cache/TenantRouteMatcher.java:68-161 + caps of DW/cache/MatchedRoutes.java:87-141),
+ * batched over tenants. Topic i belongs to tenant topic_tenant[i] (index into the tenants list);
+ * max_pfanout/max_gfanout are per tenant (Setting.MaxPersistentFanout / MaxGroupFanout).
+ * Host buffers in, host result out (H2D + kernels + D2H inside the call).
+ * ---------------------------------------------------------------------------------------------- */
+int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                  const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n_topics,
+                  const int32_t* max_pfanout, const int32_t* max_gfanout, bfq_result** out);
+
+/* Result layout (all arrays live as long as the result):
+ *   span_begin[i], span_count[i]   topic i's matched route RANGES are ranges[span_begin[i] ... +span_count[i])
+ *   ranges[j] = {first rank, count} a run of consecutive route ranks (one matched filter's routes)
+ *   route_count[i]                 routes matched by topic i before caps
+ *   throttled[k] = {topic, rank, kind} routes dropped by the fan-out caps, kind 1 = PersistentFanoutThrottled,
+ *                                  2 = GroupFanoutThrottled (MatchedRoutes.java:95-100,128-133); the caller
+ *                                  emits the events. Surviving routes of topic i = its ranges minus these. */
+typedef struct { uint32_t first; uint32_t count; } bfq_range;
+typedef struct { uint32_t topic; uint32_t rank; uint32_t kind; } bfq_throttled;
+int64_t bfq_result_num_topics(const bfq_result* r);
+const uint32_t* bfq_result_span_begin(const bfq_result* r);
+const uint32_t* bfq_result_span_count(const bfq_result* r);
+const uint32_t* bfq_result_route_count(const bfq_result* r);
+const bfq_range* bfq_result_ranges(const bfq_result* r, int64_t* n_ranges);
+const bfq_throttled* bfq_result_throttled(const bfq_result* r, int64_t* n_throttled);
+/* Convenience: flatten to CSR of surviving ranks, ascending per topic. offsets[n_topics+1]; returns the
+ * total, copies only if it fits rank_cap. */
+int64_t bfq_result_expand(const bfq_result* r, int64_t* offsets, int64_t* ranks, int64_t rank_cap);
+/* timings of the call in milliseconds: 0 h2d, 1 kernels, 2 d2h, 3 total */
+int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n);
+void bfq_result_free(bfq_result* r);
+
+/* Same match with the topic batch already resident in device memory and the result left there
+ * (used by bench.py's kernel-only leg and by callers that pipeline batches). d_* are device pointers,
+ * stream is a cudaStream_t (NULL = default stream). The call enqueues the kernels, then synchronises
+ * the stream once to read the counters. The device result buffers belong to the index and stay valid
+ * until the next match on it. */
+typedef struct {
+    const uint32_t* d_span_begin;   /* [n_topics] */
+    const uint32_t* d_span_count;   /* [n_topics] */
+    const uint32_t* d_route_count;  /* [n_topics] */
+    const bfq_range* d_ranges;      /* [n_ranges] */
+    const bfq_throttled* d_throttled; /* [n_throttled] */
+    int64_t n_ranges, n_throttled, n_routes;
+    int64_t n_overflow_topics, n_flagged_topics, n_launches;
+} bfq_device_result;
+int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                         const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
+                         int64_t n_topics, const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream,
+                         bfq_device_result* out);
+/* Flatten a device result into device CSR (d_offsets[n_topics+1] int64, d_ranks int64 capacity rank_cap)
+ * on the same stream; caps are applied (throttled routes removed). Returns total via *n_ranks. */
+int32_t bfq_expand_device(bfq_index* h, int64_t n_topics, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap,
+                          void* stream, int64_t* n_ranks);
+
+/* ------------------------------------------------------------------------------------------------
+ * Route key codec + tokeniser, native restatement of DWS/KVSchemaUtil.java:56-130 and
+ * U/TopicUtil.java:42-163,206-225 (exported so the Java side / tests can cross-check bytes).
+ * Each returns the produced length (or BFQ_E_*), copying only if it fits cap.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t bfq_receiver_url(int32_t sub_broker_id, const uint8_t* receiver_id, int64_t rn, const uint8_t* deliverer_key,
+                         int64_t dn, uint8_t* out, int64_t cap);
+/* mqtt_topic_filter may carry a $share/<g>/ or $oshare/<g>/ prefix (=> toGroupRouteKey, receiver_url ignored) */
+int64_t bfq_route_key(const uint8_t* tenant, int64_t tn, const uint8_t* mqtt_topic_filter, int64_t fn,
+                      const uint8_t* receiver_url, int64_t un, uint8_t* out, int64_t cap);
+int64_t bfq_tenant_begin_key(const uint8_t* tenant, int64_t tn, uint8_t* out, int64_t cap);
+int32_t bfq_is_valid_topic(const uint8_t* topic, int64_t n, int32_t max_level_length, int32_t max_level, int32_t max_length);
+int32_t bfq_is_valid_topic_filter(const uint8_t* tf, int64_t n, int32_t max_level_length, int32_t max_level, int32_t max_length);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inverse index == IRetainTopicIndex (RS/index/IRetainTopicIndex.java:27-35; implementation replaced:
+ * RS/index/RetainTopicIndex.java:35-144 over U/index/TopicLevelTrie.java:190-249) and, with
+ * tenant == NULL levels, DW/TopicIndex.java:39-156. Topics are staged with add/remove, published with
+ * commit, and matched BY a batch of topic filters.
+ * ---------------------------------------------------------------------------------------------- */
+int32_t bfq_rindex_create(int32_t device_ordinal, bfq_rindex** out);
+void bfq_rindex_destroy(bfq_rindex* h);
+int32_t bfq_rindex_reset(bfq_rindex* h);
+/* add n topics; topic i belongs to tenant topic_tenant[i] of the tenants list; returns via ids_out[i] the
+ * stable topic id (>= 0) used in match results. Adding an existing (tenant, topic) returns its id. */
+int32_t bfq_rindex_add(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                       const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n,
+                       int64_t* ids_out);
+int32_t bfq_rindex_remove(bfq_rindex* h, const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t n);
+int32_t bfq_rindex_commit(bfq_rindex* h);
+/* topic id -> (tenant, topic) strings */
+int32_t bfq_rindex_lookup(bfq_rindex* h, int64_t id, uint8_t* tenant_out, int64_t tenant_cap, int64_t* tenant_len,
+                          uint8_t* topic_out, int64_t topic_cap, int64_t* topic_len);
+/* match n filters; filter i is scoped to tenant filter_tenant[i]; limit[i] < 0 = unlimited, else at most
+ * limit[i] ids are returned for filter i (RS/RetainStoreCoProc.java:167-190 stops after `limit` messages;
+ * which ones is unspecified there too — it iterates a HashSet). */
+int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                   const uint8_t* filters, const int64_t* filter_off, const int32_t* filter_tenant, int64_t n_filters,
+                   const int64_t* limit, bfq_rresult** out);
+int64_t bfq_rresult_num_filters(const bfq_rresult* r);
+const int64_t* bfq_rresult_offsets(const bfq_rresult* r);            /* [n_filters+1] */
+const int64_t* bfq_rresult_ids(const bfq_rresult* r, int64_t* n);    /* topic ids, ascending per filter */
+const int64_t* bfq_rresult_total_matches(const bfq_rresult* r);      /* [n_filters] matches before the limit */
+int32_t bfq_rresult_timings(const bfq_rresult* r, double* ms, int32_t n);
+void bfq_rresult_free(bfq_rresult* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFQ_GPUMATCH_H */

@@ -1,0 +1,427 @@
+"""GPU parity tests of the forward match (publish topic -> routes): the CUDA path, called through the C-ABI,
+against the CPU oracle on the same bytes. Bit-exact: identical sets of route ranks per topic, identical
+throttle events. Cases named after the reference tests they transcribe
+(bifromq-dist/bifromq-dist-worker/src/test/java/org/apache/bifromq/dist/worker/cache/TenantRouteMatcherTest.java).
+"""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+TENANT_ID, OTHER_TENANT = "tenantA", "tenantB"
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bifromq_b200
+    from bifromq_b200 import schema, workload
+    bifromq_b200.load_library()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.pkg, ns.schema, ns.workload = bifromq_b200, schema, workload
+    return ns
+
+
+class Events:
+    def __init__(self):
+        self.events = []
+
+    def report(self, e):
+        self.events.append(e)
+
+
+def make_index(B, pairs):
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load_pairs(pairs)
+    idx.commit()
+    return idx
+
+
+def normal(B, pairs, tenant, tf, broker, receiver, deliverer, inc):
+    url = B.schema.receiver_url(broker, receiver, deliverer)
+    pairs.append((B.schema.route_key(tenant, tf, url), B.schema.incarnation_bytes(inc)))
+    return B.schema.NormalMatching(tenant, tf, url, inc)
+
+
+def group(B, pairs, tenant, tf, grp, members, ordered=False):
+    full = ("$oshare/" if ordered else "$share/") + grp + "/" + tf
+    pairs.append((B.schema.route_key(tenant, full), B.schema.route_group_bytes(members)))
+    return B.schema.GroupMatching(tenant, full, tuple(sorted(members.items())), ordered)
+
+
+# ------------------------------------------------------------------ TenantRouteMatcherTest.java:89-342
+def test_match_all_returns_empty_when_no_tenant_data(B):  # :89-111
+    pairs = []
+    normal(B, pairs, OTHER_TENANT, "sensors/+/temp", 1, "receiverX", "delivererX", 1)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    topics = {"sensors/device1/temp", "sensors/device1/humidity"}
+    matched = matcher.match_all(topics, 10, 10)
+    assert set(matched) == topics
+    for routes in matched.values():
+        assert routes.routes() == set()
+        assert routes.persistent_fanout() == 0 and routes.group_fanout() == 0
+    assert ev.events == []
+
+
+def test_match_all_across_multiple_topics(B):  # :113-146
+    pairs = []
+    temp = normal(B, pairs, TENANT_ID, "sensors/+/temp", 1, "receiverA", "delivererA", 1)
+    hum = normal(B, pairs, TENANT_ID, "sensors/+/humidity", 1, "receiverB", "delivererB", 2)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    topics = {"sensors/device1/temp", "sensors/device1/humidity", "sensors/device2/temp"}
+    matched = matcher.match_all(topics, 10, 10)
+    assert set(matched) == topics
+    assert temp in matched["sensors/device1/temp"].routes()
+    assert temp in matched["sensors/device2/temp"].routes()
+    assert hum in matched["sensors/device1/humidity"].routes()
+    for t in topics:
+        assert matched[t].persistent_fanout() == 1 and matched[t].group_fanout() == 0
+    assert ev.events == []
+
+
+def test_reuse_cached_filter_matches_for_repeated_subscriptions(B):  # :148-175
+    pairs = []
+    first = normal(B, pairs, TENANT_ID, "devices/+/status", 1, "receiverA", "delivererA", 1)
+    second = normal(B, pairs, TENANT_ID, "devices/+/status", 2, "receiverB", "delivererB", 1)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    matched = matcher.match_all({"devices/a/status", "devices/b/status"}, 5, 5)
+    for routes in matched.values():
+        assert routes.routes() == {first, second}
+        assert routes.persistent_fanout() == 1  # only subBrokerId == 1 counts as persistent
+        assert routes.group_fanout() == 0
+    assert ev.events == []
+
+
+def test_match_all_with_shared_subscription(B):  # :177-204
+    pairs = []
+    members = {B.schema.receiver_url(1, "receiverA", "delivererA"): 10, B.schema.receiver_url(2, "receiverB", "delivererB"): 11}
+    g = group(B, pairs, TENANT_ID, "alerts/+/+/temperature", "groupAlpha", members)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    matched = matcher.match_all({"alerts/site1/device1/temperature", "alerts/site1/device2/temperature"}, 10, 10)
+    for routes in matched.values():
+        assert g in routes.routes()
+        assert routes.persistent_fanout() == 0 and routes.group_fanout() == 1
+    assert ev.events == []
+
+
+def test_skip_non_matching_routes(B):  # :206-236 (the probe/seek counters have no GPU analogue)
+    pairs = []
+    for i in range(21):
+        normal(B, pairs, TENANT_ID, "invalid/%d" % i, 1, "noise%d" % i, "deliverer%d" % i, i)
+    valid = normal(B, pairs, TENANT_ID, "metrics/+/cpu", 1, "receiverA", "delivererA", 1)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    result = matcher.match_all({"metrics/server1/cpu"}, 10, 10)["metrics/server1/cpu"]
+    assert result.routes() == {valid}
+    assert result.persistent_fanout() == 1 and result.group_fanout() == 0
+    assert ev.events == []
+
+
+def test_isolate_routes_by_tenant(B):  # :238-268
+    pairs = []
+    mine = normal(B, pairs, TENANT_ID, "devices/+/signal", 1, "receiverA", "delivererA", 1)
+    other = normal(B, pairs, OTHER_TENANT, "devices/+/signal", 1, "receiverB", "delivererB", 1)
+    idx = make_index(B, pairs)
+    ev = Events()
+    r = B.pkg.GpuTenantRouteMatcher(TENANT_ID, idx, ev).match_all({"devices/a/signal"}, 10, 10)
+    assert r["devices/a/signal"].routes() == {mine}
+    r = B.pkg.GpuTenantRouteMatcher(OTHER_TENANT, idx, ev).match_all({"devices/a/signal"}, 10, 10)
+    assert r["devices/a/signal"].routes() == {other}
+    assert ev.events == []
+
+
+def test_trigger_persistent_fanout_throttling(B):  # :270-301
+    pairs = []
+    normal(B, pairs, TENANT_ID, "alarms/+/critical", 1, "receiverA", "delivererA", 1)
+    second = normal(B, pairs, TENANT_ID, "alarms/+/critical", 1, "receiverB", "delivererB", 2)
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    routes = matcher.match_all({"alarms/device1/critical"}, 1, 10)["alarms/device1/critical"]
+    assert routes.persistent_fanout() == 1 and routes.group_fanout() == 0
+    assert len(routes.routes()) == 1
+    assert len(ev.events) == 1
+    e = ev.events[0]
+    assert isinstance(e, B.pkg.PersistentFanoutThrottled)
+    assert (e.tenant_id, e.topic, e.mqtt_topic_filter, e.max_count) == (TENANT_ID, "alarms/device1/critical", second.mqtt_topic_filter, 1)
+
+
+def test_trigger_group_fanout_throttling(B):  # :303-342
+    pairs = []
+    first = group(B, pairs, TENANT_ID, "jobs/+/progress", "groupA", {B.schema.receiver_url(1, "receiverA", "delivererA"): 1})
+    group(B, pairs, TENANT_ID, "jobs/+/progress", "groupB", {B.schema.receiver_url(1, "receiverB", "delivererB"): 1})
+    ev = Events()
+    matcher = B.pkg.GpuTenantRouteMatcher(TENANT_ID, make_index(B, pairs), ev)
+    routes = matcher.match_all({"jobs/job1/progress"}, 10, 1)["jobs/job1/progress"]
+    assert routes.group_fanout() == 1
+    assert sum(1 for m in routes.routes() if isinstance(m, B.schema.GroupMatching)) == 1
+    assert len(ev.events) == 1
+    e = ev.events[0]
+    assert isinstance(e, B.pkg.GroupFanoutThrottled)
+    # "second comes before first in lexicographical order by bucketing key"
+    assert (e.tenant_id, e.topic, e.mqtt_topic_filter, e.max_count) == (TENANT_ID, "jobs/job1/progress", first.mqtt_topic_filter, 1)
+
+
+# ------------------------------------------------------------------ expansion-set fixtures (Fixtures.java:31-105)
+LOCAL_FIXTURES = {
+    "a": ["#", "+", "+/#", "a", "a/#"],
+    "$sys/a": ["$sys/#", "$sys/+", "$sys/+/#", "$sys/a", "$sys/a/#"],
+    "/": ["/", "//#", "/#", "/+", "/+/#", "#", "+/", "+//#", "+/#", "+/+", "+/+/#"],
+    "a/b": ["#", "+/#", "+/+", "+/+/#", "+/b", "+/b/#", "a/#", "a/+", "a/+/#", "a/b", "a/b/#"],
+}
+
+
+def test_fixture_expansion_sets(B):
+    # one route per filter over a vocabulary that covers every fixture filter plus non-matching neighbours
+    import itertools
+    vocab = ["", "a", "b", "$sys", "+", "#"]
+    filters = set()
+    for n in range(1, 4):
+        for combo in itertools.product(vocab, repeat=n):
+            if "#" in combo[:-1]:
+                continue
+            filters.add("/".join(combo))
+    filters.discard("")
+    filters = sorted(filters)
+    pairs = []
+    for i, f in enumerate(filters):
+        normal(B, pairs, "t", f, 0, "r%d" % i, "d", 1)
+    idx = make_index(B, pairs)
+    matcher = B.pkg.GpuTenantRouteMatcher("t", idx)
+    res = matcher.match_all(list(LOCAL_FIXTURES), 100, 100)
+    for topic, want in LOCAL_FIXTURES.items():
+        got = sorted(m.mqtt_topic_filter for m in res[topic].routes())
+        assert got == sorted(want), topic
+
+
+# ------------------------------------------------------------------ randomized cross-checks vs the oracle
+def oracle_kv_from_pairs(pairs):
+    kv = O.KV()
+    for k, v in pairs:
+        kv.put(k, v)
+    kv.freeze()
+    return kv
+
+
+def compare_with_oracle(B, idx, kv, tenants, topics, tt, max_p, max_g, mode=O.MODE_TRIE):
+    nt = len(tenants)
+    res = idx.match_topics(tenants, topics, tt, [max_p] * nt, [max_g] * nt)
+    offsets, ranks = res.expand()
+    want = kv.match_batch(tenants, topics, tt, max_p, max_g, mode)
+    assert offsets.tolist() == want.offsets.tolist()
+    assert ranks.tolist() == want.ranks.tolist()
+    got_events = sorted((int(k), int(t), int(r)) for t, r, k in res.throttled.tolist())
+    assert got_events == sorted((k, t, r) for k, t, r, _ in want.events)
+    # route_count is the pre-cap match count
+    uncapped = kv.match_batch(tenants, topics, tt, 2 ** 31 - 1, 2 ** 31 - 1, mode)
+    assert res.route_count.tolist() == np.diff(uncapped.offsets).tolist()
+    res.close()
+    return want
+
+
+def random_pairs(B, rng, n_filters, vocab, depth, empties=True):
+    def level(i, allow_empty):
+        r = rng.random()
+        if r < 0.08 and allow_empty:
+            return ""
+        if r < 0.15 and i == 0:
+            return "$" + rng.choice(vocab)
+        return rng.choice(vocab)
+
+    def filt():
+        n = rng.randint(1, depth)
+        lv = []
+        for i in range(n):
+            r = rng.random()
+            if r < 0.25:
+                lv.append("+")
+            elif r < 0.35 and i == n - 1:
+                lv.append("#")
+            else:
+                lv.append(level(i, empties))
+        return "/".join(lv)
+    tenants = ["tA", "tB", "t"]
+    pairs = {}
+    for _ in range(n_filters):
+        tenant = rng.choice(tenants)
+        f = filt()
+        if rng.random() < 0.15:
+            members = {B.schema.receiver_url(rng.choice([0, 1]), "m%d" % rng.randint(0, 5), "d"): rng.randint(1, 9)
+                       for _ in range(rng.randint(1, 3))}
+            full = rng.choice(["$share/", "$oshare/"]) + "g%d" % rng.randint(0, 3) + "/" + f
+            pairs[B.schema.route_key(tenant, full)] = B.schema.route_group_bytes(members)
+        else:
+            for _ in range(rng.choice([1, 1, 1, 2, 5])):
+                url = B.schema.receiver_url(rng.choice([0, 1, 1, 2]), "r%d" % rng.randint(0, 400), "d%d" % rng.randint(0, 3))
+                pairs[B.schema.route_key(tenant, f, url)] = B.schema.incarnation_bytes(rng.randint(0, 99))
+    topics = ["/".join(level(i, empties) for i in range(rng.randint(1, depth))) for _ in range(300)]
+    tt = np.array([rng.randrange(len(tenants)) for _ in topics], dtype=np.int32)
+    return sorted(pairs.items()), tenants, topics, tt
+
+
+@pytest.mark.parametrize("seed,caps", [(1, (2 ** 31 - 1, 100)), (2, (2, 1)), (3, (0, 0)), (4, (4, 4)), (5, (1, 2 ** 31 - 1))])
+def test_random_small_vocab_vs_oracle(B, seed, caps):
+    rng = random.Random(seed)
+    pairs, tenants, topics, tt = random_pairs(B, rng, 600, ["a", "b", "c", "dd", "e1"], 5)
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    want = compare_with_oracle(B, idx, kv, tenants, topics, tt, caps[0], caps[1], O.MODE_TRIE)
+    # and against the brute-force predicate (independent of any trie)
+    brute = kv.match_batch(tenants, topics, tt, caps[0], caps[1], O.MODE_BRUTE)
+    assert brute.route_sets() == want.route_sets()
+    assert sum(len(r) for r in want.route_sets()) > 0
+    assert idx.stats()["multi_segment_filters"] >= 0
+
+
+def test_reference_literal_algorithm_agrees_without_empty_levels(B):
+    rng = random.Random(9)
+    pairs, tenants, topics, tt = random_pairs(B, rng, 500, ["a", "b", "c", "dd"], 4, empties=False)
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    want = compare_with_oracle(B, idx, kv, tenants, topics, tt, 3, 2, O.MODE_REFERENCE)
+    assert want.stats["backward_seeks"] == 0
+
+
+def test_multi_segment_filter_interleaving(B):
+    # keys of "a//b" sort inside the bucket range of "a": the routes of "a" are not one contiguous rank run
+    pairs = []
+    for i in range(300):
+        normal(B, pairs, "t", "a", i % 2, "r%d" % i, "d", 1)
+    for i in range(60):
+        normal(B, pairs, "t", "a//b", 1, "x%d" % i, "d", 1)
+    for i in range(20):
+        normal(B, pairs, "t", "a/", 0, "y%d" % i, "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    assert idx.stats()["multi_segment_filters"] >= 1
+    kv = oracle_kv_from_pairs(pairs)
+    topics = ["a", "a//b", "a/", "b"]
+    for caps in [(2 ** 31 - 1, 2 ** 31 - 1), (7, 3), (0, 0)]:
+        compare_with_oracle(B, idx, kv, ["t"], topics, np.zeros(4, np.int32), caps[0], caps[1], O.MODE_BRUTE)
+
+
+def test_long_levels_and_long_topics(B):
+    # levels longer than the 24 inline token bytes (continuation chunks) and topics longer than the 256 B stage
+    l25, l24, l48, l49, l100 = "x" * 25, "y" * 24, "z" * 48, "w" * 49, "v" * 100
+    filters = [l25, l24, l48, l49, l100, l25 + "/" + l48, "+/" + l48, l100 + "/#", l49 + "/+", "x" * 24 + "/b", "x" * 26,
+               "/".join(["seg%02d" % i for i in range(40)]), "/".join(["seg%02d" % i for i in range(39)]) + "/#",
+               "你好" * 9, "你好" * 8]
+    pairs = []
+    for i, f in enumerate(filters):
+        normal(B, pairs, "t", f, 0, "r%d" % i, "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    assert idx.stats()["long_token_chunks"] > 0
+    kv = oracle_kv_from_pairs(pairs)
+    topics = [l25, l24, l48, l49, l100, l25 + "/" + l48, l24 + "/" + l48, l100 + "/a/b", l49 + "/q", "x" * 26, "x" * 27,
+              "/".join(["seg%02d" % i for i in range(40)]), "/".join(["seg%02d" % i for i in range(41)]), "你好" * 9, "你好" * 8,
+              "x" * 24, "x" * 23]
+    want = compare_with_oracle(B, idx, kv, ["t"], topics, np.zeros(len(topics), np.int32), 10, 10, O.MODE_BRUTE)
+    assert all(len(r) >= 1 for r in want.route_sets()[:12])
+
+
+def test_frontier_overflow_goes_through_tier2(B):
+    # every {a,+}^8 filter matches a/a/a/a/a/a/a/a: 256 ranges and a frontier of up to 128 nodes -> tier 2
+    import itertools
+    pairs = []
+    i = 0
+    for combo in itertools.product(["a", "+"], repeat=8):
+        normal(B, pairs, "t", "/".join(combo), i % 2, "r%d" % i, "d", 1)
+        i += 1
+    for n in range(1, 8):
+        normal(B, pairs, "t", "/".join(["a"] * n) + "/#", 1, "h%d" % n, "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    topics = ["/".join(["a"] * 8), "/".join(["a"] * 7 + ["b"]), "/".join(["b"] * 8), "a/a"]
+    before = idx.stats()["overflow_topics"]
+    want = compare_with_oracle(B, idx, kv, ["t"], topics, np.zeros(len(topics), np.int32), 2 ** 31 - 1, 2 ** 31 - 1, O.MODE_BRUTE)
+    assert len(want.route_sets()[0]) == 256 + 7
+    assert idx.stats()["overflow_topics"] > before
+    compare_with_oracle(B, idx, kv, ["t"], topics, np.zeros(len(topics), np.int32), 5, 0, O.MODE_BRUTE)
+
+
+def test_apply_and_commit_incremental(B):
+    pairs = []
+    a = normal(B, pairs, "t", "a/+", 1, "r1", "d", 1)
+    b = normal(B, pairs, "t", "a/b", 0, "r2", "d", 2)
+    idx = make_index(B, pairs)
+    m = B.pkg.GpuTenantRouteMatcher("t", idx)
+    assert m.match_all(["a/b"], 10, 10)["a/b"].routes() == {a, b}
+    extra = []
+    c = normal(B, extra, "t", "a/#", 1, "r3", "d", 3)
+    idx.apply(adds=extra, dels=[pairs[0][0]])
+    # not visible until commit (matches see whole snapshots)
+    assert m.match_all(["a/b"], 10, 10)["a/b"].routes() == {a, b}
+    idx.commit()
+    assert m.match_all(["a/b"], 10, 10)["a/b"].routes() == {b, c}
+    idx.reset()
+    idx.commit()
+    assert m.match_all(["a/b"], 10, 10)["a/b"].routes() == set()
+
+
+def test_load_rejects_unsorted_and_undecodable(B):
+    idx = B.pkg.GpuRouteIndex(0)
+    k1 = B.schema.route_key("t", "b", B.schema.receiver_url(0, "r", "d"))
+    k2 = B.schema.route_key("t", "a", B.schema.receiver_url(0, "r", "d"))
+    from bifromq_b200 import _native as N
+    kb, ko = N.as_blob([k1, k2])
+    vb, vo = N.as_blob([b"\0" * 8, b"\0" * 8])
+    with pytest.raises(B.pkg.NativeError):
+        idx.load(kb, ko, vb, vo)
+    idx.reset()
+    kb, ko = N.as_blob([b"\x00\x00\x01tgarbage"])
+    vb, vo = N.as_blob([b"\0" * 8])
+    idx.load(kb, ko, vb, vo)
+    with pytest.raises(B.pkg.NativeError):
+        idx.commit()
+
+
+def test_empty_batch_and_unknown_tenant(B):
+    pairs = []
+    normal(B, pairs, "t", "#", 0, "r", "d", 1)
+    idx = make_index(B, pairs)
+    res = idx.match_topics(["t"], [])
+    assert res.n_topics == 0
+    res.close()
+    res = idx.match_topics(["nobody", "t"], ["a", "a", "$sys", ""], np.array([0, 1, 1, 1], np.int32))
+    off, ranks = res.expand()
+    assert off.tolist() == [0, 0, 1, 1, 2]
+    res.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs (scaled) vs the oracle
+@pytest.mark.parametrize("config,scale", [("C1", 1.0), ("C2", 0.02), ("C3", 0.005), ("C4", 0.005)])
+@pytest.mark.parametrize("caps", [(2 ** 31 - 1, 100), (4, 4)])
+def test_baseline_configs_vs_oracle(B, config, scale, caps):
+    w = B.workload.Workload(config, scale=scale)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    kv.freeze()
+    assert len(kv) == w.n_routes
+    tenants = w.tenants
+    nt = len(tenants)
+    res = idx.match(tenants, w.topics, w.topic_off, w.topic_tenant, [caps[0]] * nt, [caps[1]] * nt)
+    offsets, ranks = res.expand()
+    tb, toff = O.blob(tenants)
+    want = kv.match_blobs(tb, toff, w.topics, w.topic_off, np.ascontiguousarray(w.topic_tenant), w.n_topics, caps[0], caps[1],
+                          O.MODE_TRIE, False, 8)
+    assert offsets.tolist() == want.offsets.tolist()
+    assert ranks.tolist() == want.ranks.tolist()
+    got_events = sorted((int(k), int(t), int(r)) for t, r, k in res.throttled.tolist())
+    assert got_events == sorted((k, t, r) for k, t, r, _ in want.events)
+    hit = float((np.diff(offsets) > 0).mean())
+    assert hit > 0.5, "workload should mostly hit (got %.2f)" % hit
+    res.close()
