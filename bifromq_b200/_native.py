@@ -41,6 +41,7 @@ _SIGNATURES = {
     "bfq_index_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]),
     "bfq_index_commit": (_i32, [_vp]),
     "bfq_index_stats": (_i32, [_vp, _vp, _i32]),
+    "bfq_host_build_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32]),
     "bfq_index_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_double)]),
     "bfq_route_lookup": (_i32, [_vp, _i64, _vp, _i64, C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]),
     "bfq_route_kind": (_i32, [_vp, _i64, C.POINTER(_i32)]),

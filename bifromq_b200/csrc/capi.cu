@@ -395,6 +395,31 @@ int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
     return BFQ_OK;
 }
 
+int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const uint8_t* vals, const int64_t* val_off,
+                             int64_t n, int64_t* stats, int32_t n_stats) {
+    if (n < 0 || !stats) return fail(BFQ_E_INVALID, "bad argument");
+    Staging st;
+    std::string err;
+    if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
+    FlatIndex flat;
+    if (!build_flat_index(st.materialize(), &flat, &err)) return fail(BFQ_E_INVALID, err);
+    // self-check of the table: every non-empty slot is reachable from its home slot by linear probing
+    int64_t used = 0;
+    for (uint32_t s = 0; s < flat.n_slots; s++) {
+        const Slot& sl = flat.slots[s];
+        if (sl.w[W_PARENT] == EMPTY_PARENT) continue;
+        used++;
+        uint32_t h0 = home_slot(token_hash(sl.w[W_LEN], &sl.w[W_TOK]), sl.w[W_PARENT], flat.n_slots);
+        for (uint32_t q = h0; q != s; q = q + 1 == flat.n_slots ? 0 : q + 1)
+            if (flat.slots[q].w[W_PARENT] == EMPTY_PARENT) return fail(BFQ_E_STATE, "hash table probe chain broken");
+    }
+    if (used + (int64_t) flat.roots.size() != flat.n_nodes) return fail(BFQ_E_STATE, "node count mismatch");
+    const int64_t v[8] = {flat.n_routes, (int64_t) flat.tenant_ordinal.size(), flat.n_nodes, (int64_t) flat.n_slots,
+                          flat.max_nodes_per_depth, flat.max_tenant_nodes, flat.n_multi, flat.n_cont_chunks};
+    for (int32_t i = 0; i < n_stats && i < 8; i++) stats[i] = v[i];
+    return BFQ_OK;
+}
+
 int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms) {
     if (!h || !ms) return fail(BFQ_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> g(h->mu);

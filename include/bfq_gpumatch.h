@@ -76,6 +76,12 @@ int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n);
  * recorded on the launching stream around the launch (for roofline accounting) */
 int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms);
 
+/* Host-only diagnostic: run the index builder on a sorted KV snapshot without touching a device and report
+ * stats[0..7] = routes, tenants, trie nodes, hash slots, max nodes per depth, max nodes per tenant,
+ * multi-segment filters, long-token chunks (used by CPU tests and to time the build). */
+int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const uint8_t* vals, const int64_t* val_off,
+                             int64_t n, int64_t* stats, int32_t n_stats);
+
 /* Map a route rank (position in the committed KV order) back to its stored key/value so the Java side
  * re-hydrates Matching objects with its own KVSchemaUtil.buildMatchRoute (DWS/KVSchemaUtil.java:73-79).
  * Lengths are returned even if the capacities are too small (nothing is copied then). */
