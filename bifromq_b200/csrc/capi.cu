@@ -15,13 +15,17 @@
 
 using namespace bfq;
 
-namespace {
-
-thread_local std::string g_err;
-int32_t fail(int32_t code, const std::string& msg) {
-    g_err = msg;
+namespace bfq {
+thread_local std::string g_last_error;
+int32_t set_error(int32_t code, const std::string& msg) {
+    g_last_error = msg;
     return code;
 }
+}  // namespace bfq
+
+namespace {
+
+int32_t fail(int32_t code, const std::string& msg) { return bfq::set_error(code, msg); }
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
@@ -286,7 +290,7 @@ int64_t emit_bytes(const std::string& s, uint8_t* out, int64_t cap) {
 
 extern "C" {
 
-const char* bfq_last_error(void) { return g_err.c_str(); }
+const char* bfq_last_error(void) { return bfq::g_last_error.c_str(); }
 
 int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
     if (!out) return fail(BFQ_E_INVALID, "out is NULL");

@@ -51,6 +51,9 @@ std::string make_tenant_begin_key(sv tenant);                                   
 std::string make_route_key(sv tenant, sv mqtt_topic_filter, sv receiver_url);              // :108-125
 std::string prefix_upper_bound(sv key, bool* open_end);
 
+// thread-local error text behind bfq_last_error() (defined in capi.cu)
+int32_t set_error(int32_t code, const std::string& msg);
+
 bool is_valid_topic(sv topic, int max_level_length, int max_level, int max_length);
 bool is_valid_topic_filter(sv tf, int max_level_length, int max_level, int max_length);
 
