@@ -104,7 +104,7 @@ struct bfq_index {
     DevBuf<uint8_t> d_topics;
     DevBuf<int64_t> d_topic_off;
     DevBuf<int32_t> d_topic_tenant, d_tenant_tab;   // tenant_tab = root | maxP | maxG, 3 x n_tenants
-    DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept;
+    DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept, d_defer;
     DevBuf<uint2> d_ranges, d_scratch;
     DevBuf<uint3> d_throttled;
     DevBuf<unsigned long long> d_counters;
@@ -115,7 +115,7 @@ struct bfq_index {
     PinBuf<uint2> h_ranges;
     PinBuf<uint3> h_throttled;
     // statistics
-    int64_t launches = 0, overflow_topics = 0, flagged_topics = 0;
+    int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0;
     // last device result (for bfq_expand_device)
     int64_t last_n_topics = 0;
 
@@ -124,7 +124,7 @@ struct bfq_index {
         d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release();
         d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
-        d_flagged.release(); d_kept.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
+        d_flagged.release(); d_kept.release(); d_defer.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
         d_counters.release(); h_counters.release(); h_tenant_tab.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -137,7 +137,7 @@ namespace {
 
 // Shared core of bfq_match / bfq_match_device: topics are on the device; runs tier 1, tier 2 and caps.
 struct CoreOut {
-    int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0;
+    int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0, n_deferred = 0;
 };
 
 int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
@@ -168,6 +168,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     CUDA_TRY(h->d_overflow.reserve(nn));
     CUDA_TRY(h->d_flagged.reserve(nn));
     CUDA_TRY(h->d_kept.reserve(nn));
+    CUDA_TRY(h->d_defer.reserve(nn));
     CUDA_TRY(h->d_counters.reserve(CTR_COUNT));
     CUDA_TRY(h->h_counters.reserve(CTR_COUNT));
     if (h->d_ranges.cap == 0) CUDA_TRY(h->d_ranges.reserve(std::max<size_t>(1 << 20, 4 * nn)));
@@ -188,6 +189,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     p.span_count = h->d_span_count.p;
     p.route_count = h->d_route_count.p;
     p.overflow_list = h->d_overflow.p;
+    p.defer_list = h->d_defer.p;
     p.flagged_list = h->d_flagged.p;
     p.counters = h->d_counters.p;
 
@@ -199,15 +201,21 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
         p.work_list = nullptr;
         p.n_work = 0;
         if (n > 0) {
+            // tier 0 (one lane per topic) over the whole batch, then tier 1 (one warp per topic) over whatever tier 0
+            // deferred — its count is read on the device, so both launches go out back to back
             CUDA_TRY(cudaEventRecord(h->evk[0], stream));
-            launch_match(p, false, 0, stream);
+            launch_match_lanes(p, stream);
             CUDA_TRY(cudaEventRecord(h->evk[1], stream));
-            out->n_launches++;
+            p.work_list = h->d_defer.p;
+            p.n_work = -1;
+            launch_match(p, false, 0, stream);
+            out->n_launches += 2;
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         out->n_overflow = (int64_t) hc[CTR_OVERFLOW];
+        out->n_deferred = (int64_t) hc[CTR_DEFER];
         if (n > 0) {
             float kms = 0;
             cudaEventElapsedTime(&kms, h->evk[0], h->evk[1]);
@@ -276,6 +284,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     }
     h->launches += out->n_launches;
     h->overflow_topics += out->n_overflow;
+    h->deferred_topics += out->n_deferred;
     h->flagged_topics += out->n_flagged;
     h->last_n_topics = n;
     return BFQ_OK;
@@ -392,10 +401,10 @@ int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
     std::lock_guard<std::mutex> g(h->mu);
     const int64_t dev_bytes = (int64_t) (h->d_slots.bytes() + h->d_roots.bytes() + h->d_segs.bytes() + h->d_rkind.bytes() +
                                          h->d_pfxP.bytes() + h->d_pfxG.bytes());
-    const int64_t v[11] = {h->flat.n_routes, (int64_t) h->flat.tenant_ordinal.size(), h->flat.n_nodes, (int64_t) h->flat.n_slots,
+    const int64_t v[12] = {h->flat.n_routes, (int64_t) h->flat.tenant_ordinal.size(), h->flat.n_nodes, (int64_t) h->flat.n_slots,
                            dev_bytes, h->flat.max_nodes_per_depth, h->launches, h->overflow_topics, h->flagged_topics,
-                           h->flat.n_multi, h->flat.n_cont_chunks};
-    for (int32_t i = 0; i < n && i < 11; i++) stats[i] = v[i];
+                           h->flat.n_multi, h->flat.n_cont_chunks, h->deferred_topics};
+    for (int32_t i = 0; i < n && i < 12; i++) stats[i] = v[i];
     return BFQ_OK;
 }
 

@@ -272,9 +272,249 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
         const uint32_t capF = (uint32_t) min((uint64_t) 0x3FFFFFFFull, p.scratch_frontier_cap);
         const uint32_t capR = (uint32_t) min((uint64_t) SPAN_COUNT_MASK, p.scratch_ranges_cap);
         for (int64_t it = gw; it < p.n_work; it += nw) match_one<true>(p, ws, p.work_list[it], lane, fr_a, fr_b, rg, capF, capR);
+    } else if (p.work_list) {
+        // tier 1 behind tier 0: the number of deferred topics is read from the device counter (no host round trip)
+        const int64_t n_work = p.n_work >= 0 ? p.n_work : (int64_t) p.counters[CTR_DEFER];
+        for (int64_t it = gw; it < n_work; it += nw)
+            match_one<false>(p, ws, p.work_list[it], lane, ws.fr[0], ws.fr[1], ws.rg, FR_CAP, RG_CAP);
     } else {
         for (int64_t it = gw; it < p.n_topics; it += nw)
             match_one<false>(p, ws, (uint32_t) it, lane, ws.fr[0], ws.fr[1], ws.rg, FR_CAP, RG_CAP);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ tier 0
+// ONE LANE PER TOPIC. The warp-per-topic walk above leaves most lanes idle when the frontier is a handful of
+// nodes (the common case: ~4 per level on BASELINE config C4) and spends ~2100 warp instructions per topic
+// (ncu, profiles/r1_v1_*). Here a warp takes 32 consecutive topics:
+//   * their bytes are one contiguous run of the blob -> staged into shared memory with one coalesced copy;
+//   * each lane finds its own '/' offsets once (<= 16 levels) and then walks the trie depth-first. A node has
+//     at most two continuations per level (exact child, '+' child), so the DFS needs ONE pending entry per
+//     level: a 16-entry per-lane array plus a bitmask, never a growing frontier;
+//   * per step a lane builds the 24-byte key of its current level from shared memory (aligned words + funnel
+//     shift), issues the exact-child probe and the '+' child load together (eight independent LDG.128), emits the
+//     discovered ranges into its own shared staging row;
+//   * when all 32 topics are done the warp does one prefix sum + ONE atomicAdd for the whole batch and copies
+//     the ranges out.
+// Anything that does not fit the bounded buffers (topic > 255 B, > 16 levels, a level > 24 B, > L_RG ranges,
+// batch bytes beyond the stage) is handed, whole, to the warp-per-topic tier through defer_list.
+constexpr int L_WARPS = 4;
+constexpr int L_SEG = 3072;
+constexpr int L_RG = 12;
+constexpr int L_MAXLV = 16;
+
+struct LaneSmem {
+    uint32_t seg[(L_SEG + 64) / 4];       // staged topic bytes (word array: aligned LDS.32 + funnel shift)
+    uint8_t lv[32][L_MAXLV + 4];          // per lane: start offset of each level (relative to the topic), +sentinel
+    uint2 rg[L_RG][32];                   // per lane range staging, lane-minor (bank-conflict free)
+    uint2 stk[L_MAXLV + 1][32];           // pending '+' branch per level: {node id, plus | has_exact << 31}
+};
+
+__global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
+    __shared__ LaneSmem sm[L_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    LaneSmem& ws = sm[wid];
+    const uint8_t* segb = reinterpret_cast<const uint8_t*>(ws.seg);
+    const int64_t gw = (int64_t) blockIdx.x * L_WARPS + wid, nw = (int64_t) gridDim.x * L_WARPS;
+    const int64_t n_batches = (p.n_topics + 31) / 32;
+    const uint32_t lt_mask = (1u << lane) - 1;
+
+    for (int64_t batch = gw; batch < n_batches; batch += nw) {
+        const int64_t t64 = batch * 32 + lane;
+        const bool valid = t64 < p.n_topics;
+        const uint32_t t = (uint32_t) t64;
+        const int64_t my_off = valid ? p.topic_off[t64] : 0;
+        const int64_t my_end = valid ? p.topic_off[t64 + 1] : 0;
+        const int64_t off0 = __shfl_sync(FULL, my_off, 0);
+        const int nvalid = __popc(__ballot_sync(FULL, valid));
+        const int64_t seg_end = __shfl_sync(FULL, my_end, nvalid - 1);
+        const int seg_len = (int) min((int64_t) L_SEG, seg_end - off0);
+        __syncwarp();
+        {   // coalesced stage of the batch's bytes
+            const uint8_t* src = p.topics + off0;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(ws.seg);
+            for (int i = lane; i < seg_len; i += 32) dst[i] = src[i];
+        }
+        __syncwarp();
+        const int rel = (int) (my_off - off0);
+        const int len = (int) (my_end - my_off);
+        bool ok = valid && (my_end - off0) <= L_SEG && len <= 255;
+
+        // ---- per-lane level table
+        int nlev = 1;
+        {
+            int maxlen = ok ? len : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+            ws.lv[lane][0] = 0;
+            int last_start = 0;
+            bool too_long = false;
+            for (int i = 0; i < maxlen; i++) {
+                if (ok && i < len && segb[rel + i] == '/') {
+                    if (i - last_start > (int) TOKEN_BYTES) too_long = true;
+                    if (nlev <= L_MAXLV) ws.lv[lane][nlev] = (uint8_t) (i + 1);
+                    nlev++;
+                    last_start = i + 1;
+                }
+            }
+            if (len - last_start > (int) TOKEN_BYTES) too_long = true;
+            if (nlev > L_MAXLV || too_long) ok = false;
+            if (ok) ws.lv[lane][nlev] = (uint8_t) 0;   // sentinel slot, the end of the last level is `len` (handled below)
+        }
+
+        const int tenant = valid ? p.topic_tenant[t] : 0;
+        const int root_ord = valid ? p.tenant_root[tenant] : -1;
+        uint32_t n_rg = 0, acc_r = 0;
+        uint64_t acc_p = 0, acc_g = 0;
+        bool overflow = false;
+        auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
+            if (n_rg < (uint32_t) L_RG) ws.rg[n_rg][lane] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
+            else overflow = true;
+            n_rg++;
+            acc_r += count;
+            acc_p += caps_value(caps & 0xFFFFu);
+            acc_g += caps_value(caps >> 16);
+        };
+
+        // ---- DFS state
+        bool have = false;
+        uint32_t node = 0, plusf = NONE31;
+        int level = 0;
+        uint32_t pending = 0;
+        if (ok && root_ord >= 0) {
+            uint32_t rw[16];
+            load_slot(p.roots + root_ord, rw);
+            const bool sys = len > 0 && segb[rel] == '$';
+            if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
+            const uint32_t plus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
+            const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
+            if (has_exact || plus != NONE31) {
+                have = true;
+                node = ROOT_BASE + (uint32_t) root_ord;
+                plusf = plus | (has_exact ? 0x80000000u : 0u);
+            }
+        }
+        while (__any_sync(FULL, have)) {
+            if (have) {
+                const int s = ws.lv[lane][level];
+                const bool last = level == nlev - 1;
+                const int e = last ? len : (int) ws.lv[lane][level + 1] - 1;
+                const int tlen = e - s;
+                // '+' child first (independent of the token)
+                const uint32_t plus = plusf & NONE31;
+                const bool has_plus = plus != NONE31;
+                uint32_t pw[16];
+                if (has_plus) load_slot(p.slots + plus, pw);
+                bool alive = plusf >> 31;
+                uint32_t cw[16], cid = 0;
+                if (alive) {
+                    // key words of [rel+s, rel+e): aligned words + funnel shift, bytes past the token zeroed
+                    const int a = rel + s;
+                    const uint32_t* wp = ws.seg + (a >> 2);
+                    const int sh = (a & 3) * 8;
+                    uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4], x5 = wp[5], x6 = wp[6];
+                    uint32_t k[6];
+                    k[0] = __funnelshift_r(x0, x1, sh); k[1] = __funnelshift_r(x1, x2, sh); k[2] = __funnelshift_r(x2, x3, sh);
+                    k[3] = __funnelshift_r(x3, x4, sh); k[4] = __funnelshift_r(x4, x5, sh); k[5] = __funnelshift_r(x5, x6, sh);
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        const int vb = tlen - 4 * j;   // valid bytes in word j
+                        k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
+                    }
+                    const uint64_t tokh = token_hash((uint32_t) tlen, k);
+                    alive = probe(p.slots, p.n_slots, node, (uint32_t) tlen, k, tokh, cw, cid);
+                }
+                bool push_c = false, push_p = false;
+                if (alive) {
+                    if (cw[W_HASH_COUNT] > 0) emit(cw[W_HASH_FIRST], cw[W_HASH_COUNT], cw[W_FLAGS] & FLAG_HASH_MULTI, cw[W_HASH_CAPS]);
+                    if (last) {
+                        if (cw[W_OWN_COUNT] > 0) emit(cw[W_OWN_FIRST], cw[W_OWN_COUNT], cw[W_FLAGS] & FLAG_OWN_MULTI, cw[W_OWN_CAPS]);
+                    } else {
+                        push_c = (cw[W_FLAGS] & FLAG_HAS_EXACT) || cw[W_PLUS] != NONE;
+                    }
+                }
+                if (has_plus) {
+                    if (pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_FLAGS] & FLAG_HASH_MULTI, pw[W_HASH_CAPS]);
+                    if (last) {
+                        if (pw[W_OWN_COUNT] > 0) emit(pw[W_OWN_FIRST], pw[W_OWN_COUNT], pw[W_FLAGS] & FLAG_OWN_MULTI, pw[W_OWN_CAPS]);
+                    } else {
+                        push_p = (pw[W_FLAGS] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE;
+                    }
+                }
+                const uint32_t c_plusf = (cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS]) | ((cw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
+                const uint32_t p_plusf = (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) | ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
+                if (overflow) {
+                    have = false;
+                } else if (push_c) {
+                    if (push_p) {   // park the '+' branch of this level, continue down the exact branch
+                        ws.stk[level + 1][lane] = make_uint2(plus, p_plusf);
+                        pending |= 1u << (level + 1);
+                    }
+                    node = cid;
+                    plusf = c_plusf;
+                    level++;
+                } else if (push_p) {
+                    node = plus;
+                    plusf = p_plusf;
+                    level++;
+                } else if (pending) {
+                    const int l = 31 - __clz(pending);
+                    pending &= ~(1u << l);
+                    const uint2 it = ws.stk[l][lane];
+                    node = it.x;
+                    plusf = it.y;
+                    level = l;
+                } else {
+                    have = false;
+                }
+            }
+        }
+
+        // ---- batch epilogue: defer what did not fit, flush the rest with one atomicAdd per warp
+        const bool defer = valid && (!ok || overflow);
+        const bool done = valid && !defer;
+        const unsigned md = __ballot_sync(FULL, defer);
+        if (md) {
+            unsigned long long dbase = 0;
+            if (lane == 0) dbase = atomicAdd(&p.counters[CTR_DEFER], (unsigned long long) __popc(md));
+            dbase = __shfl_sync(FULL, dbase, 0);
+            if (defer) {
+                p.defer_list[dbase + __popc(md & lt_mask)] = t;
+                p.span_begin[t] = 0;
+                p.span_count[t] = SPAN_OVERFLOW;
+                p.route_count[t] = 0;
+            }
+        }
+        const uint32_t cnt = done ? n_rg : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        unsigned long long base = 0;
+        if (total > 0) {
+            if (lane == 0) base = atomicAdd(&p.counters[CTR_RANGES], (unsigned long long) total);
+            base = __shfl_sync(FULL, base, 0);
+        }
+        if (done) {
+            const unsigned long long mine = base + (incl - cnt);
+            if (base + total <= p.ranges_cap)
+                for (uint32_t j = 0; j < cnt; j++) p.ranges[mine + j] = ws.rg[j][lane];
+            const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
+            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint64_t) (maxP < 0 ? 0 : maxP);
+            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint64_t) (maxG < 0 ? 0 : maxG);
+            const bool flagged = flag_p || flag_g;
+            p.span_begin[t] = (uint32_t) mine;
+            p.span_count[t] = cnt | (flagged ? SPAN_FLAGGED : 0u);
+            p.route_count[t] = acc_r;
+            if (flagged) {
+                const unsigned long long idx = atomicAdd(&p.counters[CTR_FLAGGED], 1ull);
+                p.flagged_list[idx] = t;
+            }
+        }
     }
 }
 
@@ -368,9 +608,26 @@ void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStrea
     }
     // persistent grid: a whole number of waves (SM count x resident CTAs per SM), grid-stride over topics
     int64_t ctas = (int64_t) sms * ctas_per_sm;
-    const int64_t need = (p.n_topics + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int64_t items = p.work_list ? (p.n_work >= 0 ? p.n_work : p.n_topics) : p.n_topics;
+    const int64_t need = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (need < ctas) ctas = need < 1 ? 1 : need;
     match_topics_kernel<false><<<(unsigned) ctas, WARPS_PER_CTA * 32, 0, stream>>>(p);
+}
+
+void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, match_topics_lane_kernel, L_WARPS * 32, 0);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    // persistent grid (SM count x resident CTAs), each warp strides over batches of 32 consecutive topics
+    int64_t ctas = (int64_t) sms * ctas_per_sm;
+    const int64_t need = ((p.n_topics + 31) / 32 + L_WARPS - 1) / L_WARPS;
+    if (need < ctas) ctas = need < 1 ? 1 : need;
+    match_topics_lane_kernel<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
 }
 
 void launch_caps(const CapsParams& p, cudaStream_t stream) {

@@ -15,6 +15,7 @@ enum : int {
     CTR_THROTTLED = 3,   // cursor into the throttled list
     CTR_ROUTES = 4,      // total matched routes (before caps)
     CTR_ERROR = 5,       // tier-2 scratch exhausted (cannot happen with correctly sized scratch)
+    CTR_DEFER = 6,       // topics the lane-per-topic tier handed to the warp-per-topic tier
     CTR_COUNT = 8,
 };
 
@@ -35,7 +36,7 @@ struct MatchParams {
     const int32_t* max_pfanout;     // [n_tenants]
     const int32_t* max_gfanout;     // [n_tenants]
     int64_t n_topics;
-    // tier 2: list of topic indices to process (nullptr => all topics 0..n_topics)
+    // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
     int64_t n_work;
     // outputs
@@ -45,6 +46,7 @@ struct MatchParams {
     uint2* ranges;                  // [ranges_cap] {first, count | RANGE_MULTI}
     uint64_t ranges_cap;
     uint32_t* overflow_list;        // [n] topic indices deferred to tier 2
+    uint32_t* defer_list;           // [n] topic indices deferred from tier 0 to tier 1
     uint32_t* flagged_list;         // [n] topic indices needing caps
     unsigned long long* counters;   // [CTR_COUNT]
     // tier-2 scratch (global memory frontier / range staging), per warp
@@ -87,6 +89,8 @@ struct ExpandParams {
     const uint32_t* thr_topic_begin; // [n+1] index into throttled per topic (only valid if n_throttled > 0)
 };
 
+// tier 0: one LANE per topic (DFS, bounded smem); tier 1: one WARP per topic; tier 2: warp per topic, global scratch
+void launch_match_lanes(const MatchParams& p, cudaStream_t stream);
 void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStream_t stream);
 void launch_caps(const CapsParams& p, cudaStream_t stream);
 int match_kernel_smem_bytes();

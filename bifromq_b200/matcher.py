@@ -115,10 +115,10 @@ class GpuRouteIndex:
         N.check(N.lib.bfq_index_commit(self._h))
 
     def stats(self):
-        s = np.zeros(11, np.int64)
-        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 11))
+        s = np.zeros(12, np.int64)
+        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 12))
         names = ["routes", "tenants", "nodes", "slots", "device_bytes", "max_nodes_per_depth", "launches",
-                 "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks"]
+                 "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks", "deferred_topics"]
         return dict(zip(names, s.tolist()))
 
     def last_kernel_ms(self):

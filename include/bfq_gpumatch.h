@@ -70,7 +70,8 @@ int32_t bfq_index_commit(bfq_index* h);
 
 /* stats[k], k < n: 0 routes, 1 tenants, 2 trie nodes, 3 hash-table slots, 4 device bytes, 5 max nodes per
  * depth, 6 kernel launches so far, 7 overflow (tier-2) topics so far, 8 cap-flagged topics so far,
- * 9 multi-segment filters, 10 long-token chunks */
+ * 9 multi-segment filters, 10 long-token chunks, 11 topics handed from the lane-per-topic tier to the
+ * warp-per-topic tier so far */
 int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n);
 /* device time of the tier-1 match kernel of the latest match call on this handle, measured with CUDA events
  * recorded on the launching stream around the launch (for roofline accounting) */
