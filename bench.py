@@ -302,6 +302,7 @@ def main():
         res = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy())
         routes_per_batch = int(res.route_count.astype(np.int64).sum())
         res.close()
+        stats = idx.stats()
         cpu_base, roof = None, None
         k_ms = float(np.mean(kernel_ms))
         if not args.no_cpu_baseline:
@@ -318,7 +319,7 @@ def main():
             achieved = per_topic * n / (k_ms / 1000.0) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                    "kernel": "match_topics_kernel<false>", "kernel_ms": k_ms, "alg_bytes_per_topic": per_topic,
+                    "kernel": "match_topics_lane_kernel (tier 0, one lane per topic)", "kernel_ms": k_ms, "alg_bytes_per_topic": per_topic,
                     "alg_counters_per_topic": {"V": st["V"] / ns, "P": st["P"] / ns, "ranges": st["ranges"] / ns, "R": st["R"] / ns},
                     "note": "algorithmic bytes per topic measured by the oracle on the cpu_baseline sample"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -105,7 +105,9 @@ struct bfq_index {
     DevBuf<int64_t> d_topic_off;
     DevBuf<int32_t> d_topic_tenant, d_tenant_tab;   // tenant_tab = root | maxP | maxG, 3 x n_tenants
     DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept, d_defer;
-    DevBuf<uint2> d_ranges, d_scratch;
+    DevBuf<uint2> d_ranges, d_scratch, d_ranges_c;
+    DevBuf<uint8_t> d_scan_tmp;
+    DevBuf<uint32_t> d_cnt, d_new_begin;
     DevBuf<uint3> d_throttled;
     DevBuf<unsigned long long> d_counters;
     PinBuf<unsigned long long> h_counters;
@@ -124,7 +126,7 @@ struct bfq_index {
         d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release();
         d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
-        d_flagged.release(); d_kept.release(); d_defer.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
+        d_flagged.release(); d_kept.release(); d_defer.release(); d_ranges_c.release(); d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
         d_counters.release(); h_counters.release(); h_tenant_tab.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -171,7 +173,10 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     CUDA_TRY(h->d_defer.reserve(nn));
     CUDA_TRY(h->d_counters.reserve(CTR_COUNT));
     CUDA_TRY(h->h_counters.reserve(CTR_COUNT));
-    if (h->d_ranges.cap == 0) CUDA_TRY(h->d_ranges.reserve(std::max<size_t>(1 << 20, 4 * nn)));
+    // ranges[0, dyn_base): tier-0 inline slots; ranges[dyn_base, cap): cursor-allocated region of tiers 1 and 2
+    const uint64_t dyn_base = (uint64_t) n * INLINE_RANGES;
+    if (dyn_base >= 0xF0000000ull) return fail(BFQ_E_RANGE, "batch too large for 32-bit range indices; split the batch");
+    if (h->d_ranges.cap < dyn_base + (1u << 20)) CUDA_TRY(h->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, nn))));
     if (h->d_throttled.cap == 0) CUDA_TRY(h->d_throttled.reserve(1 << 16));
 
     MatchParams p{};
@@ -197,6 +202,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     for (int attempt = 0; attempt < 8; attempt++) {
         p.ranges = h->d_ranges.p;
         p.ranges_cap = h->d_ranges.cap;
+        p.dyn_base = dyn_base;
         CUDA_TRY(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), stream));
         p.work_list = nullptr;
         p.n_work = 0;
@@ -242,14 +248,14 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
             CUDA_TRY(cudaStreamSynchronize(stream));
             if (hc[CTR_ERROR] != 0) return fail(BFQ_E_STATE, "tier-2 scratch exhausted (index statistics inconsistent)");
         }
-        if (hc[CTR_RANGES] <= h->d_ranges.cap) break;
+        if (dyn_base + hc[CTR_RANGES] <= h->d_ranges.cap) break;
         // the range buffer was too small: grow and redo the batch
-        const size_t want = (size_t) (hc[CTR_RANGES] + hc[CTR_RANGES] / 4 + 1024);
+        const size_t want = (size_t) (dyn_base + hc[CTR_RANGES] + hc[CTR_RANGES] / 4 + 1024);
         if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
         CUDA_TRY(h->d_ranges.reserve(want));
         if (attempt == 7) return fail(BFQ_E_STATE, "range buffer sizing did not converge");
     }
-    out->n_ranges = (int64_t) hc[CTR_RANGES];
+    out->n_ranges = (int64_t) (dyn_base + hc[CTR_RANGES]);   // extent of the sparse range array
     out->n_flagged = (int64_t) hc[CTR_FLAGGED];
     out->n_throttled = 0;
     if (hc[CTR_FLAGGED] > 0) {
@@ -503,20 +509,46 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     CoreOut co;
     rc = match_core(h, h->d_topics.p, h->d_topic_off.p, h->d_topic_tenant.p, n, n_tenants, st, &co);
     if (rc != BFQ_OK) return rc;
+    // ---- compact the sparse (inline + dynamic) ranges on the device, then D2H into the pinned result buffers
+    CUDA_TRY(h->d_cnt.reserve(nn));
+    CUDA_TRY(h->d_new_begin.reserve(nn));
+    CUDA_TRY(h->d_ranges_c.reserve((size_t) std::max<int64_t>(co.n_ranges, 1)));
+    CompactParams cp{};
+    cp.n_topics = n;
+    cp.span_begin = h->d_span_begin.p;
+    cp.span_count = h->d_span_count.p;
+    cp.ranges = h->d_ranges.p;
+    cp.counts = h->d_cnt.p;
+    cp.new_begin = h->d_new_begin.p;
+    cp.ranges_out = h->d_ranges_c.p;
+    cp.ranges_out_cap = h->d_ranges_c.cap;
+    cp.total_out = h->d_counters.p + CTR_ROUTES;
+    int64_t n_compact = 0;
+    if (n > 0) {
+        size_t tmp_bytes = 0;
+        CUDA_TRY(launch_compact(cp, nullptr, &tmp_bytes, st));
+        CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes));
+        CUDA_TRY(launch_compact(cp, h->d_scan_tmp.p, &tmp_bytes, st));
+        co.n_launches += 3;
+        h->launches += 3;
+        CUDA_TRY(cudaMemcpyAsync(h->h_counters.p, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        n_compact = (int64_t) h->h_counters.p[CTR_ROUTES];
+    }
+    co.n_ranges = n_compact;
     CUDA_TRY(cudaEventRecord(h->ev[2], st));
-    // ---- D2H into the pinned result buffers
     CUDA_TRY(h->h_span_begin.reserve(nn));
     CUDA_TRY(h->h_span_count.reserve(nn));
     CUDA_TRY(h->h_route_count.reserve(nn));
     CUDA_TRY(h->h_ranges.reserve((size_t) std::max<int64_t>(co.n_ranges, 1)));
     CUDA_TRY(h->h_throttled.reserve((size_t) std::max<int64_t>(co.n_throttled, 1)));
     if (n > 0) {
-        CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p, h->d_span_begin.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p, h->d_new_begin.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(h->h_span_count.p, h->d_span_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(h->h_route_count.p, h->d_route_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
     }
     if (co.n_ranges > 0)
-        CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p, h->d_ranges.p, (size_t) co.n_ranges * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p, h->d_ranges_c.p, (size_t) co.n_ranges * sizeof(uint2), cudaMemcpyDeviceToHost, st));
     if (co.n_throttled > 0)
         CUDA_TRY(cudaMemcpyAsync(h->h_throttled.p, h->d_throttled.p, (size_t) co.n_throttled * sizeof(uint3), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(h->ev[3], st));

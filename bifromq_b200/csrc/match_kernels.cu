@@ -16,6 +16,8 @@
 // same code with per-warp buffers in global memory sized from the index statistics — never truncated.
 #include "match_kernels.cuh"
 
+#include <cub/device/device_scan.cuh>
+
 namespace bfq {
 
 namespace {
@@ -243,6 +245,7 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
     if (n_rg > 0) {
         if (lane == 0) base = atomicAdd(&p.counters[CTR_RANGES], (unsigned long long) n_rg);
         base = __shfl_sync(FULL, base, 0);
+        base += p.dyn_base;
         if (base + n_rg <= p.ranges_cap)
             for (uint32_t i = lane; i < n_rg; i += 32) p.ranges[base + i] = rg[i];
     }
@@ -285,123 +288,162 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 
 
 // ------------------------------------------------------------------------------------------------ tier 0
-// ONE LANE PER TOPIC. The warp-per-topic walk above leaves most lanes idle when the frontier is a handful of
-// nodes (the common case: ~4 per level on BASELINE config C4) and spends ~2100 warp instructions per topic
-// (ncu, profiles/r1_v1_*). Here a warp takes 32 consecutive topics:
-//   * their bytes are one contiguous run of the blob -> staged into shared memory with one coalesced copy;
-//   * each lane finds its own '/' offsets once (<= 16 levels) and then walks the trie depth-first. A node has
-//     at most two continuations per level (exact child, '+' child), so the DFS needs ONE pending entry per
-//     level: a 16-entry per-lane array plus a bitmask, never a growing frontier;
-//   * per step a lane builds the 24-byte key of its current level from shared memory (aligned words + funnel
-//     shift), issues the exact-child probe and the '+' child load together (eight independent LDG.128), emits the
-//     discovered ranges into its own shared staging row;
-//   * when all 32 topics are done the warp does one prefix sum + ONE atomicAdd for the whole batch and copies
-//     the ranges out.
-// Anything that does not fit the bounded buffers (topic > 255 B, > 16 levels, a level > 24 B, > L_RG ranges,
-// batch bytes beyond the stage) is handed, whole, to the warp-per-topic tier through defer_list.
+// ONE LANE PER TOPIC, persistent lanes. The warp-per-topic walk above leaves most lanes idle when the frontier
+// is a handful of nodes (the common case: ~4 per level on BASELINE config C4; ncu: ~2100 warp instructions per
+// topic, profiles/r1_v1_*). Here every lane walks its own topic depth-first:
+//   * a node has at most two continuations per level (exact child, '+' child), so the DFS parks at most ONE
+//     pending '+' branch per level: a 16-entry per-lane array plus a bitmask, never a growing frontier;
+//   * per step a lane reads the 28 bytes at its current level start (aligned words + funnel shift), finds the
+//     '/' with a SWAR zero-byte test — the level table is filled lazily, there is no tokenising pre-pass —,
+//     issues the exact-child probe and the '+' child load together (eight independent LDG.128) and writes the
+//     discovered ranges straight to the topic's INLINE_RANGES inline slots: no staging, no output atomics;
+//   * a lane that finishes takes the next topic at once (warp-uniform refill from 128-topic chunks claimed with
+//     one atomicAdd per chunk), so a straggler never idles the other 31 lanes (v2 of this kernel waited for the
+//     whole batch of 32: ncu showed 10 of 32 lanes active, profiles/r1_v2_*).
+// Anything that does not fit the bounded state (> 16 levels, a level > 24 B, > INLINE_RANGES ranges, topic > 64 KB)
+// is handed, whole, to the warp-per-topic tier through defer_list.
 constexpr int L_WARPS = 4;
-constexpr int L_SEG = 3072;
-constexpr int L_RG = 12;
 constexpr int L_MAXLV = 16;
+constexpr int L_CHUNK = 128;
 
 struct LaneSmem {
-    uint32_t seg[(L_SEG + 64) / 4];       // staged topic bytes (word array: aligned LDS.32 + funnel shift)
-    uint8_t lv[32][L_MAXLV + 4];          // per lane: start offset of each level (relative to the topic), +sentinel
-    uint2 rg[L_RG][32];                   // per lane range staging, lane-minor (bank-conflict free)
-    uint2 stk[L_MAXLV + 1][32];           // pending '+' branch per level: {node id, plus | has_exact << 31}
+    uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
+    uint2 stk[L_MAXLV + 1][32];     // parked '+' branch per level: {node id, plus | has_exact << 31}
 };
 
 __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
     __shared__ LaneSmem sm[L_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     LaneSmem& ws = sm[wid];
-    const uint8_t* segb = reinterpret_cast<const uint8_t*>(ws.seg);
-    const int64_t gw = (int64_t) blockIdx.x * L_WARPS + wid, nw = (int64_t) gridDim.x * L_WARPS;
-    const int64_t n_batches = (p.n_topics + 31) / 32;
     const uint32_t lt_mask = (1u << lane) - 1;
+    const int64_t n = p.n_topics;
 
-    for (int64_t batch = gw; batch < n_batches; batch += nw) {
-        const int64_t t64 = batch * 32 + lane;
-        const bool valid = t64 < p.n_topics;
-        const uint32_t t = (uint32_t) t64;
-        const int64_t my_off = valid ? p.topic_off[t64] : 0;
-        const int64_t my_end = valid ? p.topic_off[t64 + 1] : 0;
-        const int64_t off0 = __shfl_sync(FULL, my_off, 0);
-        const int nvalid = __popc(__ballot_sync(FULL, valid));
-        const int64_t seg_end = __shfl_sync(FULL, my_end, nvalid - 1);
-        const int seg_len = (int) min((int64_t) L_SEG, seg_end - off0);
-        __syncwarp();
-        {   // coalesced stage of the batch's bytes
-            const uint8_t* src = p.topics + off0;
-            uint8_t* dst = reinterpret_cast<uint8_t*>(ws.seg);
-            for (int i = lane; i < seg_len; i += 32) dst[i] = src[i];
+    // warp-uniform work cursor
+    int64_t next = 0, end = 0;
+    bool exhausted = false;
+    // per-lane topic state
+    bool have = false, bad = false;
+    uint32_t t = 0, node = 0, plusf = NONE31, pending = 0, n_rg = 0, acc_r = 0;
+    uint64_t acc_p = 0, acc_g = 0;
+    int64_t my_off = 0;
+    int len = 0, level = 0, tenant = 0;
+
+    auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
+        if (n_rg < INLINE_RANGES) p.ranges[(uint64_t) t * INLINE_RANGES + n_rg] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
+        else bad = true;
+        n_rg++;
+        acc_r += count;
+        acc_p += caps_value(caps & 0xFFFFu);
+        acc_g += caps_value(caps >> 16);
+    };
+    auto finish = [&]() {
+        if (bad) {
+            const unsigned long long idx = atomicAdd(&p.counters[CTR_DEFER], 1ull);
+            p.defer_list[idx] = t;
+            p.span_begin[t] = 0;
+            p.span_count[t] = SPAN_OVERFLOW;
+            p.route_count[t] = 0;
+        } else {
+            const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
+            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint64_t) (maxP < 0 ? 0 : maxP);
+            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint64_t) (maxG < 0 ? 0 : maxG);
+            const bool flagged = flag_p || flag_g;
+            p.span_begin[t] = t * INLINE_RANGES;
+            p.span_count[t] = n_rg | (flagged ? SPAN_FLAGGED : 0u);
+            p.route_count[t] = acc_r;
+            if (flagged) {
+                const unsigned long long idx = atomicAdd(&p.counters[CTR_FLAGGED], 1ull);
+                p.flagged_list[idx] = t;
+            }
         }
-        __syncwarp();
-        const int rel = (int) (my_off - off0);
-        const int len = (int) (my_end - my_off);
-        bool ok = valid && (my_end - off0) <= L_SEG && len <= 255;
+        have = false;
+    };
 
-        // ---- per-lane level table
-        int nlev = 1;
-        {
-            int maxlen = ok ? len : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
-            ws.lv[lane][0] = 0;
-            int last_start = 0;
-            bool too_long = false;
-            for (int i = 0; i < maxlen; i++) {
-                if (ok && i < len && segb[rel + i] == '/') {
-                    if (i - last_start > (int) TOKEN_BYTES) too_long = true;
-                    if (nlev <= L_MAXLV) ws.lv[lane][nlev] = (uint8_t) (i + 1);
-                    nlev++;
-                    last_start = i + 1;
+    while (true) {
+        // ---- refill idle lanes with the next unclaimed topics
+        const unsigned idle = __ballot_sync(FULL, !have);
+        if (idle) {
+            if (next >= end && !exhausted) {
+                unsigned long long c = 0;
+                if (lane == 0) c = atomicAdd(&p.counters[CTR_CHUNK], (unsigned long long) L_CHUNK);
+                c = __shfl_sync(FULL, c, 0);
+                if ((int64_t) c >= n) {
+                    exhausted = true;
+                } else {
+                    next = (int64_t) c;
+                    end = min(n, next + L_CHUNK);
                 }
             }
-            if (len - last_start > (int) TOKEN_BYTES) too_long = true;
-            if (nlev > L_MAXLV || too_long) ok = false;
-            if (ok) ws.lv[lane][nlev] = (uint8_t) 0;   // sentinel slot, the end of the last level is `len` (handled below)
-        }
-
-        const int tenant = valid ? p.topic_tenant[t] : 0;
-        const int root_ord = valid ? p.tenant_root[tenant] : -1;
-        uint32_t n_rg = 0, acc_r = 0;
-        uint64_t acc_p = 0, acc_g = 0;
-        bool overflow = false;
-        auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
-            if (n_rg < (uint32_t) L_RG) ws.rg[n_rg][lane] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
-            else overflow = true;
-            n_rg++;
-            acc_r += count;
-            acc_p += caps_value(caps & 0xFFFFu);
-            acc_g += caps_value(caps >> 16);
-        };
-
-        // ---- DFS state
-        bool have = false;
-        uint32_t node = 0, plusf = NONE31;
-        int level = 0;
-        uint32_t pending = 0;
-        if (ok && root_ord >= 0) {
-            uint32_t rw[16];
-            load_slot(p.roots + root_ord, rw);
-            const bool sys = len > 0 && segb[rel] == '$';
-            if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
-            const uint32_t plus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
-            const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
-            if (has_exact || plus != NONE31) {
-                have = true;
-                node = ROOT_BASE + (uint32_t) root_ord;
-                plusf = plus | (has_exact ? 0x80000000u : 0u);
+            if (next < end) {
+                const int64_t idx = next + __popc(idle & lt_mask);
+                const bool take = !have && idx < end;
+                next = min(end, next + (int64_t) __popc(idle));
+                if (take) {
+                    t = (uint32_t) idx;
+                    my_off = p.topic_off[idx];
+                    const int64_t l64 = p.topic_off[idx + 1] - my_off;
+                    len = (int) l64;
+                    tenant = p.topic_tenant[idx];
+                    const int root_ord = p.tenant_root[tenant];
+                    n_rg = 0; acc_r = 0; acc_p = 0; acc_g = 0; pending = 0; level = 0;
+                    bad = l64 > 65535;
+                    have = true;
+                    ws.lv[0][lane] = 0;
+                    bool start = false;
+                    if (root_ord >= 0 && !bad) {
+                        uint32_t rw[16];
+                        load_slot(p.roots + root_ord, rw);
+                        const bool sys = len > 0 && p.topics[my_off] == '$';
+                        if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
+                        const uint32_t plus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
+                        const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
+                        if (has_exact || plus != NONE31) {
+                            node = ROOT_BASE + (uint32_t) root_ord;
+                            plusf = plus | (has_exact ? 0x80000000u : 0u);
+                            start = true;
+                        }
+                    }
+                    if (!start) finish();
+                }
+            } else if (idle == FULL) {
+                break;   // nothing left to claim and every lane is done
             }
         }
-        while (__any_sync(FULL, have)) {
-            if (have) {
-                const int s = ws.lv[lane][level];
-                const bool last = level == nlev - 1;
-                const int e = last ? len : (int) ws.lv[lane][level + 1] - 1;
-                const int tlen = e - s;
-                // '+' child first (independent of the token)
+        if (have) {
+            // ---- one DFS step: expand `node` along level `level`
+            const int s = ws.lv[level][lane];
+            const int rem = len - s;
+            // 28 bytes at the level start: aligned words + funnel shift (words at/after the topic end are not read)
+            const uint64_t a = (uint64_t) (uintptr_t) p.topics + (uint64_t) my_off + (uint64_t) s;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~3ull);
+            const uint32_t* wend = reinterpret_cast<const uint32_t*>((uint64_t) (uintptr_t) p.topics + (uint64_t) my_off + (uint64_t) len);
+            const int sh = (int) (a & 3) * 8;
+            uint32_t x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = (wp + j) < wend ? __ldg(wp + j) : 0u;
+            uint32_t k[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            // first '/' within the 28 bytes (SWAR zero-byte test on w ^ "////")
+            int q = 28;
+#pragma unroll
+            for (int j = 6; j >= 0; j--) {
+                const uint32_t y = k[j] ^ 0x2F2F2F2Fu;
+                const uint32_t hz = (y - 0x01010101u) & ~y & 0x80808080u;
+                if (hz) q = 4 * j + ((__ffs(hz) - 1) >> 3);
+            }
+            const int tlen = min(q, rem);
+            const bool last = tlen == rem;
+            if (tlen > (int) TOKEN_BYTES || (!last && level >= L_MAXLV - 1)) {
+                bad = true;   // a level longer than the inline key, or deeper than the level table: tier 1 takes it
+                finish();
+            } else {
+                if (!last) ws.lv[level + 1][lane] = (uint16_t) (s + tlen + 1);
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const int vb = tlen - 4 * j;
+                    k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
+                }
                 const uint32_t plus = plusf & NONE31;
                 const bool has_plus = plus != NONE31;
                 uint32_t pw[16];
@@ -409,21 +451,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 bool alive = plusf >> 31;
                 uint32_t cw[16], cid = 0;
                 if (alive) {
-                    // key words of [rel+s, rel+e): aligned words + funnel shift, bytes past the token zeroed
-                    const int a = rel + s;
-                    const uint32_t* wp = ws.seg + (a >> 2);
-                    const int sh = (a & 3) * 8;
-                    uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4], x5 = wp[5], x6 = wp[6];
-                    uint32_t k[6];
-                    k[0] = __funnelshift_r(x0, x1, sh); k[1] = __funnelshift_r(x1, x2, sh); k[2] = __funnelshift_r(x2, x3, sh);
-                    k[3] = __funnelshift_r(x3, x4, sh); k[4] = __funnelshift_r(x4, x5, sh); k[5] = __funnelshift_r(x5, x6, sh);
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        const int vb = tlen - 4 * j;   // valid bytes in word j
-                        k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
-                    }
-                    const uint64_t tokh = token_hash((uint32_t) tlen, k);
-                    alive = probe(p.slots, p.n_slots, node, (uint32_t) tlen, k, tokh, cw, cid);
+                    uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
+                    alive = probe(p.slots, p.n_slots, node, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
                 }
                 bool push_c = false, push_p = false;
                 if (alive) {
@@ -442,21 +471,20 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                         push_p = (pw[W_FLAGS] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE;
                     }
                 }
-                const uint32_t c_plusf = (cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS]) | ((cw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
-                const uint32_t p_plusf = (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) | ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
-                if (overflow) {
-                    have = false;
+                if (bad) {
+                    finish();
                 } else if (push_c) {
                     if (push_p) {   // park the '+' branch of this level, continue down the exact branch
-                        ws.stk[level + 1][lane] = make_uint2(plus, p_plusf);
+                        ws.stk[level + 1][lane] = make_uint2(plus, (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) |
+                                                                       ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u));
                         pending |= 1u << (level + 1);
                     }
                     node = cid;
-                    plusf = c_plusf;
+                    plusf = (cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS]) | ((cw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
                     level++;
                 } else if (push_p) {
                     node = plus;
-                    plusf = p_plusf;
+                    plusf = (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) | ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
                     level++;
                 } else if (pending) {
                     const int l = 31 - __clz(pending);
@@ -466,56 +494,25 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     plusf = it.y;
                     level = l;
                 } else {
-                    have = false;
+                    finish();
                 }
             }
         }
-
-        // ---- batch epilogue: defer what did not fit, flush the rest with one atomicAdd per warp
-        const bool defer = valid && (!ok || overflow);
-        const bool done = valid && !defer;
-        const unsigned md = __ballot_sync(FULL, defer);
-        if (md) {
-            unsigned long long dbase = 0;
-            if (lane == 0) dbase = atomicAdd(&p.counters[CTR_DEFER], (unsigned long long) __popc(md));
-            dbase = __shfl_sync(FULL, dbase, 0);
-            if (defer) {
-                p.defer_list[dbase + __popc(md & lt_mask)] = t;
-                p.span_begin[t] = 0;
-                p.span_count[t] = SPAN_OVERFLOW;
-                p.route_count[t] = 0;
-            }
-        }
-        const uint32_t cnt = done ? n_rg : 0u;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        unsigned long long base = 0;
-        if (total > 0) {
-            if (lane == 0) base = atomicAdd(&p.counters[CTR_RANGES], (unsigned long long) total);
-            base = __shfl_sync(FULL, base, 0);
-        }
-        if (done) {
-            const unsigned long long mine = base + (incl - cnt);
-            if (base + total <= p.ranges_cap)
-                for (uint32_t j = 0; j < cnt; j++) p.ranges[mine + j] = ws.rg[j][lane];
-            const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
-            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint64_t) (maxP < 0 ? 0 : maxP);
-            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint64_t) (maxG < 0 ? 0 : maxG);
-            const bool flagged = flag_p || flag_g;
-            p.span_begin[t] = (uint32_t) mine;
-            p.span_count[t] = cnt | (flagged ? SPAN_FLAGGED : 0u);
-            p.route_count[t] = acc_r;
-            if (flagged) {
-                const unsigned long long idx = atomicAdd(&p.counters[CTR_FLAGGED], 1ull);
-                p.flagged_list[idx] = t;
-            }
-        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ compaction
+__global__ void compact_counts_kernel(int64_t n, const uint32_t* span_count, uint32_t* counts) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = span_count[i] & SPAN_COUNT_MASK;
+}
+__global__ void compact_gather_kernel(const CompactParams p) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_topics) return;
+    const uint32_t c = p.counts[i], nb = p.new_begin[i], ob = p.span_begin[i];
+    if ((uint64_t) nb + c <= p.ranges_out_cap)
+        for (uint32_t j = 0; j < c; j++) p.ranges_out[nb + j] = p.ranges[ob + j];
+    if (i == p.n_topics - 1) *p.total_out = (unsigned long long) nb + c;
 }
 
 // ------------------------------------------------------------------------------------------------ caps
@@ -623,11 +620,22 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, match_topics_lane_kernel, L_WARPS * 32, 0);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    // persistent grid (SM count x resident CTAs), each warp strides over batches of 32 consecutive topics
+    // persistent grid (SM count x resident CTAs); warps claim 128-topic chunks with one atomicAdd each
     int64_t ctas = (int64_t) sms * ctas_per_sm;
-    const int64_t need = ((p.n_topics + 31) / 32 + L_WARPS - 1) / L_WARPS;
+    const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;
     match_topics_lane_kernel<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
+}
+
+cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream) {
+    if (!d_scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
+    if (p.n_topics <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned) ((p.n_topics + 255) / 256);
+    compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
+    if (e != cudaSuccess) return e;
+    compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 void launch_caps(const CapsParams& p, cudaStream_t stream) {

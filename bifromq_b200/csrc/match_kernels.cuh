@@ -16,6 +16,7 @@ enum : int {
     CTR_ROUTES = 4,      // total matched routes (before caps)
     CTR_ERROR = 5,       // tier-2 scratch exhausted (cannot happen with correctly sized scratch)
     CTR_DEFER = 6,       // topics the lane-per-topic tier handed to the warp-per-topic tier
+    CTR_CHUNK = 7,       // tier-0 work distribution: next unclaimed topic index
     CTR_COUNT = 8,
 };
 
@@ -45,6 +46,8 @@ struct MatchParams {
     uint32_t* route_count;          // [n]
     uint2* ranges;                  // [ranges_cap] {first, count | RANGE_MULTI}
     uint64_t ranges_cap;
+    uint64_t dyn_base;              // ranges[0, dyn_base) = tier-0 inline slots (INLINE_RANGES per topic); the cursor
+                                    // CTR_RANGES allocates from ranges[dyn_base, ranges_cap) for tiers 1 and 2
     uint32_t* overflow_list;        // [n] topic indices deferred to tier 2
     uint32_t* defer_list;           // [n] topic indices deferred from tier 0 to tier 1
     uint32_t* flagged_list;         // [n] topic indices needing caps
@@ -93,6 +96,23 @@ struct ExpandParams {
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream);
 void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStream_t stream);
 void launch_caps(const CapsParams& p, cudaStream_t stream);
+
+constexpr uint32_t INLINE_RANGES = 12;   // tier 0 writes topic t's ranges at ranges[t * INLINE_RANGES ...)
+
+// Compaction for the host path: gathers the sparse (inline + dynamic) ranges into one dense array in topic order.
+// d_scan_tmp / tmp_bytes: scratch for the exclusive scan (query the size with d_scan_tmp == nullptr).
+struct CompactParams {
+    int64_t n_topics;
+    const uint32_t* span_begin;     // in
+    const uint32_t* span_count;     // in (flag bits allowed)
+    const uint2* ranges;            // in
+    uint32_t* counts;               // scratch [n]
+    uint32_t* new_begin;            // out [n]
+    uint2* ranges_out;              // out [total]
+    uint64_t ranges_out_cap;
+    unsigned long long* total_out;  // device scalar: total number of ranges
+};
+cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream);
 int match_kernel_smem_bytes();
 
 }  // namespace bfq
