@@ -99,7 +99,7 @@ struct bfq_index {
     // snapshot on device
     DevBuf<Slot> d_slots, d_roots;
     DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
-    DevBuf<uint8_t> d_rkind;
+    DevBuf<uint8_t> d_rkind, d_tags;
     // per-call workspace
     DevBuf<uint8_t> d_topics;
     DevBuf<int64_t> d_topic_off;
@@ -123,7 +123,7 @@ struct bfq_index {
 
     ~bfq_index() {
         cudaSetDevice(device);
-        d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release();
+        d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release(); d_tags.release();
         d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
         d_flagged.release(); d_kept.release(); d_defer.release(); d_ranges_c.release(); d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
@@ -182,7 +182,8 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     MatchParams p{};
     p.slots = h->d_slots.p;
     p.roots = h->d_roots.p;
-    p.n_slots = h->flat.n_slots;
+    p.tags = reinterpret_cast<const uint4*>(h->d_tags.p);
+    p.n_blocks = h->flat.n_blocks;
     p.topics = d_topics;
     p.topic_off = d_topic_off;
     p.topic_tenant = d_topic_tenant;
@@ -375,12 +376,14 @@ int32_t bfq_index_commit(bfq_index* h) {
     // upload the new snapshot, then swap (matches are serialised by the handle mutex)
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(h->d_slots.reserve(flat.slots.size()));
+    CUDA_TRY(h->d_tags.reserve(flat.tags.size()));
     CUDA_TRY(h->d_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
     CUDA_TRY(h->d_segs.reserve(flat.segs.size()));
     CUDA_TRY(h->d_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
     CUDA_TRY(h->d_pfxP.reserve(flat.pfx_persistent.size()));
     CUDA_TRY(h->d_pfxG.reserve(flat.pfx_group.size()));
     CUDA_TRY(cudaMemcpy(h->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
     if (!flat.roots.empty())
         CUDA_TRY(cudaMemcpy(h->d_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -391,6 +394,8 @@ int32_t bfq_index_commit(bfq_index* h) {
     // the host keeps only what it needs after the upload
     flat.slots.clear();
     flat.slots.shrink_to_fit();
+    flat.tags.clear();
+    flat.tags.shrink_to_fit();
     flat.roots.clear();
     flat.pfx_persistent.clear();
     flat.pfx_persistent.shrink_to_fit();
@@ -405,7 +410,7 @@ int32_t bfq_index_commit(bfq_index* h) {
 int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
     if (!h || !stats) return fail(BFQ_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> g(h->mu);
-    const int64_t dev_bytes = (int64_t) (h->d_slots.bytes() + h->d_roots.bytes() + h->d_segs.bytes() + h->d_rkind.bytes() +
+    const int64_t dev_bytes = (int64_t) (h->d_slots.bytes() + h->d_tags.bytes() + h->d_roots.bytes() + h->d_segs.bytes() + h->d_rkind.bytes() +
                                          h->d_pfxP.bytes() + h->d_pfxG.bytes());
     const int64_t v[12] = {h->flat.n_routes, (int64_t) h->flat.tenant_ordinal.size(), h->flat.n_nodes, (int64_t) h->flat.n_slots,
                            dev_bytes, h->flat.max_nodes_per_depth, h->launches, h->overflow_topics, h->flagged_topics,
@@ -422,20 +427,25 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
     FlatIndex flat;
     if (!build_flat_index(st.materialize(), &flat, &err)) return fail(BFQ_E_INVALID, err);
-    // self-check of the table: every non-empty slot is reachable from its home slot by linear probing
-    int64_t used = 0;
-    for (uint32_t s = 0; s < flat.n_slots; s++) {
-        const Slot& sl = flat.slots[s];
-        if (sl.w[W_PARENT] == EMPTY_PARENT) continue;
-        used++;
-        uint32_t h0 = home_slot(token_hash(sl.w[W_LEN], &sl.w[W_TOK]), sl.w[W_PARENT], flat.n_slots);
-        for (uint32_t q = h0; q != s; q = q + 1 == flat.n_slots ? 0 : q + 1)
-            if (flat.slots[q].w[W_PARENT] == EMPTY_PARENT) return fail(BFQ_E_STATE, "hash table probe chain broken");
+    // self-check of the table: every occupied slot is found again through its tag block
+    {
+        EdgeTable t;
+        t.slots = std::move(flat.slots);
+        t.tags = std::move(flat.tags);
+        t.n_blocks = flat.n_blocks;
+        int64_t used = 0;
+        for (uint32_t s = 0; s < flat.n_slots; s++) {
+            const Slot& sl = t.slots[s];
+            if (sl.w[W_PARENT] == EMPTY_PARENT) continue;
+            used++;
+            if (t.find(sl.w[W_PARENT], sl.w[W_LEN], &sl.w[W_TOK]) != s) return fail(BFQ_E_STATE, "edge table lookup does not find a placed slot");
+        }
+        if (used + (int64_t) flat.roots.size() != flat.n_nodes) return fail(BFQ_E_STATE, "node count mismatch");
     }
-    if (used + (int64_t) flat.roots.size() != flat.n_nodes) return fail(BFQ_E_STATE, "node count mismatch");
     const int64_t v[8] = {flat.n_routes, (int64_t) flat.tenant_ordinal.size(), flat.n_nodes, (int64_t) flat.n_slots,
                           flat.max_nodes_per_depth, flat.max_tenant_nodes, flat.n_multi, flat.n_cont_chunks};
     for (int32_t i = 0; i < n_stats && i < 8; i++) stats[i] = v[i];
+    if (n_stats > 8) stats[8] = flat.overflowed_blocks;
     return BFQ_OK;
 }
 

@@ -1,0 +1,57 @@
+// hash_probe.cuh — device-side lookup in the tag-filtered blocked edge table (layout: trie_layout.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trie_layout.h"
+
+namespace bfq {
+
+__device__ __forceinline__ void load_slot(const Slot* s, uint32_t (&w)[16]) {
+    const uint4* p = reinterpret_cast<const uint4*>(s);
+    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
+}
+
+// bytes of w equal to fp -> 0x80 in that byte (SWAR zero-byte test; it can also flag a byte just above a true
+// match — such a false candidate only costs one extra slot compare, a true match is never missed)
+__device__ __forceinline__ uint32_t match_bytes(uint32_t w, uint32_t fp4) {
+    const uint32_t y = w ^ fp4;
+    return (y - 0x01010101u) & ~y & 0x80808080u;
+}
+
+// Lookup of the edge (parent, lenw, k[0..5]). On success `w` holds the child record and `slot` its index.
+__device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t parent, uint32_t lenw,
+                                      const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
+    const uint64_t h = edge_hash(tokh, parent);
+    uint32_t b = home_block(h, n_blocks);
+    const uint32_t fp4 = fingerprint(h) * 0x01010101u;
+    while (true) {
+        const uint4 tg = __ldg(tags + b);
+        const uint32_t tw[4] = {tg.x, tg.y, tg.z, tg.w & 0x00FFFFFFu};   // byte 15 is the control byte
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t m = match_bytes(tw[q], fp4);
+            while (m) {
+                const uint32_t j = 4u * q + ((__ffs(m) - 1) >> 3);
+                m &= m - 1;
+                const uint32_t s = b * BLOCK_SLOTS + j;
+                if (j < BLOCK_USABLE) {
+                    load_slot(slots + s, w);
+                    if (w[W_PARENT] == parent && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] &&
+                        w[5] == k[3] && w[6] == k[4] && w[7] == k[5]) {
+                        slot = s;
+                        return true;
+                    }
+                }
+            }
+        }
+        if ((tg.w >> 24) == 0) return false;   // the block never overflowed: the edge does not exist
+        b = b + 1 == n_blocks ? 0 : b + 1;
+    }
+}
+
+}  // namespace bfq

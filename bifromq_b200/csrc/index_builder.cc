@@ -308,17 +308,15 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     const size_t n_roots = out->tenant_ordinal.size();
     const size_t n_table = total_nodes - n_roots;
     out->n_nodes = (int64_t) total_nodes;
-    uint64_t want = std::max<uint64_t>(1024, (uint64_t) n_table * 2);
-    if (want >= 0x7FFFFFF0ull) {
-        if (err) *err = "index too large for 31-bit slot ids";
-        return false;
+    EdgeTable table;
+    {
+        const uint64_t nb = ((uint64_t) n_table * 2 + BLOCK_USABLE - 1) / BLOCK_USABLE;
+        if (nb * BLOCK_SLOTS >= 0x7FFFFFF0ull) {
+            if (err) *err = "index too large for 31-bit slot ids";
+            return false;
+        }
     }
-    out->n_slots = (uint32_t) want;
-    out->slots.assign(out->n_slots, Slot());
-    for (auto& s : out->slots) {
-        memset(s.w, 0, sizeof(s.w));
-        s.w[W_PARENT] = EMPTY_PARENT;
-    }
+    table.init(n_table);
     out->roots.assign(n_roots, Slot());
     std::vector<uint32_t> id_of(total_nodes, NONE);
     out->segs.clear();
@@ -352,13 +350,9 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
             rec->w[W_PARENT] = NONE;
         } else {
             const uint32_t parent_id = id_of[nd.parent];
-            uint32_t s = home_slot(token_hash(nd.lenw, nd.tok), parent_id, out->n_slots);
-            while (out->slots[s].w[W_PARENT] != EMPTY_PARENT) s = s + 1 == out->n_slots ? 0 : s + 1;
+            const uint32_t s = table.place(parent_id, nd.lenw, nd.tok);
             id_of[i] = s;
-            rec = &out->slots[s];
-            rec->w[W_PARENT] = parent_id;
-            rec->w[W_LEN] = nd.lenw;
-            for (uint32_t k = 0; k < TOKEN_WORDS; k++) rec->w[W_TOK + k] = nd.tok[k];
+            rec = &table.slots[s];
         }
         uint32_t flags = nd.flags;
         emit_target(nd.own, &rec->w[W_OWN_FIRST], &rec->w[W_OWN_COUNT], &rec->w[W_OWN_CAPS], FLAG_OWN_MULTI, &flags);
@@ -369,10 +363,15 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     for (size_t i = 0; i < total_nodes; i++) {
         const BNode& nd = b.nodes[i];
         if (nd.plus == NONE) continue;
-        Slot* rec = nd.parent == NONE ? &out->roots[nd.root_ordinal] : &out->slots[id_of[i]];
+        Slot* rec = nd.parent == NONE ? &out->roots[nd.root_ordinal] : &table.slots[id_of[i]];
         rec->w[W_PLUS] = id_of[nd.plus];
     }
     if (out->segs.empty()) out->segs.assign(2, 0);
+    out->n_blocks = table.n_blocks;
+    out->n_slots = table.n_blocks * BLOCK_SLOTS;
+    out->overflowed_blocks = table.overflowed_blocks;
+    out->slots = std::move(table.slots);
+    out->tags = std::move(table.tags);
     return true;
 }
 

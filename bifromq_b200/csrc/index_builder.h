@@ -31,7 +31,8 @@ struct KVBlob {
 
 // Everything the device needs, in host memory, plus build statistics.
 struct FlatIndex {
-    std::vector<Slot> slots;                  // hash table
+    std::vector<Slot> slots;                  // blocked hash table (n_blocks * BLOCK_SLOTS)
+    std::vector<uint8_t> tags;                // 16 tag bytes per block
     std::vector<Slot> roots;                  // one record per tenant (key words unused)
     std::vector<uint32_t> segs;               // segment table (pairs), see trie_layout.h
     std::vector<uint8_t> rkind;               // per rank RouteKind
@@ -39,7 +40,8 @@ struct FlatIndex {
     std::vector<uint32_t> pfx_group;          // [n_routes+1] exclusive prefix count of KIND_GROUP
     std::unordered_map<std::string, uint32_t> tenant_ordinal;
     int64_t n_routes = 0, n_nodes = 0, max_nodes_per_depth = 0, max_tenant_nodes = 0, n_multi = 0, n_cont_chunks = 0;
-    uint32_t n_slots = 0;
+    uint32_t n_slots = 0, n_blocks = 0;
+    int64_t overflowed_blocks = 0;
 };
 
 // Build the flat index from a sorted KV snapshot. Returns false and sets *err on undecodable input.

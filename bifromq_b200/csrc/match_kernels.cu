@@ -15,6 +15,7 @@
 // Tier 2 (kBig): the rare topic whose frontier or range count outgrows the shared buffers is re-run by the
 // same code with per-warp buffers in global memory sized from the index statistics — never truncated.
 #include "match_kernels.cuh"
+#include "hash_probe.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -35,31 +36,6 @@ struct WarpSmem {
     uint2 fr[2][FR_CAP];
     uint2 rg[RG_CAP];
 };
-
-__device__ __forceinline__ void load_slot(const Slot* s, uint32_t (&w)[16]) {
-    const uint4* p = reinterpret_cast<const uint4*>(s);
-    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-    w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
-}
-
-// open-addressing lookup of the edge (parent, lenw, k[0..5]); on success w holds the child record
-__device__ __forceinline__ bool probe(const Slot* slots, uint32_t n_slots, uint32_t parent, uint32_t lenw,
-                                      const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
-    uint32_t s = home_slot(tokh, parent, n_slots);
-    while (true) {
-        load_slot(slots + s, w);
-        if (w[W_PARENT] == EMPTY_PARENT) return false;
-        if (w[W_PARENT] == parent && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] &&
-            w[5] == k[3] && w[6] == k[4] && w[7] == k[5]) {
-            slot = s;
-            return true;
-        }
-        s = s + 1 == n_slots ? 0 : s + 1;
-    }
-}
 
 __device__ __forceinline__ uint64_t caps_value(uint32_t c16) { return c16 == 0xFFFFu ? (1ull << 32) : (uint64_t) c16; }
 
@@ -165,7 +141,7 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
                     for (int j = 0; j < 6; j++) k[j] = ws.keyw[j];
                     const uint64_t tokh = token_hash(lenw, k);
                     if (alive) {
-                        alive = probe(p.slots, p.n_slots, node, lenw, k, tokh, cw, cid);
+                        alive = probe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh, cw, cid);
                         node = cid;
                     }
                 }
@@ -452,7 +428,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 uint32_t cw[16], cid = 0;
                 if (alive) {
                     uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
-                    alive = probe(p.slots, p.n_slots, node, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
+                    alive = probe(p.slots, p.tags, p.n_blocks, node, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
                 }
                 bool push_c = false, push_p = false;
                 if (alive) {

@@ -26,9 +26,10 @@ constexpr uint32_t SPAN_COUNT_MASK = 0x3FFFFFFFu;
 
 struct MatchParams {
     // index snapshot
-    const Slot* slots;
+    const Slot* slots;              // blocked edge table (trie_layout.h)
+    const uint4* tags;              // one 16-byte tag word per block
     const Slot* roots;
-    uint32_t n_slots;
+    uint32_t n_blocks;
     // topic batch
     const uint8_t* topics;          // blob
     const int64_t* topic_off;       // [n+1]

@@ -35,6 +35,7 @@
 #include "../../include/bfq_gpumatch.h"
 #include "codec.h"
 #include "trie_layout.h"
+#include "hash_probe.cuh"
 
 using namespace bfq;
 
@@ -68,7 +69,8 @@ enum : int { RC_RANGES = 0, RC_OVERFLOW = 1, RC_ERROR = 2, RC_COUNT = 4 };
 struct RMatchParams {
     const RNode* nodes;
     const Slot* slots;
-    uint32_t n_slots;
+    const uint4* tags;
+    uint32_t n_blocks;
     const uint8_t* filters;
     const int64_t* filter_off;
     const int32_t* filter_tenant;
@@ -110,17 +112,10 @@ __device__ __forceinline__ RNode load_node(const RNode* n) {
 }
 
 // (parent, lenw, k) -> child id, or NONE
-__device__ __forceinline__ uint32_t rprobe(const Slot* slots, uint32_t n_slots, uint32_t parent, uint32_t lenw,
+__device__ __forceinline__ uint32_t rprobe(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t parent, uint32_t lenw,
                                            const uint32_t (&k)[6], uint64_t tokh) {
-    uint32_t s = home_slot(tokh, parent, n_slots);
-    while (true) {
-        const uint4* p = reinterpret_cast<const uint4*>(slots + s);
-        const uint4 a = __ldg(p), b = __ldg(p + 1);
-        if (a.x == EMPTY_PARENT) return NONE;
-        if (a.x == parent && a.y == lenw && a.z == k[0] && a.w == k[1] && b.x == k[2] && b.y == k[3] && b.z == k[4] && b.w == k[5])
-            return __ldg(reinterpret_cast<const uint32_t*>(slots + s) + W_PLUS);
-        s = s + 1 == n_slots ? 0 : s + 1;
-    }
+    uint32_t w[16], slot = 0;
+    return probe(slots, tags, n_blocks, parent, lenw, k, tokh, w, slot) ? w[W_PLUS] : NONE;
 }
 
 template <bool kBig>
@@ -310,7 +305,7 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
                             for (int q = 0; q < 6; q++) k[q] = ws.keyw[q];
                             const uint64_t tokh = token_hash(lenw, k);
                             if (alive) {
-                                node = rprobe(p.slots, p.n_slots, node, lenw, k, tokh);
+                                node = rprobe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh);
                                 alive = node != NONE;
                             }
                         }
@@ -461,10 +456,11 @@ struct bfq_rindex {
     bool have_snapshot = false;
     // snapshot
     std::unordered_map<std::string, int32_t> tenant_root;
-    uint32_t n_slots = 0;
+    uint32_t n_blocks = 0;
     int64_t n_nodes = 0, max_nodes_per_depth = 0, n_topics = 0;
     DBuf<RNode> d_nodes;
     DBuf<Slot> d_slots;
+    DBuf<uint8_t> d_tags;
     DBuf<int64_t> d_dfs_to_id, d_bfs_to_id;
     // workspace
     DBuf<uint8_t> d_filters, d_scan_tmp;
@@ -477,7 +473,7 @@ struct bfq_rindex {
 
     ~bfq_rindex() {
         cudaSetDevice(device);
-        d_nodes.release(); d_slots.release(); d_dfs_to_id.release(); d_bfs_to_id.release(); d_filters.release();
+        d_nodes.release(); d_slots.release(); d_tags.release(); d_dfs_to_id.release(); d_bfs_to_id.release(); d_filters.release();
         d_scan_tmp.release(); d_filter_off.release(); d_limit.release(); d_ids.release(); d_filter_tenant.release();
         d_tenant_root.release(); d_span_begin.release(); d_span_count.release(); d_overflow.release(); d_total.release();
         d_kept.release(); d_offsets.release(); d_counters.release(); d_ranges.release(); d_scratch.release();
@@ -637,38 +633,32 @@ int32_t rebuild(bfq_rindex* h) {
             edges.push_back(e);
         }
     }
-    const uint64_t want = std::max<uint64_t>(1024, (uint64_t) edges.size() * 2);
-    if (want >= 0x7FFFFFF0ull) return rfail(BFQ_E_RANGE, "topic index too large");
-    std::vector<Slot> slots((size_t) want);
-    for (auto& s : slots) {
-        memset(s.w, 0, sizeof(s.w));
-        s.w[W_PARENT] = EMPTY_PARENT;
-    }
-    const uint32_t n_slots = (uint32_t) want;
+    if (((uint64_t) edges.size() * 2 / BLOCK_USABLE + 64) * BLOCK_SLOTS >= 0x7FFFFFF0ull) return rfail(BFQ_E_RANGE, "topic index too large");
+    EdgeTable table;
+    table.init(edges.size());
     for (const Edge& e : edges) {
-        uint32_t s = home_slot(token_hash(e.lenw, e.tok), e.parent, n_slots);
-        while (slots[s].w[W_PARENT] != EMPTY_PARENT) s = s + 1 == n_slots ? 0 : s + 1;
-        slots[s].w[W_PARENT] = e.parent;
-        slots[s].w[W_LEN] = e.lenw;
-        for (uint32_t k = 0; k < TOKEN_WORDS; k++) slots[s].w[W_TOK + k] = e.tok[k];
-        slots[s].w[W_PLUS] = e.child;
+        const uint32_t s = table.place(e.parent, e.lenw, e.tok);
+        table.slots[s].w[W_PLUS] = e.child;
     }
+    std::vector<Slot>& slots = table.slots;
     // ---- upload
     RCUDA_TRY(cudaSetDevice(h->device));
     RCUDA_TRY(cudaStreamSynchronize(h->stream));
     RCUDA_TRY(h->d_nodes.reserve(rn.size()));
     RCUDA_TRY(h->d_slots.reserve(slots.size()));
+    RCUDA_TRY(h->d_tags.reserve(table.tags.size()));
     RCUDA_TRY(h->d_dfs_to_id.reserve(std::max<size_t>(dfs_to_id.size(), 1)));
     RCUDA_TRY(h->d_bfs_to_id.reserve(std::max<size_t>(bfs_to_id.size(), 1)));
     RCUDA_TRY(cudaMemcpy(h->d_nodes.p, rn.data(), rn.size() * sizeof(RNode), cudaMemcpyHostToDevice));
     RCUDA_TRY(cudaMemcpy(h->d_slots.p, slots.data(), slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    RCUDA_TRY(cudaMemcpy(h->d_tags.p, table.tags.data(), table.tags.size(), cudaMemcpyHostToDevice));
     if (!dfs_to_id.empty()) {
         RCUDA_TRY(cudaMemcpy(h->d_dfs_to_id.p, dfs_to_id.data(), dfs_to_id.size() * 8, cudaMemcpyHostToDevice));
         RCUDA_TRY(cudaMemcpy(h->d_bfs_to_id.p, bfs_to_id.data(), bfs_to_id.size() * 8, cudaMemcpyHostToDevice));
     }
     h->tenant_root.clear();
     for (const auto& e : root_of) h->tenant_root[e.first] = (int32_t) nodes[e.second].bfs;
-    h->n_slots = n_slots;
+    h->n_blocks = table.n_blocks;
     h->n_nodes = (int64_t) N;
     h->n_topics = (int64_t) dfs_to_id.size();
     h->max_nodes_per_depth = max_depth_nodes;
@@ -811,7 +801,8 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     RMatchParams p{};
     p.nodes = h->d_nodes.p;
     p.slots = h->d_slots.p;
-    p.n_slots = h->n_slots;
+    p.tags = reinterpret_cast<const uint4*>(h->d_tags.p);
+    p.n_blocks = h->n_blocks;
     p.filters = h->d_filters.p;
     p.filter_off = h->d_filter_off.p;
     p.filter_tenant = h->d_filter_tenant.p;

@@ -1,9 +1,19 @@
 // trie_layout.h — HBM layout of the forward index, shared by the host builder and the kernels.
 //
-// The per-tenant filter tries are flattened into ONE open-addressing hash table of 64-byte slots,
-// keyed by (parent node id, level token). A slot is the child NODE RECORD itself, so following an
-// exact edge costs a single 64 B (one DRAM burst, two 32 B sectors) random access and no separate
-// node fetch. Node id == slot index; tenant roots live in a small side array (id = ROOT_BASE + ordinal).
+// The per-tenant filter tries are flattened into ONE hash table of 64-byte slots keyed by (parent node id,
+// level token). A slot is the child NODE RECORD itself, so following an exact edge costs a single 64 B
+// (two 32 B sectors) random access and no separate node fetch. Node id == slot index; tenant roots live in
+// a small side array (id = ROOT_BASE + ordinal).
+//
+// The table is BLOCKED and TAG-FILTERED (Swiss-table style): slots are grouped in blocks of 16 (15 usable),
+// and a parallel 16-byte tag word per block holds one fingerprint byte per slot (0 = free, 2..255 = fingerprint
+// of the slot's key) plus a control byte (byte 15: 1 = the block overflowed into the next one). An edge hashes
+// to ONE block; a lookup loads that block's 16 tags (the tag array is ~1/64 of the table and mostly L2
+// resident), SWAR-compares them with the key's fingerprint and loads only the slot(s) whose tag matches:
+//   hit  = 1 tag load (L2) + 1 slot load (HBM);  miss = 1 tag load, NO slot load (3% false positives);
+// and — what matters for one-lane-per-topic SIMT — the number of dependent memory round trips per lookup is
+// constant. (The first version used linear probing over the slots themselves: ncu showed a warp step waiting
+// for its longest probe chain, ~7 serial HBM round trips with 3 of 32 lanes active; profiles/r1_v3_*.)
 //
 //   word  0      parent node id              (EMPTY_PARENT = free slot)
 //   word  1      token length in bytes       (LEN_PLUS for the '+' child, LEN_CONT|j for the j-th
@@ -70,9 +80,81 @@ BFQ_HD uint64_t token_hash(uint32_t lenw, const uint32_t* k /*[6]*/) {
     h += (uint64_t) k[5] * 0xE7037ED1A0B428DBull;
     return h;
 }
-BFQ_HD uint32_t home_slot(uint64_t tokh, uint32_t parent, uint32_t n_slots) {
-    uint64_t h = fmix64(tokh + (uint64_t) parent * 0xC2B2AE3D27D4EB4Full);
-    return (uint32_t) (((h >> 32) * (uint64_t) n_slots) >> 32);
+constexpr uint32_t BLOCK_SLOTS = 16;     // slots per block (slot 15 of every block is never used)
+constexpr uint32_t BLOCK_USABLE = 15;
+constexpr uint32_t TAG_CTRL = 15;        // control byte index inside the 16-byte tag word
+
+BFQ_HD uint64_t edge_hash(uint64_t tokh, uint32_t parent) { return fmix64(tokh + (uint64_t) parent * 0xC2B2AE3D27D4EB4Full); }
+BFQ_HD uint32_t home_block(uint64_t h, uint32_t n_blocks) { return (uint32_t) (((h >> 32) * (uint64_t) n_blocks) >> 32); }
+BFQ_HD uint32_t fingerprint(uint64_t h) {
+    const uint32_t f = (uint32_t) (h & 0xFFu);
+    return f < 2u ? f + 2u : f;          // 0 = free slot, 1 is reserved for the control byte
 }
 
+}  // namespace bfq
+
+// ---- host-side placement shared by the forward and the inverse index builders
+#include <vector>
+namespace bfq {
+struct EdgeTable {
+    std::vector<Slot> slots;        // n_blocks * BLOCK_SLOTS
+    std::vector<uint8_t> tags;      // n_blocks * 16
+    uint32_t n_blocks = 0;
+    int64_t overflowed_blocks = 0;
+
+    void init(uint64_t n_edges) {
+        // target load 0.5 of the usable slots
+        uint64_t nb = (n_edges * 2 + BLOCK_USABLE - 1) / BLOCK_USABLE;
+        if (nb < 64) nb = 64;
+        n_blocks = (uint32_t) nb;
+        slots.assign((size_t) n_blocks * BLOCK_SLOTS, Slot());
+        for (auto& sl : slots) {
+            for (auto& w : sl.w) w = 0;
+            sl.w[W_PARENT] = EMPTY_PARENT;
+        }
+        tags.assign((size_t) n_blocks * 16, 0);
+    }
+    // claims a slot for the edge key and returns its index (the caller fills the payload)
+    uint32_t place(uint32_t parent, uint32_t lenw, const uint32_t* tok) {
+        const uint64_t h = edge_hash(token_hash(lenw, tok), parent);
+        uint32_t b = home_block(h, n_blocks);
+        const uint8_t fp = (uint8_t) fingerprint(h);
+        while (true) {
+            uint8_t* tg = &tags[(size_t) b * 16];
+            for (uint32_t j = 0; j < BLOCK_USABLE; j++) {
+                if (tg[j] == 0) {
+                    tg[j] = fp;
+                    const uint32_t s = b * BLOCK_SLOTS + j;
+                    slots[s].w[W_PARENT] = parent;
+                    slots[s].w[W_LEN] = lenw;
+                    for (uint32_t k = 0; k < TOKEN_WORDS; k++) slots[s].w[W_TOK + k] = tok[k];
+                    return s;
+                }
+            }
+            if (tg[TAG_CTRL] == 0) {
+                tg[TAG_CTRL] = 1;
+                overflowed_blocks++;
+            }
+            b = b + 1 == n_blocks ? 0 : b + 1;
+        }
+    }
+    // host-side lookup (self-check only): slot index or NONE
+    uint32_t find(uint32_t parent, uint32_t lenw, const uint32_t* tok) const {
+        const uint64_t h = edge_hash(token_hash(lenw, tok), parent);
+        uint32_t b = home_block(h, n_blocks);
+        const uint8_t fp = (uint8_t) fingerprint(h);
+        while (true) {
+            const uint8_t* tg = &tags[(size_t) b * 16];
+            for (uint32_t j = 0; j < BLOCK_USABLE; j++) {
+                if (tg[j] != fp) continue;
+                const Slot& sl = slots[(size_t) b * BLOCK_SLOTS + j];
+                bool eq = sl.w[W_PARENT] == parent && sl.w[W_LEN] == lenw;
+                for (uint32_t k = 0; k < TOKEN_WORDS && eq; k++) eq = sl.w[W_TOK + k] == tok[k];
+                if (eq) return b * BLOCK_SLOTS + j;
+            }
+            if (tg[TAG_CTRL] == 0) return NONE;
+            b = b + 1 == n_blocks ? 0 : b + 1;
+        }
+    }
+};
 }  // namespace bfq
