@@ -23,6 +23,11 @@ __device__ __forceinline__ uint32_t match_bytes(uint32_t w, uint32_t fp4) {
     return (y - 0x01010101u) & ~y & 0x80808080u;
 }
 
+// 0x80 flags in bytes 0..3 -> bits 0..3
+__device__ __forceinline__ uint32_t nibble(uint32_t m) {
+    return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+}
+
 // Lookup of the edge (parent, lenw, k[0..5]). On success `w` holds the child record and `slot` its index.
 __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t parent, uint32_t lenw,
                                       const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
@@ -31,22 +36,21 @@ __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint
     const uint32_t fp4 = fingerprint(h) * 0x01010101u;
     while (true) {
         const uint4 tg = __ldg(tags + b);
-        const uint32_t tw[4] = {tg.x, tg.y, tg.z, tg.w & 0x00FFFFFFu};   // byte 15 is the control byte
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t m = match_bytes(tw[q], fp4);
-            while (m) {
-                const uint32_t j = 4u * q + ((__ffs(m) - 1) >> 3);
-                m &= m - 1;
-                const uint32_t s = b * BLOCK_SLOTS + j;
-                if (j < BLOCK_USABLE) {
-                    load_slot(slots + s, w);
-                    if (w[W_PARENT] == parent && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] &&
-                        w[5] == k[3] && w[6] == k[4] && w[7] == k[5]) {
-                        slot = s;
-                        return true;
-                    }
-                }
+        // 16-bit candidate mask over the block's tags (bit j = tag j matches); byte 15 is the control byte.
+        // All candidates are then tried from ONE loop so that every lane's slot load is issued at the same place
+        // (a per-word candidate loop serialises the lanes by the word their match sits in: 4 HBM round trips).
+        uint32_t cand = nibble(match_bytes(tg.x, fp4)) | (nibble(match_bytes(tg.y, fp4)) << 4) |
+                        (nibble(match_bytes(tg.z, fp4)) << 8) | (nibble(match_bytes(tg.w & 0x00FFFFFFu, fp4)) << 12);
+        cand &= 0x7FFFu;
+        while (cand) {
+            const uint32_t j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint32_t s = b * BLOCK_SLOTS + j;
+            load_slot(slots + s, w);
+            if (w[W_PARENT] == parent && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] &&
+                w[5] == k[3] && w[6] == k[4] && w[7] == k[5]) {
+                slot = s;
+                return true;
             }
         }
         if ((tg.w >> 24) == 0) return false;   // the block never overflowed: the edge does not exist

@@ -280,11 +280,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 // is handed, whole, to the warp-per-topic tier through defer_list.
 constexpr int L_WARPS = 4;
 constexpr int L_MAXLV = 16;
-constexpr int L_CHUNK = 128;
+constexpr int L_CHUNK = 64;
 
 struct LaneSmem {
     uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
     uint2 stk[L_MAXLV + 1][32];     // parked '+' branch per level: {node id, plus | has_exact << 31}
+    // metadata of the warp's current chunk of topics, loaded cooperatively (coalesced) when the chunk is claimed
+    uint32_t m_off[L_CHUNK];        // byte offset relative to the chunk's first topic
+    uint32_t m_len[L_CHUNK];
+    int32_t m_tenant[L_CHUNK];
+    int32_t m_root[L_CHUNK];        // root ordinal of the topic's tenant, or -1
 };
 
 __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
@@ -294,10 +299,10 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     const uint32_t lt_mask = (1u << lane) - 1;
     const int64_t n = p.n_topics;
 
-    // warp-uniform work cursor
-    int64_t next = 0, end = 0;
+    // warp-uniform work cursor over the current chunk [cstart, end)
+    int64_t next = 0, end = 0, cstart = 0, cbase = 0;
     bool exhausted = false;
-    // per-lane topic state
+    // per-lane topic state; level < 0: the tenant root has not been expanded yet (`node` holds the root ordinal)
     bool have = false, bad = false;
     uint32_t t = 0, node = 0, plusf = NONE31, pending = 0, n_rg = 0, acc_r = 0;
     uint64_t acc_p = 0, acc_g = 0;
@@ -346,8 +351,19 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 if ((int64_t) c >= n) {
                     exhausted = true;
                 } else {
-                    next = (int64_t) c;
+                    cstart = next = (int64_t) c;
                     end = min(n, next + L_CHUNK);
+                    cbase = p.topic_off[cstart];
+                    __syncwarp();
+                    for (int i = lane; i < (int) (end - cstart); i += 32) {
+                        const int64_t o = p.topic_off[cstart + i], o2 = p.topic_off[cstart + i + 1];
+                        const int tn = p.topic_tenant[cstart + i];
+                        ws.m_off[i] = (uint32_t) (o - cbase);
+                        ws.m_len[i] = (uint32_t) min((int64_t) 0x7FFFFFFF, o2 - o);
+                        ws.m_tenant[i] = tn;
+                        ws.m_root[i] = p.tenant_root[tn];
+                    }
+                    __syncwarp();
                 }
             }
             if (next < end) {
@@ -355,39 +371,30 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 const bool take = !have && idx < end;
                 next = min(end, next + (int64_t) __popc(idle));
                 if (take) {
+                    const int i = (int) (idx - cstart);
                     t = (uint32_t) idx;
-                    my_off = p.topic_off[idx];
-                    const int64_t l64 = p.topic_off[idx + 1] - my_off;
-                    len = (int) l64;
-                    tenant = p.topic_tenant[idx];
-                    const int root_ord = p.tenant_root[tenant];
-                    n_rg = 0; acc_r = 0; acc_p = 0; acc_g = 0; pending = 0; level = 0;
-                    bad = l64 > 65535;
+                    my_off = cbase + (int64_t) ws.m_off[i];
+                    len = (int) ws.m_len[i];
+                    tenant = ws.m_tenant[i];
+                    const int root_ord = ws.m_root[i];
+                    n_rg = 0; acc_r = 0; acc_p = 0; acc_g = 0; pending = 0;
+                    bad = len > 65535;
                     have = true;
                     ws.lv[0][lane] = 0;
-                    bool start = false;
-                    if (root_ord >= 0 && !bad) {
-                        uint32_t rw[16];
-                        load_slot(p.roots + root_ord, rw);
-                        const bool sys = len > 0 && p.topics[my_off] == '$';
-                        if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
-                        const uint32_t plus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
-                        const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
-                        if (has_exact || plus != NONE31) {
-                            node = ROOT_BASE + (uint32_t) root_ord;
-                            plusf = plus | (has_exact ? 0x80000000u : 0u);
-                            start = true;
-                        }
-                    }
-                    if (!start) finish();
+                    level = -1;
+                    node = (uint32_t) root_ord;
+                    plusf = NONE31;
+                    if (root_ord < 0 || bad) finish();   // tenant without routes: an empty result; oversized: tier 1
                 }
             } else if (idle == FULL) {
                 break;   // nothing left to claim and every lane is done
             }
         }
         if (have) {
-            // ---- one DFS step: expand `node` along level `level`
-            const int s = ws.lv[level][lane];
+            // ---- one DFS step. level < 0: expand the tenant root (its record is loaded where a '+' child would be)
+            const bool rootstep = level < 0;
+            const int lvl = rootstep ? 0 : level;
+            const int s = ws.lv[lvl][lane];
             const int rem = len - s;
             // 28 bytes at the level start: aligned words + funnel shift (words at/after the topic end are not read)
             const uint64_t a = (uint64_t) (uintptr_t) p.topics + (uint64_t) my_off + (uint64_t) s;
@@ -397,9 +404,15 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             uint32_t x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) x[j] = (wp + j) < wend ? __ldg(wp + j) : 0u;
+            // the '+' child (or the tenant root) record: independent of the token, issue its load right away
+            const uint32_t plus = plusf & NONE31;
+            const bool has_plus = rootstep || plus != NONE31;
+            uint32_t pw[16];
+            if (has_plus) load_slot(rootstep ? p.roots + node : p.slots + plus, pw);
             uint32_t k[7];
 #pragma unroll
             for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            const uint32_t first_byte = k[0] & 0xFFu;
             // first '/' within the 28 bytes (SWAR zero-byte test on w ^ "////")
             int q = 28;
 #pragma unroll
@@ -410,7 +423,19 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             }
             const int tlen = min(q, rem);
             const bool last = tlen == rem;
-            if (tlen > (int) TOKEN_BYTES || (!last && level >= L_MAXLV - 1)) {
+            if (rootstep) {
+                const bool sys = len > 0 && first_byte == '$';   // '+' and '#' at the first level skip '$' topics
+                if (!sys && pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_FLAGS] & FLAG_HASH_MULTI, pw[W_HASH_CAPS]);
+                const uint32_t rplus = (sys || pw[W_PLUS] == NONE) ? NONE31 : pw[W_PLUS];
+                const uint32_t has_exact = pw[W_FLAGS] & FLAG_HAS_EXACT;
+                if ((has_exact || rplus != NONE31) && !bad) {
+                    node = ROOT_BASE + node;
+                    plusf = rplus | (has_exact ? 0x80000000u : 0u);
+                    level = 0;
+                } else {
+                    finish();
+                }
+            } else if (tlen > (int) TOKEN_BYTES || (!last && level >= L_MAXLV - 1)) {
                 bad = true;   // a level longer than the inline key, or deeper than the level table: tier 1 takes it
                 finish();
             } else {
@@ -420,10 +445,6 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     const int vb = tlen - 4 * j;
                     k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
                 }
-                const uint32_t plus = plusf & NONE31;
-                const bool has_plus = plus != NONE31;
-                uint32_t pw[16];
-                if (has_plus) load_slot(p.slots + plus, pw);
                 bool alive = plusf >> 31;
                 uint32_t cw[16], cid = 0;
                 if (alive) {
@@ -581,6 +602,8 @@ void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStrea
     }
     // persistent grid: a whole number of waves (SM count x resident CTAs per SM), grid-stride over topics
     int64_t ctas = (int64_t) sms * ctas_per_sm;
+    // chained behind tier 0 (n_work < 0: count read on the device) the deferral list is short: one CTA per SM
+    if (p.work_list && p.n_work < 0) ctas = sms;
     const int64_t items = p.work_list ? (p.n_work >= 0 ? p.n_work : p.n_topics) : p.n_topics;
     const int64_t need = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (need < ctas) ctas = need < 1 ? 1 : need;
