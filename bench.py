@@ -287,13 +287,9 @@ def main():
     h2d_bytes = blob_bytes + 8 * (n + 1) + 4 * n
 
     # ---- whole-job numbers: MAX over ranks of the time, SUM over ranks of the topics
-    tot = torch.tensor([total_ms, e2e_total * 1000.0], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max = tot.tolist()
-    topics_all = cnt.item()
+    from bifromq_b200 import dist as D
+    total_ms_max, topics_all = D.aggregate(total_ms, n, dev)
+    e2e_ms_max, _ = D.aggregate(e2e_total * 1000.0, n, dev)
     value = topics_all * args.steps / (total_ms_max / 1000.0)
     e2e_value = topics_all * args.steps / (e2e_ms_max / 1000.0)
 

@@ -1,0 +1,88 @@
+"""N > 1 logic on CPU: two gloo ranks each own the tenants fnv1a64(tenant) % 2 == rank, match their shard with the
+oracle (no GPU here), and the aggregated result equals the single-process run."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import oracle_lib as O
+    from bifromq_b200 import dist as D
+    from bifromq_b200.workload import Workload
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = Workload("C3", scale=0.004, shard_index=rank, shard_count=world)
+    assert all(D.tenant_shard(t, world) == rank for t in w.tenants)
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    tb, toff = O.blob(w.tenants)
+    out = kv.match_blobs(tb, toff, w.topics, w.topic_off, np.ascontiguousarray(w.topic_tenant), w.n_topics, 2 ** 31 - 1, 100,
+                         O.MODE_TRIE, False, 1)
+    routes = int(np.diff(out.offsets).sum())
+    # a fake per-rank time: rank r "took" (r + 1) * 10 ms -> whole-job time is the max
+    ms, units = D.aggregate((rank + 1) * 10.0, w.n_topics)
+    _, total_routes = D.aggregate(0.0, routes)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, w.n_topics, routes, ms, units, total_routes, sorted(w.tenants)))
+
+
+def test_two_rank_tenant_sharding_matches_single_process():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from bifromq_b200 import dist as D
+    from bifromq_b200.workload import Workload
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = Workload("C3", scale=0.004)
+    kv = O.KV()
+    kv.load(full.keys, full.key_off, full.vals, full.val_off)
+    tb, toff = O.blob(full.tenants)
+    out = kv.match_blobs(tb, toff, full.topics, full.topic_off, np.ascontiguousarray(full.topic_tenant), full.n_topics,
+                         2 ** 31 - 1, 100, O.MODE_TRIE, False, 2)
+    total_routes = int(np.diff(out.offsets).sum())
+    assert sum(r[1] for r in results) == full.n_topics
+    assert sum(r[2] for r in results) == total_routes
+    for r in results:
+        assert r[3] == 20.0                      # MAX over ranks of the per-rank time
+        assert r[4] == float(full.n_topics)      # SUM over ranks of the units
+        assert r[5] == float(total_routes)
+    assert sorted(results[0][6] + results[1][6]) == sorted(full.tenants)
+    # the batch splitter used by a front-end agrees with the generator's shard function
+    parts = D.split_batch_by_owner(full.tenants, full.topic_tenant[:full.n_topics], 2)
+    assert [len(p) for p in parts] == [results[0][1], results[1][1]]
+
+
+def test_fnv1a64_known_answers():
+    from bifromq_b200 import dist as D
+    assert D.fnv1a64(b"") == 0xCBF29CE484222325
+    assert D.fnv1a64(b"a") == 0xAF63DC4C8601EC8C
+    assert D.fnv1a64("foobar") == 0x85944171F73967E8
