@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -96,6 +97,7 @@ struct bfq_index {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};
     double last_kernel_ms = 0;
+    size_t l2_window_bytes = 0;
     // snapshot on device
     DevBuf<Slot> d_slots, d_roots;
     DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
@@ -199,6 +201,16 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     p.flagged_list = h->d_flagged.p;
     p.counters = h->d_counters.p;
 
+    if (h->l2_window_bytes > 0) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = h->d_tags.p;
+        attr.accessPolicyWindow.num_bytes = h->l2_window_bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     unsigned long long* hc = h->h_counters.p;
     for (int attempt = 0; attempt < 8; attempt++) {
         p.ranges = h->d_ranges.p;
@@ -404,6 +416,20 @@ int32_t bfq_index_commit(bfq_index* h) {
     h->flat = std::move(flat);
     h->committed = kv;
     h->have_snapshot = true;
+    // Keep the tag array resident in L2 (persisting access window): every lookup starts with a tag read and the
+    // array (~1/64 of the table) competes for L2 with the streaming slot traffic. BFQ_L2PERSIST=0 disables.
+    {
+        const char* e = getenv("BFQ_L2PERSIST");
+        h->l2_window_bytes = 0;
+        if (!e || atoi(e) != 0) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+            size_t want = std::min<size_t>(h->d_tags.bytes(), std::min<size_t>((size_t) max_persist, (size_t) max_window));
+            if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_window_bytes = want;
+            cudaGetLastError();
+        }
+    }
     return BFQ_OK;
 }
 

@@ -19,6 +19,8 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 namespace bfq {
 
 namespace {
@@ -292,6 +294,7 @@ struct LaneSmem {
     int32_t m_root[L_CHUNK];        // root ordinal of the topic's tenant, or -1
 };
 
+template <bool kRootStep, bool kPrefetch>
 __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
     __shared__ LaneSmem sm[L_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -364,6 +367,13 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                         ws.m_root[i] = p.tenant_root[tn];
                     }
                     __syncwarp();
+                    if (kPrefetch) {
+                        // pull the chunk's topic bytes towards L2 now: the first key read of each topic would
+                        // otherwise be a compulsory HBM miss in the middle of a lock-step warp step
+                        const int64_t cend = p.topic_off[end];
+                        for (int64_t o = cbase + (int64_t) lane * 128; o < cend; o += 32 * 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.topics + o));
+                    }
                 }
             }
             if (next < end) {
@@ -384,7 +394,24 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     level = -1;
                     node = (uint32_t) root_ord;
                     plusf = NONE31;
-                    if (root_ord < 0 || bad) finish();   // tenant without routes: an empty result; oversized: tier 1
+                    if (root_ord < 0 || bad) {
+                        finish();   // tenant without routes: an empty result; oversized: tier 1
+                    } else if (!kRootStep) {
+                        // expand the tenant root right here instead of spending a lock-step DFS step on it
+                        uint32_t rw[16];
+                        load_slot(p.roots + root_ord, rw);
+                        const bool sys = len > 0 && p.topics[my_off] == '$';
+                        if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
+                        const uint32_t rplus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
+                        const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
+                        if ((has_exact || rplus != NONE31) && !bad) {
+                            node = ROOT_BASE + (uint32_t) root_ord;
+                            plusf = rplus | (has_exact ? 0x80000000u : 0u);
+                            level = 0;
+                        } else {
+                            finish();
+                        }
+                    }
                 }
             } else if (idle == FULL) {
                 break;   // nothing left to claim and every lane is done
@@ -392,7 +419,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
         }
         if (have) {
             // ---- one DFS step. level < 0: expand the tenant root (its record is loaded where a '+' child would be)
-            const bool rootstep = level < 0;
+            const bool rootstep = kRootStep && level < 0;
             const int lvl = rootstep ? 0 : level;
             const int s = ws.lv[lvl][lane];
             const int rem = len - s;
@@ -614,27 +641,24 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, match_topics_lane_kernel, L_WARPS * 32, 0);
+    // experiment switches (defaults are the measured best): BFQ_ROOTSTEP=0/1, BFQ_PREFETCH=0/1
+    static int variant = -1, ctas_per_sm = 0;
+    typedef void (*kern_t)(const MatchParams);
+    static const kern_t kerns[4] = {match_topics_lane_kernel<false, false>, match_topics_lane_kernel<false, true>,
+                                    match_topics_lane_kernel<true, false>, match_topics_lane_kernel<true, true>};
+    if (variant < 0) {
+        const char* rs = getenv("BFQ_ROOTSTEP");
+        const char* pf = getenv("BFQ_PREFETCH");
+        const int rootstep = rs ? atoi(rs) : 0, prefetch = pf ? atoi(pf) : 1;
+        variant = (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    // persistent grid (SM count x resident CTAs); warps claim 128-topic chunks with one atomicAdd each
+    // persistent grid (SM count x resident CTAs); warps claim 64-topic chunks with one atomicAdd each
     int64_t ctas = (int64_t) sms * ctas_per_sm;
     const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;
-    match_topics_lane_kernel<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
-}
-
-cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream) {
-    if (!d_scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
-    if (p.n_topics <= 0) return cudaSuccess;
-    const unsigned blocks = (unsigned) ((p.n_topics + 255) / 256);
-    compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
-    if (e != cudaSuccess) return e;
-    compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
-    return cudaGetLastError();
+    kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
 }
 
 void launch_caps(const CapsParams& p, cudaStream_t stream) {
