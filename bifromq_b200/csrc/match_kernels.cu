@@ -661,6 +661,17 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
 }
 
+cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream) {
+    if (!d_scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
+    if (p.n_topics <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned) ((p.n_topics + 255) / 256);
+    compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
+    if (e != cudaSuccess) return e;
+    compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 void launch_caps(const CapsParams& p, cudaStream_t stream) {
     if (p.n_flagged <= 0) return;
     caps_kernel<<<(unsigned) p.n_flagged, CAPS_THREADS, 0, stream>>>(p);
