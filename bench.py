@@ -313,7 +313,12 @@ def main():
                 pass
             peak = float(peaks.get("hbm_gbs", 6650.0))
             achieved = per_topic * n / (k_ms / 1000.0) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            traffic = None
+            try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+                traffic = _j.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                     "kernel": "match_topics_lane_kernel (tier 0, one lane per topic)", "kernel_ms": k_ms, "alg_bytes_per_topic": per_topic,
                     "alg_counters_per_topic": {"V": st["V"] / ns, "P": st["P"] / ns, "ranges": st["ranges"] / ns, "R": st["R"] / ns},

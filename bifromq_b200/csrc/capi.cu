@@ -472,6 +472,7 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
                           flat.max_nodes_per_depth, flat.max_tenant_nodes, flat.n_multi, flat.n_cont_chunks};
     for (int32_t i = 0; i < n_stats && i < 8; i++) stats[i] = v[i];
     if (n_stats > 8) stats[8] = flat.overflowed_blocks;
+    for (int32_t i = 9; i < n_stats && i < 9 + 5; i++) stats[i] = flat.child_hist[i - 9];
     return BFQ_OK;
 }
 

@@ -367,6 +367,12 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
         rec->w[W_PLUS] = id_of[nd.plus];
     }
     if (out->segs.empty()) out->segs.assign(2, 0);
+    {
+        std::vector<uint32_t> nchild(total_nodes, 0);
+        for (size_t i = 0; i < total_nodes; i++)
+            if (b.nodes[i].parent != NONE && b.nodes[i].lenw != LEN_PLUS) nchild[b.nodes[i].parent]++;
+        for (size_t i = 0; i < total_nodes; i++) out->child_hist[std::min<uint32_t>(nchild[i], 4)]++;
+    }
     out->n_blocks = table.n_blocks;
     out->n_slots = table.n_blocks * BLOCK_SLOTS;
     out->overflowed_blocks = table.overflowed_blocks;

@@ -42,6 +42,7 @@ struct FlatIndex {
     int64_t n_routes = 0, n_nodes = 0, max_nodes_per_depth = 0, max_tenant_nodes = 0, n_multi = 0, n_cont_chunks = 0;
     uint32_t n_slots = 0, n_blocks = 0;
     int64_t overflowed_blocks = 0;
+    int64_t child_hist[5] = {0, 0, 0, 0, 0};   // nodes with 0, 1, 2, 3, >=4 exact children (diagnostic)
 };
 
 // Build the flat index from a sorted KV snapshot. Returns false and sets *err on undecodable input.
