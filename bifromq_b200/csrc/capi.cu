@@ -244,7 +244,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
             // ---- tier 2: per-warp global scratch sized from the index statistics (exact upper bounds)
             const uint64_t capF = (uint64_t) h->flat.max_nodes_per_depth + 2;
             const uint64_t capR = 2 * ((uint64_t) h->flat.max_tenant_nodes + 2) + 2;
-            const uint64_t per_warp = 2 * capF + capR;
+            const uint64_t per_warp = 4 * capF + capR;   // uint2 units: two frontier buffers of uint4 entries + ranges
             uint64_t warps = std::min<uint64_t>(hc[CTR_OVERFLOW], std::max<uint64_t>(8, (1ull << 31) / (per_warp * sizeof(uint2))));
             warps = std::min<uint64_t>(warps, 148 * 8);
             warps = (warps + 7) / 8 * 8;
@@ -453,7 +453,7 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
     FlatIndex flat;
     if (!build_flat_index(st.materialize(), &flat, &err)) return fail(BFQ_E_INVALID, err);
-    // self-check of the table: every occupied slot is found again through its tag block
+    // self-check: every placed node is found again from its parent's record the way the kernels look it up
     {
         EdgeTable t;
         t.slots = std::move(flat.slots);
@@ -464,7 +464,23 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
             const Slot& sl = t.slots[s];
             if (sl.w[W_PARENT] == EMPTY_PARENT) continue;
             used++;
-            if (t.find(sl.w[W_PARENT], sl.w[W_LEN], &sl.w[W_TOK]) != s) return fail(BFQ_E_STATE, "edge table lookup does not find a placed slot");
+            const uint32_t pid = sl.w[W_PARENT];
+            const Slot& pr = pid >= ROOT_BASE ? flat.roots[pid - ROOT_BASE] : t.slots[pid];
+            if (sl.w[W_LEN] == LEN_PLUS) {
+                if (pr.w[W_PLUS] != s) return fail(BFQ_E_STATE, "'+' child is not linked from its parent");
+                continue;
+            }
+            const uint32_t meta = pr.w[W_META];
+            if (!(meta & FLAG_HAS_EXACT)) return fail(BFQ_E_STATE, "parent of an exact child lacks HAS_EXACT");
+            uint32_t found;
+            if (meta & FLAG_BIG) {
+                found = t.find(pid, sl.w[W_LEN], &sl.w[W_TOK]);
+            } else {
+                const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(token_hash(sl.w[W_LEN], &sl.w[W_TOK]));
+                if (lg == 0 && (t32 & 0xFFFFu) != sd) return fail(BFQ_E_STATE, "single-child fingerprint mismatch");
+                found = pr.w[W_CHILD_BASE] + (lg ? child_index(t32, sd, lg) : 0u);
+            }
+            if (found != s) return fail(BFQ_E_STATE, "child lookup does not find a placed node");
         }
         if (used + (int64_t) flat.roots.size() != flat.n_nodes) return fail(BFQ_E_STATE, "node count mismatch");
     }

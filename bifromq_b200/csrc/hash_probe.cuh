@@ -58,4 +58,27 @@ __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint
     }
 }
 
+// Exact child of a node described by (a, meta): a = the node id for BIG nodes (global tag table), else the base of the
+// node's private child array (perfect hash: one access, hit or miss; single-child nodes filter by fingerprint first).
+__device__ __forceinline__ bool find_child(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t a, uint32_t meta,
+                                           uint32_t lenw, const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
+    if (meta & FLAG_BIG) return probe(slots, tags, n_blocks, a, lenw, k, tokh, w, slot);
+    const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(tokh);
+    uint32_t idx = 0;
+    if (lg == 0) {
+        if ((t32 & 0xFFFFu) != sd) return false;
+    } else {
+        idx = child_index(t32, sd, lg);
+    }
+    slot = a + idx;
+    load_slot(slots + slot, w);
+    return w[W_PARENT] != EMPTY_PARENT && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] && w[5] == k[3] &&
+           w[6] == k[4] && w[7] == k[5];
+}
+
+// the `a` word of a node: what find_child needs to address its children
+__device__ __forceinline__ uint32_t child_ref(uint32_t node_id, const uint32_t (&w)[16]) {
+    return (w[W_META] & FLAG_BIG) ? node_id : w[W_CHILD_BASE];
+}
+
 }  // namespace bfq

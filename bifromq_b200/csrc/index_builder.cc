@@ -303,25 +303,143 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     out->pfx_group[(size_t) n] = pg;
     out->n_cont_chunks = b.n_cont;
 
-    // ---- flatten: place every non-root node into the device hash table (parents precede children)
+    // ---- flatten. Exact children of a node go either into a private perfect-hashed array (small fan-out) or into the
+    // global tag table (big fan-out); '+' children get a slot of their own. Nodes are laid out in BFS order so a parent's
+    // id is known before its children are keyed, and siblings are adjacent in memory.
     const size_t total_nodes = b.nodes.size();
     const size_t n_roots = out->tenant_ordinal.size();
-    const size_t n_table = total_nodes - n_roots;
     out->n_nodes = (int64_t) total_nodes;
-    EdgeTable table;
+    // group the exact children by parent (counting sort)
+    std::vector<uint32_t> child_off(total_nodes + 1, 0);
+    for (size_t i = 0; i < total_nodes; i++) {
+        const BNode& nd = b.nodes[i];
+        if (nd.parent != NONE && nd.lenw != LEN_PLUS) child_off[nd.parent + 1]++;
+    }
+    for (size_t i = 0; i < total_nodes; i++) child_off[i + 1] += child_off[i];
+    std::vector<uint32_t> child_list(child_off[total_nodes]);
     {
-        const uint64_t nb = ((uint64_t) n_table * 2 + BLOCK_USABLE - 1) / BLOCK_USABLE;
-        if (nb * BLOCK_SLOTS >= 0x7FFFFFF0ull) {
-            if (err) *err = "index too large for 31-bit slot ids";
+        std::vector<uint32_t> fill(child_off.begin(), child_off.end() - 1);
+        for (size_t i = 0; i < total_nodes; i++) {
+            const BNode& nd = b.nodes[i];
+            if (nd.parent != NONE && nd.lenw != LEN_PLUS) child_list[fill[nd.parent]++] = (uint32_t) i;
+        }
+    }
+    // sizing pass: per parent choose {single, perfect hash of 2^lg slots with a seed, big}
+    struct ChildPlan { uint8_t lg; uint8_t big; uint16_t seed; };
+    std::vector<ChildPlan> plan(total_nodes, ChildPlan{0, 0, 0});
+    uint64_t n_big_edges = 0, csr_slots = 0;
+    {
+        std::vector<uint32_t> t32, seen;
+        for (size_t i = 0; i < total_nodes; i++) {
+            const uint32_t c = child_off[i + 1] - child_off[i];
+            if (b.nodes[i].plus != NONE) csr_slots++;
+            if (c == 0) continue;
+            ChildPlan& pl = plan[i];
+            t32.clear();
+            for (uint32_t j = child_off[i]; j < child_off[i + 1]; j++) {
+                const BNode& ch = b.nodes[child_list[j]];
+                t32.push_back(fold32(token_hash(ch.lenw, ch.tok)));
+            }
+            bool big = c > SMALL_FANOUT_MAX;
+            if (!big && c == 1) {
+                pl.lg = 0;
+                pl.seed = (uint16_t) (t32[0] & 0xFFFFu);
+            } else if (!big) {
+                std::vector<uint32_t> sorted(t32);
+                std::sort(sorted.begin(), sorted.end());
+                if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) big = true;   // 32-bit fold collision
+                uint32_t lg = 1;
+                while ((1u << lg) < c) lg++;
+                if (c > 4) lg++;
+                bool found = false;
+                for (; !big && !found && lg <= 8; lg++) {
+                    for (uint32_t seed = 0; seed < 65536 && !found; seed++) {
+                        uint64_t mask_lo = 0, mask_hi = 0, mask_2 = 0, mask_3 = 0;   // up to 256 positions
+                        bool ok = true;
+                        for (uint32_t v : t32) {
+                            const uint32_t idx = child_index(v, seed, lg);
+                            uint64_t& m = idx < 64 ? mask_lo : (idx < 128 ? mask_hi : (idx < 192 ? mask_2 : mask_3));
+                            const uint64_t bit = 1ull << (idx & 63);
+                            if (m & bit) { ok = false; break; }
+                            m |= bit;
+                        }
+                        if (ok) {
+                            found = true;
+                            pl.lg = (uint8_t) lg;
+                            pl.seed = (uint16_t) seed;
+                        }
+                    }
+                    if (found) break;
+                }
+                if (!found) big = true;
+            }
+            if (big) {
+                pl.big = 1;
+                n_big_edges += c;
+            } else {
+                csr_slots += 1ull << pl.lg;
+            }
+        }
+    }
+    EdgeTable table;
+    table.init(n_big_edges);
+    const uint64_t csr_base = (uint64_t) table.n_blocks * BLOCK_SLOTS;
+    if (csr_base + csr_slots >= 0x7FFFFFF0ull) {
+        if (err) *err = "index too large for 31-bit slot ids";
+        return false;
+    }
+    {
+        Slot empty;
+        memset(empty.w, 0, sizeof(empty.w));
+        empty.w[W_PARENT] = EMPTY_PARENT;
+        table.slots.resize((size_t) (csr_base + csr_slots), empty);
+    }
+    out->roots.assign(n_roots, Slot());
+    std::vector<uint32_t> id_of(total_nodes, NONE), child_base(total_nodes, 0);
+    // BFS placement
+    {
+        std::vector<uint32_t> order;
+        order.reserve(total_nodes);
+        for (size_t i = 0; i < total_nodes; i++)
+            if (b.nodes[i].parent == NONE) {
+                id_of[i] = ROOT_BASE + b.nodes[i].root_ordinal;
+                order.push_back((uint32_t) i);
+            }
+        uint64_t cursor = csr_base;
+        for (size_t qi = 0; qi < order.size(); qi++) {
+            const uint32_t pi = order[qi];
+            const BNode& P = b.nodes[pi];
+            if (P.plus != NONE) {
+                id_of[P.plus] = (uint32_t) cursor++;
+                order.push_back(P.plus);
+            }
+            const ChildPlan& pl = plan[pi];
+            const uint32_t c0 = child_off[pi], c1 = child_off[pi + 1];
+            if (c1 == c0) continue;
+            if (pl.big) {
+                for (uint32_t j = c0; j < c1; j++) {
+                    const BNode& ch = b.nodes[child_list[j]];
+                    id_of[child_list[j]] = table.place(id_of[pi], ch.lenw, ch.tok);
+                    order.push_back(child_list[j]);
+                }
+            } else {
+                child_base[pi] = (uint32_t) cursor;
+                for (uint32_t j = c0; j < c1; j++) {
+                    const BNode& ch = b.nodes[child_list[j]];
+                    const uint32_t idx = pl.lg ? child_index(fold32(token_hash(ch.lenw, ch.tok)), pl.seed, pl.lg) : 0u;
+                    id_of[child_list[j]] = (uint32_t) (cursor + idx);
+                    order.push_back(child_list[j]);
+                }
+                cursor += 1ull << pl.lg;
+            }
+        }
+        if (order.size() != total_nodes || cursor != csr_base + csr_slots) {
+            if (err) *err = "internal error: BFS placement did not cover the trie";
             return false;
         }
     }
-    table.init(n_table);
-    out->roots.assign(n_roots, Slot());
-    std::vector<uint32_t> id_of(total_nodes, NONE);
     out->segs.clear();
-    auto emit_target = [&](Target& t, uint32_t* first, uint32_t* count, uint32_t* caps, uint32_t multi_flag, uint32_t* flags) {
-        *caps = sat16(t.pc) | (sat16(t.gc) << 16);
+    auto emit_target = [&](Target& t, uint32_t* first, uint32_t* count, uint32_t multi_flag, uint32_t* flags) {
         if (t.multi >= 0) {
             auto& lst = b.multi_lists[t.multi];
             lst.push_back({t.first, t.count});
@@ -340,31 +458,28 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
             *count = t.total;
         }
     };
+    auto sat8 = [](uint32_t v) { return v > 255u ? 255u : v; };
     for (size_t i = 0; i < total_nodes; i++) {
         BNode& nd = b.nodes[i];
         Slot* rec;
         if (nd.parent == NONE) {
-            id_of[i] = ROOT_BASE + nd.root_ordinal;
             rec = &out->roots[nd.root_ordinal];
             memset(rec->w, 0, sizeof(rec->w));
             rec->w[W_PARENT] = NONE;
         } else {
-            const uint32_t parent_id = id_of[nd.parent];
-            const uint32_t s = table.place(parent_id, nd.lenw, nd.tok);
-            id_of[i] = s;
-            rec = &table.slots[s];
+            rec = &table.slots[id_of[i]];
+            rec->w[W_PARENT] = id_of[nd.parent];
+            rec->w[W_LEN] = nd.lenw;
+            for (uint32_t k = 0; k < TOKEN_WORDS; k++) rec->w[W_TOK + k] = nd.tok[k];
         }
-        uint32_t flags = nd.flags;
-        emit_target(nd.own, &rec->w[W_OWN_FIRST], &rec->w[W_OWN_COUNT], &rec->w[W_OWN_CAPS], FLAG_OWN_MULTI, &flags);
-        emit_target(nd.hash, &rec->w[W_HASH_FIRST], &rec->w[W_HASH_COUNT], &rec->w[W_HASH_CAPS], FLAG_HASH_MULTI, &flags);
-        rec->w[W_FLAGS] = flags;
-        rec->w[W_PLUS] = NONE;  // patched below once the '+' child has a slot
-    }
-    for (size_t i = 0; i < total_nodes; i++) {
-        const BNode& nd = b.nodes[i];
-        if (nd.plus == NONE) continue;
-        Slot* rec = nd.parent == NONE ? &out->roots[nd.root_ordinal] : &table.slots[id_of[i]];
-        rec->w[W_PLUS] = id_of[nd.plus];
+        uint32_t flags = nd.flags & FLAG_HAS_EXACT;
+        emit_target(nd.own, &rec->w[W_OWN_FIRST], &rec->w[W_OWN_COUNT], FLAG_OWN_MULTI, &flags);
+        emit_target(nd.hash, &rec->w[W_HASH_FIRST], &rec->w[W_HASH_COUNT], FLAG_HASH_MULTI, &flags);
+        rec->w[W_CAPS] = sat8(nd.own.pc) | (sat8(nd.own.gc) << 8) | (sat8(nd.hash.pc) << 16) | (sat8(nd.hash.gc) << 24);
+        if (plan[i].big) flags |= FLAG_BIG;
+        rec->w[W_META] = meta_pack(flags, plan[i].lg, plan[i].seed);
+        rec->w[W_CHILD_BASE] = child_base[i];
+        rec->w[W_PLUS] = nd.plus == NONE ? NONE : id_of[nd.plus];
     }
     if (out->segs.empty()) out->segs.assign(2, 0);
     {
@@ -374,7 +489,7 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
         for (size_t i = 0; i < total_nodes; i++) out->child_hist[std::min<uint32_t>(nchild[i], 4)]++;
     }
     out->n_blocks = table.n_blocks;
-    out->n_slots = table.n_blocks * BLOCK_SLOTS;
+    out->n_slots = (uint32_t) table.slots.size();
     out->overflowed_blocks = table.overflowed_blocks;
     out->slots = std::move(table.slots);
     out->tags = std::move(table.tags);

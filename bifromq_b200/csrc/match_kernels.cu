@@ -35,14 +35,15 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct WarpSmem {
     uint8_t stage[STAGE_BYTES];
     uint32_t keyw[8];
-    uint2 fr[2][FR_CAP];
+    uint4 fr[2][FR_CAP];     // frontier entry: {child ref a, '+' child slot or NONE31, meta, -}
     uint2 rg[RG_CAP];
 };
 
-__device__ __forceinline__ uint64_t caps_value(uint32_t c16) { return c16 == 0xFFFFu ? (1ull << 32) : (uint64_t) c16; }
+// one saturating byte per counter in the node record: 255 means "255 or more" -> force the exact caps kernel
+__device__ __forceinline__ uint64_t caps_value(uint32_t c8) { return c8 == 0xFFu ? (1ull << 32) : (uint64_t) c8; }
 
 template <bool kBig>
-__device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, uint32_t t, int lane, uint2* fr_a, uint2* fr_b,
+__device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, uint32_t t, int lane, uint4* fr_a, uint4* fr_b,
                                           uint2* rg, uint32_t capF, uint32_t capR) {
     const int64_t tb = p.topic_off[t];
     const int len = (int) (p.topic_off[t + 1] - tb);
@@ -69,8 +70,8 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
             const uint32_t idx = n_rg + __popc(m & ((1u << lane) - 1));
             if (idx < capR) rg[idx] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
             acc_r += count;
-            acc_p += caps_value(caps & 0xFFFFu);
-            acc_g += caps_value(caps >> 16);
+            acc_p += caps_value(caps & 0xFFu);
+            acc_g += caps_value((caps >> 8) & 0xFFu);
         }
         n_rg += __popc(m);
         if (n_rg > capR) overflow = true;
@@ -81,16 +82,16 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
         load_slot(p.roots + root_ord, rw);
         const bool sys = len > 0 && byte_at(0) == '$';
         // "#" at level 0 matches every non-'$' topic
-        emit(lane == 0 && !sys && rw[W_HASH_COUNT] > 0, rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI,
-             rw[W_HASH_CAPS]);
-        uint2* fr_cur = fr_a;
-        uint2* fr_next = fr_b;
+        emit(lane == 0 && !sys && rw[W_HASH_COUNT] > 0, rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI,
+             (rw[W_CAPS] >> 16));
+        uint4* fr_cur = fr_a;
+        uint4* fr_next = fr_b;
         uint32_t n_fr = 0;
         {
             const uint32_t plus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];   // '+' at level 0 skips '$' topics
-            const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
+            const uint32_t has_exact = rw[W_META] & FLAG_HAS_EXACT;
             if (has_exact || plus != NONE31) {
-                if (lane == 0) fr_cur[0] = make_uint2(ROOT_BASE + (uint32_t) root_ord, plus | (has_exact ? 0x80000000u : 0u));
+                if (lane == 0) fr_cur[0] = make_uint4(child_ref(ROOT_BASE + (uint32_t) root_ord, rw), plus, rw[W_META], 0u);
                 n_fr = 1;
             }
         }
@@ -113,15 +114,15 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
             __syncwarp();
             for (uint32_t base = 0; base < n_fr && !overflow; base += 32) {
                 const bool active = base + lane < n_fr;
-                const uint2 fe = active ? fr_cur[base + lane] : make_uint2(0u, NONE31);
-                const uint32_t plus = fe.y & NONE31;
+                const uint4 fe = active ? fr_cur[base + lane] : make_uint4(0u, NONE31, 0u, 0u);
+                const uint32_t plus = fe.y;
                 // '+' child record: independent of the token, issue its load first
                 const bool has_plus = active && plus != NONE31;
                 uint32_t pw[16];
                 if (has_plus) load_slot(p.slots + plus, pw);
                 // exact child: one probe per 24-byte chunk of the token (one chunk unless the level is > 24 B)
-                bool alive = active && (fe.y >> 31);
-                uint32_t node = fe.x, cid = 0;
+                bool alive = active && (fe.z & FLAG_HAS_EXACT);
+                uint32_t node = fe.x, node_meta = fe.z, cid = 0;
                 uint32_t cw[16];
                 for (int c = 0; c < nchunks; c++) {
                     const int cpos = pos + c * (int) TOKEN_BYTES;
@@ -143,45 +144,44 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
                     for (int j = 0; j < 6; j++) k[j] = ws.keyw[j];
                     const uint64_t tokh = token_hash(lenw, k);
                     if (alive) {
-                        alive = probe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh, cw, cid);
-                        node = cid;
+                        alive = find_child(p.slots, p.tags, p.n_blocks, node, node_meta, lenw, k, tokh, cw, cid);
+                        if (alive) {   // an intermediate chunk node: its own children continue the chain
+                            node = child_ref(cid, cw);
+                            node_meta = cw[W_META];
+                        }
                     }
                 }
                 // ---- emit ranges of the discovered children and build the next frontier
-                emit(alive && cw[W_HASH_COUNT] > 0, cw[W_HASH_FIRST], cw[W_HASH_COUNT], alive && (cw[W_FLAGS] & FLAG_HASH_MULTI),
-                     cw[W_HASH_CAPS]);
+                emit(alive && cw[W_HASH_COUNT] > 0, cw[W_HASH_FIRST], cw[W_HASH_COUNT], alive && (cw[W_META] & FLAG_HASH_MULTI),
+                     (cw[W_CAPS] >> 16));
                 emit(has_plus && pw[W_HASH_COUNT] > 0, pw[W_HASH_FIRST], pw[W_HASH_COUNT],
-                     has_plus && (pw[W_FLAGS] & FLAG_HASH_MULTI), pw[W_HASH_CAPS]);
+                     has_plus && (pw[W_META] & FLAG_HASH_MULTI), (pw[W_CAPS] >> 16));
                 if (last) {
-                    emit(alive && cw[W_OWN_COUNT] > 0, cw[W_OWN_FIRST], cw[W_OWN_COUNT], alive && (cw[W_FLAGS] & FLAG_OWN_MULTI),
-                         cw[W_OWN_CAPS]);
+                    emit(alive && cw[W_OWN_COUNT] > 0, cw[W_OWN_FIRST], cw[W_OWN_COUNT], alive && (cw[W_META] & FLAG_OWN_MULTI),
+                         (cw[W_CAPS] & 0xFFFFu));
                     emit(has_plus && pw[W_OWN_COUNT] > 0, pw[W_OWN_FIRST], pw[W_OWN_COUNT],
-                         has_plus && (pw[W_FLAGS] & FLAG_OWN_MULTI), pw[W_OWN_CAPS]);
+                         has_plus && (pw[W_META] & FLAG_OWN_MULTI), (pw[W_CAPS] & 0xFFFFu));
                 } else {
-                    const bool push_c = alive && ((cw[W_FLAGS] & FLAG_HAS_EXACT) || cw[W_PLUS] != NONE);
-                    const bool push_p = has_plus && ((pw[W_FLAGS] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE);
+                    const bool push_c = alive && ((cw[W_META] & FLAG_HAS_EXACT) || cw[W_PLUS] != NONE);
+                    const bool push_p = has_plus && ((pw[W_META] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE);
                     const unsigned mc = __ballot_sync(FULL, push_c);
                     const unsigned mp = __ballot_sync(FULL, push_p);
                     const uint32_t lt = (1u << lane) - 1;
                     if (push_c) {
                         const uint32_t idx = n_next + __popc(mc & lt);
-                        if (idx < capF)
-                            fr_next[idx] = make_uint2(cid, (cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS]) |
-                                                               ((cw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u));
+                        if (idx < capF) fr_next[idx] = make_uint4(child_ref(cid, cw), cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS], cw[W_META], 0u);
                     }
                     n_next += __popc(mc);
                     if (push_p) {
                         const uint32_t idx = n_next + __popc(mp & lt);
-                        if (idx < capF)
-                            fr_next[idx] = make_uint2(plus, (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) |
-                                                                ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u));
+                        if (idx < capF) fr_next[idx] = make_uint4(child_ref(plus, pw), pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS], pw[W_META], 0u);
                     }
                     n_next += __popc(mp);
                     if (n_next > capF) overflow = true;
                 }
             }
             __syncwarp();
-            uint2* tmp = fr_cur;
+            uint4* tmp = fr_cur;
             fr_cur = fr_next;
             fr_next = tmp;
             n_fr = n_next;
@@ -246,10 +246,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
     const int64_t gw = (int64_t) blockIdx.x * WARPS_PER_CTA + wid;
     const int64_t nw = (int64_t) gridDim.x * WARPS_PER_CTA;
     if (kBig) {
-        uint2* basep = p.scratch + (uint64_t) gw * (2 * p.scratch_frontier_cap + p.scratch_ranges_cap);
-        uint2* fr_a = basep;
-        uint2* fr_b = basep + p.scratch_frontier_cap;
-        uint2* rg = basep + 2 * p.scratch_frontier_cap;
+        // per-warp scratch, in uint2 units: two frontier buffers of uint4 entries, then the range staging
+        uint2* basep = p.scratch + (uint64_t) gw * (4 * p.scratch_frontier_cap + p.scratch_ranges_cap);
+        uint4* fr_a = reinterpret_cast<uint4*>(basep);
+        uint4* fr_b = reinterpret_cast<uint4*>(basep + 2 * p.scratch_frontier_cap);
+        uint2* rg = basep + 4 * p.scratch_frontier_cap;
         const uint32_t capF = (uint32_t) min((uint64_t) 0x3FFFFFFFull, p.scratch_frontier_cap);
         const uint32_t capR = (uint32_t) min((uint64_t) SPAN_COUNT_MASK, p.scratch_ranges_cap);
         for (int64_t it = gw; it < p.n_work; it += nw) match_one<true>(p, ws, p.work_list[it], lane, fr_a, fr_b, rg, capF, capR);
@@ -281,12 +282,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 // Anything that does not fit the bounded state (> 16 levels, a level > 24 B, > INLINE_RANGES ranges, topic > 64 KB)
 // is handed, whole, to the warp-per-topic tier through defer_list.
 constexpr int L_WARPS = 4;
-constexpr int L_MAXLV = 16;
+constexpr int L_MAXLV = 12;
 constexpr int L_CHUNK = 64;
 
 struct LaneSmem {
     uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
-    uint2 stk[L_MAXLV + 1][32];     // parked '+' branch per level: {node id, plus | has_exact << 31}
+    uint2 stk[L_MAXLV + 1][32];     // parked '+' branch per level: {child ref a, '+' child slot or NONE31}
+    uint32_t stkm[L_MAXLV + 1][32]; //   ... and its meta word
     // metadata of the warp's current chunk of topics, loaded cooperatively (coalesced) when the chunk is claimed
     uint32_t m_off[L_CHUNK];        // byte offset relative to the chunk's first topic
     uint32_t m_len[L_CHUNK];
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     bool exhausted = false;
     // per-lane topic state; level < 0: the tenant root has not been expanded yet (`node` holds the root ordinal)
     bool have = false, bad = false;
-    uint32_t t = 0, node = 0, plusf = NONE31, pending = 0, n_rg = 0, acc_r = 0;
+    uint32_t t = 0, node = 0 /* child ref a (root ordinal while level < 0) */, plusf = NONE31, meta = 0, pending = 0, n_rg = 0, acc_r = 0;
     uint64_t acc_p = 0, acc_g = 0;
     int64_t my_off = 0;
     int len = 0, level = 0, tenant = 0;
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
         else bad = true;
         n_rg++;
         acc_r += count;
-        acc_p += caps_value(caps & 0xFFFFu);
-        acc_g += caps_value(caps >> 16);
+        acc_p += caps_value(caps & 0xFFu);
+        acc_g += caps_value((caps >> 8) & 0xFFu);
     };
     auto finish = [&]() {
         if (bad) {
@@ -401,12 +403,13 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                         uint32_t rw[16];
                         load_slot(p.roots + root_ord, rw);
                         const bool sys = len > 0 && p.topics[my_off] == '$';
-                        if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_FLAGS] & FLAG_HASH_MULTI, rw[W_HASH_CAPS]);
+                        if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI, (rw[W_CAPS] >> 16));
                         const uint32_t rplus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
-                        const uint32_t has_exact = rw[W_FLAGS] & FLAG_HAS_EXACT;
+                        const uint32_t has_exact = rw[W_META] & FLAG_HAS_EXACT;
                         if ((has_exact || rplus != NONE31) && !bad) {
-                            node = ROOT_BASE + (uint32_t) root_ord;
-                            plusf = rplus | (has_exact ? 0x80000000u : 0u);
+                            node = child_ref(ROOT_BASE + (uint32_t) root_ord, rw);
+                            plusf = rplus;
+                            meta = rw[W_META];
                             level = 0;
                         } else {
                             finish();
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
 #pragma unroll
             for (int j = 0; j < 8; j++) x[j] = (wp + j) < wend ? __ldg(wp + j) : 0u;
             // the '+' child (or the tenant root) record: independent of the token, issue its load right away
-            const uint32_t plus = plusf & NONE31;
+            const uint32_t plus = plusf;
             const bool has_plus = rootstep || plus != NONE31;
             uint32_t pw[16];
             if (has_plus) load_slot(rootstep ? p.roots + node : p.slots + plus, pw);
@@ -452,12 +455,13 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             const bool last = tlen == rem;
             if (rootstep) {
                 const bool sys = len > 0 && first_byte == '$';   // '+' and '#' at the first level skip '$' topics
-                if (!sys && pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_FLAGS] & FLAG_HASH_MULTI, pw[W_HASH_CAPS]);
+                if (!sys && pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_META] & FLAG_HASH_MULTI, (pw[W_CAPS] >> 16));
                 const uint32_t rplus = (sys || pw[W_PLUS] == NONE) ? NONE31 : pw[W_PLUS];
-                const uint32_t has_exact = pw[W_FLAGS] & FLAG_HAS_EXACT;
+                const uint32_t has_exact = pw[W_META] & FLAG_HAS_EXACT;
                 if ((has_exact || rplus != NONE31) && !bad) {
-                    node = ROOT_BASE + node;
-                    plusf = rplus | (has_exact ? 0x80000000u : 0u);
+                    node = child_ref(ROOT_BASE + node, pw);
+                    plusf = rplus;
+                    meta = pw[W_META];
                     level = 0;
                 } else {
                     finish();
@@ -472,43 +476,45 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     const int vb = tlen - 4 * j;
                     k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
                 }
-                bool alive = plusf >> 31;
+                bool alive = meta & FLAG_HAS_EXACT;
                 uint32_t cw[16], cid = 0;
                 if (alive) {
                     uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
-                    alive = probe(p.slots, p.tags, p.n_blocks, node, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
+                    alive = find_child(p.slots, p.tags, p.n_blocks, node, meta, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
                 }
                 bool push_c = false, push_p = false;
                 if (alive) {
-                    if (cw[W_HASH_COUNT] > 0) emit(cw[W_HASH_FIRST], cw[W_HASH_COUNT], cw[W_FLAGS] & FLAG_HASH_MULTI, cw[W_HASH_CAPS]);
+                    if (cw[W_HASH_COUNT] > 0) emit(cw[W_HASH_FIRST], cw[W_HASH_COUNT], cw[W_META] & FLAG_HASH_MULTI, (cw[W_CAPS] >> 16));
                     if (last) {
-                        if (cw[W_OWN_COUNT] > 0) emit(cw[W_OWN_FIRST], cw[W_OWN_COUNT], cw[W_FLAGS] & FLAG_OWN_MULTI, cw[W_OWN_CAPS]);
+                        if (cw[W_OWN_COUNT] > 0) emit(cw[W_OWN_FIRST], cw[W_OWN_COUNT], cw[W_META] & FLAG_OWN_MULTI, (cw[W_CAPS] & 0xFFFFu));
                     } else {
-                        push_c = (cw[W_FLAGS] & FLAG_HAS_EXACT) || cw[W_PLUS] != NONE;
+                        push_c = (cw[W_META] & FLAG_HAS_EXACT) || cw[W_PLUS] != NONE;
                     }
                 }
                 if (has_plus) {
-                    if (pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_FLAGS] & FLAG_HASH_MULTI, pw[W_HASH_CAPS]);
+                    if (pw[W_HASH_COUNT] > 0) emit(pw[W_HASH_FIRST], pw[W_HASH_COUNT], pw[W_META] & FLAG_HASH_MULTI, (pw[W_CAPS] >> 16));
                     if (last) {
-                        if (pw[W_OWN_COUNT] > 0) emit(pw[W_OWN_FIRST], pw[W_OWN_COUNT], pw[W_FLAGS] & FLAG_OWN_MULTI, pw[W_OWN_CAPS]);
+                        if (pw[W_OWN_COUNT] > 0) emit(pw[W_OWN_FIRST], pw[W_OWN_COUNT], pw[W_META] & FLAG_OWN_MULTI, (pw[W_CAPS] & 0xFFFFu));
                     } else {
-                        push_p = (pw[W_FLAGS] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE;
+                        push_p = (pw[W_META] & FLAG_HAS_EXACT) || pw[W_PLUS] != NONE;
                     }
                 }
                 if (bad) {
                     finish();
                 } else if (push_c) {
                     if (push_p) {   // park the '+' branch of this level, continue down the exact branch
-                        ws.stk[level + 1][lane] = make_uint2(plus, (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) |
-                                                                       ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u));
+                        ws.stk[level + 1][lane] = make_uint2(child_ref(plus, pw), pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]);
+                        ws.stkm[level + 1][lane] = pw[W_META];
                         pending |= 1u << (level + 1);
                     }
-                    node = cid;
-                    plusf = (cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS]) | ((cw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
+                    node = child_ref(cid, cw);
+                    plusf = cw[W_PLUS] == NONE ? NONE31 : cw[W_PLUS];
+                    meta = cw[W_META];
                     level++;
                 } else if (push_p) {
-                    node = plus;
-                    plusf = (pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS]) | ((pw[W_FLAGS] & FLAG_HAS_EXACT) ? 0x80000000u : 0u);
+                    node = child_ref(plus, pw);
+                    plusf = pw[W_PLUS] == NONE ? NONE31 : pw[W_PLUS];
+                    meta = pw[W_META];
                     level++;
                 } else if (pending) {
                     const int l = 31 - __clz(pending);
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     const uint2 it = ws.stk[l][lane];
                     node = it.x;
                     plusf = it.y;
+                    meta = ws.stkm[l][lane];
                     level = l;
                 } else {
                     finish();

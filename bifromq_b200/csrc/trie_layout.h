@@ -5,7 +5,15 @@
 // (two 32 B sectors) random access and no separate node fetch. Node id == slot index; tenant roots live in
 // a small side array (id = ROOT_BASE + ordinal).
 //
-// The table is BLOCKED and TAG-FILTERED (Swiss-table style): slots are grouped in blocks of 16 (15 usable),
+// Exact children are found in one of two ways, chosen per parent node at build time:
+//   * SMALL fan-out (<= 16 exact children; > 90 % of all nodes have exactly one): the children sit in a private,
+//     contiguous array of 2^k slots right in the slot array (CSR), addressed by a per-node PERFECT HASH:
+//     slot = child_base + ((fold32(token hash) ^ seed * C1) * C2 >> (32 - k)); the parent record carries child_base,
+//     k and the 16-bit seed (found by search at build time). A lookup is ONE 64 B access, hit or miss, no probing;
+//     a single-child node stores a 16-bit fingerprint instead of a seed, so most misses cost no access at all.
+//   * BIG fan-out: the global blocked, tag-filtered table below, keyed by (parent id, token).
+//
+// The global table is BLOCKED and TAG-FILTERED (Swiss-table style): slots are grouped in blocks of 16 (15 usable),
 // and a parallel 16-byte tag word per block holds one fingerprint byte per slot (0 = free, 2..255 = fingerprint
 // of the slot's key) plus a control byte (byte 15: 1 = the block overflowed into the next one). An edge hashes
 // to ONE block; a lookup loads that block's 16 tags (the tag array is ~1/64 of the table and mostly L2
@@ -20,12 +28,14 @@
 //                                             24-byte continuation chunk of a token longer than 24 B)
 //   words 2..7   token bytes, zero padded    (exact compare: no hash collisions by construction)
 //   word  8      slot of the '+' child       (NONE if absent)
-//   word  9      flags                       (HAS_EXACT: node has >= 1 exact child; *_MULTI see below)
+//   word  9      child_base                  (first slot of the private child array; unused for BIG nodes)
 //   words 10,11  own routes  [first rank, count)   routes of the filter ending at this node
 //   words 12,13  '#' routes  [first rank, count)   routes of the filter "<this node>/#" ('#' is always the
 //                                                   last level, so the '#' child is inlined into its parent)
-//   word  14     own  caps counters: lo16 persistent (subBrokerId==1) routes, hi16 group routes, saturating
-//   word  15     '#'  caps counters, same packing
+//   word  14     caps counters, one saturating byte each: own persistent (subBrokerId==1), own group,
+//                '#' persistent, '#' group   (255 = "255 or more": the exact caps kernel decides)
+//   word  15     meta: bits 0-7 flags (HAS_EXACT, OWN_MULTI, HASH_MULTI, BIG), bits 8-11 k = log2(child array
+//                size), bits 16-31 perfect-hash seed (k >= 1) or the only child's fingerprint (k == 0)
 //
 // A rank is the position of a route in the committed KV order (the reference's RocksDB order), so a
 // filter's routes are one contiguous run [first, first+count) — except in the rare interleaving case
@@ -43,15 +53,16 @@ struct alignas(64) Slot {
 static_assert(sizeof(Slot) == 64, "slot must be one 64-byte burst");
 
 enum : uint32_t {
-    W_PARENT = 0, W_LEN = 1, W_TOK = 2, W_PLUS = 8, W_FLAGS = 9,
-    W_OWN_FIRST = 10, W_OWN_COUNT = 11, W_HASH_FIRST = 12, W_HASH_COUNT = 13, W_OWN_CAPS = 14, W_HASH_CAPS = 15,
+    W_PARENT = 0, W_LEN = 1, W_TOK = 2, W_PLUS = 8, W_CHILD_BASE = 9,
+    W_OWN_FIRST = 10, W_OWN_COUNT = 11, W_HASH_FIRST = 12, W_HASH_COUNT = 13, W_CAPS = 14, W_META = 15,
 };
 constexpr uint32_t EMPTY_PARENT = 0xFFFFFFFFu;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t LEN_PLUS = 0xFFFFFFFFu;
 constexpr uint32_t LEN_CONT = 0x80000000u;       // | chunk index
 constexpr uint32_t ROOT_BASE = 0x80000000u;      // node id of tenant root = ROOT_BASE + tenant ordinal
-constexpr uint32_t FLAG_HAS_EXACT = 1u, FLAG_OWN_MULTI = 2u, FLAG_HASH_MULTI = 4u;
+constexpr uint32_t FLAG_HAS_EXACT = 1u, FLAG_OWN_MULTI = 2u, FLAG_HASH_MULTI = 4u, FLAG_BIG = 8u;
+constexpr uint32_t SMALL_FANOUT_MAX = 16;        // more exact children than this => global tag table
 constexpr uint32_t TOKEN_WORDS = 6;              // 24 inline token bytes per edge
 constexpr uint32_t TOKEN_BYTES = 24;
 constexpr uint32_t RANGE_MULTI = 0x80000000u;    // marker in an emitted range's count word
@@ -83,6 +94,13 @@ BFQ_HD uint64_t token_hash(uint32_t lenw, const uint32_t* k /*[6]*/) {
 constexpr uint32_t BLOCK_SLOTS = 16;     // slots per block (slot 15 of every block is never used)
 constexpr uint32_t BLOCK_USABLE = 15;
 constexpr uint32_t TAG_CTRL = 15;        // control byte index inside the 16-byte tag word
+
+// per-node perfect hash over the 32-bit fold of the token hash
+BFQ_HD uint32_t fold32(uint64_t tokh) { return (uint32_t) (tokh ^ (tokh >> 32)); }
+BFQ_HD uint32_t child_index(uint32_t t32, uint32_t seed, uint32_t log2size) {   // log2size >= 1
+    return ((t32 ^ (seed * 0x9E3779B9u)) * 0x85EBCA6Bu) >> (32u - log2size);
+}
+BFQ_HD uint32_t meta_pack(uint32_t flags, uint32_t log2size, uint32_t seed) { return (flags & 0xFFu) | ((log2size & 15u) << 8) | (seed << 16); }
 
 BFQ_HD uint64_t edge_hash(uint64_t tokh, uint32_t parent) { return fmix64(tokh + (uint64_t) parent * 0xC2B2AE3D27D4EB4Full); }
 BFQ_HD uint32_t home_block(uint64_t h, uint32_t n_blocks) { return (uint32_t) (((h >> 32) * (uint64_t) n_blocks) >> 32); }
