@@ -7,9 +7,22 @@
 
 namespace bfq {
 
+// kNA: bypass L1 allocation (ld.global.nc.L1::no_allocate) — node records are touched once per walk, keeping them out
+// of L1 leaves it to the topic bytes / tenant roots that every step re-reads
+template <bool kNA>
+__device__ __forceinline__ uint4 ld16(const uint4* p) {
+    if (kNA) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        return v;
+    }
+    return __ldg(p);
+}
+
+template <bool kNA = false>
 __device__ __forceinline__ void load_slot(const Slot* s, uint32_t (&w)[16]) {
     const uint4* p = reinterpret_cast<const uint4*>(s);
-    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    uint4 a = ld16<kNA>(p), b = ld16<kNA>(p + 1), c = ld16<kNA>(p + 2), d = ld16<kNA>(p + 3);
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
     w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
     w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
@@ -29,6 +42,7 @@ __device__ __forceinline__ uint32_t nibble(uint32_t m) {
 }
 
 // Lookup of the edge (parent, lenw, k[0..5]). On success `w` holds the child record and `slot` its index.
+template <bool kNA = false>
 __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t parent, uint32_t lenw,
                                       const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
     const uint64_t h = edge_hash(tokh, parent);
@@ -46,7 +60,7 @@ __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint
             const uint32_t j = __ffs(cand) - 1;
             cand &= cand - 1;
             const uint32_t s = b * BLOCK_SLOTS + j;
-            load_slot(slots + s, w);
+            load_slot<kNA>(slots + s, w);
             if (w[W_PARENT] == parent && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] &&
                 w[5] == k[3] && w[6] == k[4] && w[7] == k[5]) {
                 slot = s;
@@ -60,9 +74,10 @@ __device__ __forceinline__ bool probe(const Slot* slots, const uint4* tags, uint
 
 // Exact child of a node described by (a, meta): a = the node id for BIG nodes (global tag table), else the base of the
 // node's private child array (perfect hash: one access, hit or miss; single-child nodes filter by fingerprint first).
+template <bool kNA = false>
 __device__ __forceinline__ bool find_child(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t a, uint32_t meta,
                                            uint32_t lenw, const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
-    if (meta & FLAG_BIG) return probe(slots, tags, n_blocks, a, lenw, k, tokh, w, slot);
+    if (meta & FLAG_BIG) return probe<kNA>(slots, tags, n_blocks, a, lenw, k, tokh, w, slot);
     const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(tokh);
     uint32_t idx = 0;
     if (lg == 0) {
@@ -71,7 +86,7 @@ __device__ __forceinline__ bool find_child(const Slot* slots, const uint4* tags,
         idx = child_index(t32, sd, lg);
     }
     slot = a + idx;
-    load_slot(slots + slot, w);
+    load_slot<kNA>(slots + slot, w);
     return w[W_PARENT] != EMPTY_PARENT && w[W_LEN] == lenw && w[2] == k[0] && w[3] == k[1] && w[4] == k[2] && w[5] == k[3] &&
            w[6] == k[4] && w[7] == k[5];
 }

@@ -296,8 +296,8 @@ struct LaneSmem {
     int32_t m_root[L_CHUNK];        // root ordinal of the topic's tenant, or -1
 };
 
-template <bool kRootStep, bool kPrefetch>
-__global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
+template <bool kRootStep, bool kPrefetch, bool kNA>
+__global__ void __launch_bounds__(L_WARPS * 32, 8) match_topics_lane_kernel(const MatchParams p) {
     __shared__ LaneSmem sm[L_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     LaneSmem& ws = sm[wid];
@@ -438,7 +438,10 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             const uint32_t plus = plusf;
             const bool has_plus = rootstep || plus != NONE31;
             uint32_t pw[16];
-            if (has_plus) load_slot(rootstep ? p.roots + node : p.slots + plus, pw);
+            if (has_plus) {
+                if (rootstep) load_slot<false>(p.roots + node, pw);
+                else load_slot<kNA>(p.slots + plus, pw);
+            }
             uint32_t k[7];
 #pragma unroll
             for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(x[j], x[j + 1], sh);
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 uint32_t cw[16], cid = 0;
                 if (alive) {
                     uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
-                    alive = find_child(p.slots, p.tags, p.n_blocks, node, meta, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
+                    alive = find_child<kNA>(p.slots, p.tags, p.n_blocks, node, meta, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
                 }
                 bool push_c = false, push_p = false;
                 if (alive) {
@@ -648,16 +651,19 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // experiment switches (defaults are the measured best): BFQ_ROOTSTEP=0/1, BFQ_PREFETCH=0/1
+    // experiment switches (defaults are the measured best): BFQ_ROOTSTEP=0/1, BFQ_PREFETCH=0/1, BFQ_NOALLOC=0/1
     static int variant = -1, ctas_per_sm = 0;
     typedef void (*kern_t)(const MatchParams);
-    static const kern_t kerns[4] = {match_topics_lane_kernel<false, false>, match_topics_lane_kernel<false, true>,
-                                    match_topics_lane_kernel<true, false>, match_topics_lane_kernel<true, true>};
+    static const kern_t kerns[8] = {match_topics_lane_kernel<false, false, false>, match_topics_lane_kernel<false, true, false>,
+                                    match_topics_lane_kernel<true, false, false>,  match_topics_lane_kernel<true, true, false>,
+                                    match_topics_lane_kernel<false, false, true>,  match_topics_lane_kernel<false, true, true>,
+                                    match_topics_lane_kernel<true, false, true>,   match_topics_lane_kernel<true, true, true>};
     if (variant < 0) {
         const char* rs = getenv("BFQ_ROOTSTEP");
         const char* pf = getenv("BFQ_PREFETCH");
-        const int rootstep = rs ? atoi(rs) : 0, prefetch = pf ? atoi(pf) : 1;
-        variant = (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
+        const char* na = getenv("BFQ_NOALLOC");
+        const int rootstep = rs ? atoi(rs) : 0, prefetch = pf ? atoi(pf) : 1, noalloc = na ? atoi(na) : 0;
+        variant = (noalloc ? 4 : 0) + (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
