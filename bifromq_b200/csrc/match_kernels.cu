@@ -297,7 +297,7 @@ struct LaneSmem {
 };
 
 template <bool kRootStep, bool kPrefetch, bool kNA>
-__global__ void __launch_bounds__(L_WARPS * 32, 8) match_topics_lane_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const MatchParams p) {
     __shared__ LaneSmem sm[L_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     LaneSmem& ws = sm[wid];
