@@ -243,8 +243,9 @@ def main():
     def step_e2e():
         r = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy())
         d2h = 12 * n + 8 * len(r.ranges) + 12 * len(r.throttled)
+        tm = r.timings_ms
         r.close()
-        return d2h
+        return d2h, tm
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -273,14 +274,14 @@ def main():
     # ---- e2e through the host-buffer call
     for _ in range(2):
         step_e2e()
-    e2e_t, d2h_bytes = [], 0
+    e2e_t, d2h_bytes, e2e_tm = [], 0, {}
     if world > 1:
         dist.barrier()
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        d2h_bytes = step_e2e()
+        d2h_bytes, e2e_tm = step_e2e()
         e2e_t.append(time.perf_counter() - t0)
     clocks = sampler.stop()
     e2e_total = float(sum(e2e_t))
@@ -330,7 +331,8 @@ def main():
                            "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "parallelism": "tenant-sharded x%d" % world,
                            "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
                            "caps": "MaxPersistentFanout=INT_MAX, MaxGroupFanout=INT_MAX", "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},
                 "gpu_launches": launches, "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
                 "ranges_per_step": n_ranges, "tier2_topics_per_step": n_overflow, "index": stats, "clocks": clocks}
         if roof:

@@ -93,8 +93,9 @@ struct bfq_index {
     FlatIndex flat;          // host copy of the committed snapshot (segs / tenant map / stats are used on the host)
     KVBlob committed;        // committed KV (for bfq_route_lookup)
     bool have_snapshot = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, work_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};
     double last_kernel_ms = 0;
     size_t l2_window_bytes = 0;
@@ -133,6 +134,9 @@ struct bfq_index {
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : evk) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_h2d) if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto& w : work_stream) if (w) cudaStreamDestroy(w);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -142,6 +146,8 @@ namespace {
 // Shared core of bfq_match / bfq_match_device: topics are on the device; runs tier 1, tier 2 and caps.
 struct CoreOut {
     int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0, n_deferred = 0;
+    uint64_t want_dyn = 0, want_thr = 0;
+    int64_t chunk_throttled[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
@@ -161,10 +167,20 @@ int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* ten
     return BFQ_OK;
 }
 
-int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
-                   int64_t n, int32_t n_tenants, cudaStream_t stream, CoreOut* out) {
+// One sub-batch of a match: topics [begin, begin + n) of a batch of n_total. Device buffers are indexed by the position
+// in the whole batch, so sub-batches of one call never overlap; each has its own counter block, its own slice of the
+// dynamic range region and of the throttled list.
+struct SubBatch {
+    int64_t begin = 0, n = 0, n_total = 0;
+    int chunk = 0;
+    uint64_t dyn_off = 0, dyn_cap = 0;     // slice of ranges[n_total * INLINE_RANGES ...) for tiers 1/2
+    uint64_t thr_off = 0, thr_cap = 0;     // slice of the throttled list
+};
+constexpr int MAX_CHUNKS = 8;
+constexpr int32_t BFQ_RETRY_GROW = -100;   // internal: a slice was too small, redo the batch un-chunked with bigger buffers
+
+int32_t prepare_workspace(bfq_index* h, int64_t n, int n_chunks) {
     const size_t nn = (size_t) std::max<int64_t>(n, 1);
-    const size_t nt = (size_t) std::max(n_tenants, 1);
     if (n >= (int64_t) 0x3FFFFFFF) return fail(BFQ_E_INVALID, "too many topics in one batch");
     CUDA_TRY(h->d_span_begin.reserve(nn));
     CUDA_TRY(h->d_span_count.reserve(nn));
@@ -173,33 +189,57 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     CUDA_TRY(h->d_flagged.reserve(nn));
     CUDA_TRY(h->d_kept.reserve(nn));
     CUDA_TRY(h->d_defer.reserve(nn));
-    CUDA_TRY(h->d_counters.reserve(CTR_COUNT));
-    CUDA_TRY(h->h_counters.reserve(CTR_COUNT));
-    // ranges[0, dyn_base): tier-0 inline slots; ranges[dyn_base, cap): cursor-allocated region of tiers 1 and 2
+    CUDA_TRY(h->d_counters.reserve(CTR_COUNT * MAX_CHUNKS));
+    CUDA_TRY(h->h_counters.reserve(CTR_COUNT * MAX_CHUNKS));
+    // ranges[0, n * INLINE_RANGES): tier-0 inline slots; the rest: cursor-allocated region of tiers 1 and 2
     const uint64_t dyn_base = (uint64_t) n * INLINE_RANGES;
     if (dyn_base >= 0xF0000000ull) return fail(BFQ_E_RANGE, "batch too large for 32-bit range indices; split the batch");
-    if (h->d_ranges.cap < dyn_base + (1u << 20)) CUDA_TRY(h->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, nn))));
-    if (h->d_throttled.cap == 0) CUDA_TRY(h->d_throttled.reserve(1 << 16));
+    const size_t min_dyn = std::max<size_t>((size_t) n_chunks << 18, nn);
+    if (h->d_ranges.cap < dyn_base + min_dyn) CUDA_TRY(h->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, min_dyn))));
+    if (h->d_throttled.cap < ((size_t) n_chunks << 14)) CUDA_TRY(h->d_throttled.reserve(std::max<size_t>(1 << 16, (size_t) n_chunks << 14)));
+    return BFQ_OK;
+}
 
+SubBatch whole_batch(bfq_index* h, int64_t n) {
+    SubBatch sb;
+    sb.begin = 0;
+    sb.n = sb.n_total = n;
+    sb.dyn_cap = h->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
+    sb.thr_cap = h->d_throttled.cap;
+    return sb;
+}
+
+// Runs tier 0 + tier 1 (+ tier 2, + caps) for one sub-batch on `stream`; blocks until its kernels have finished.
+int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
+                   int32_t n_tenants, cudaStream_t stream, const SubBatch& sb, CoreOut* out) {
+    const size_t nt = (size_t) std::max(n_tenants, 1);
+    const int64_t n = sb.n, b = sb.begin;
     MatchParams p{};
     p.slots = h->d_slots.p;
     p.roots = h->d_roots.p;
     p.tags = reinterpret_cast<const uint4*>(h->d_tags.p);
     p.n_blocks = h->flat.n_blocks;
     p.topics = d_topics;
-    p.topic_off = d_topic_off;
-    p.topic_tenant = d_topic_tenant;
+    p.topic_off = d_topic_off + b;
+    p.topic_tenant = d_topic_tenant + b;
     p.tenant_root = h->d_tenant_tab.p;
     p.max_pfanout = h->d_tenant_tab.p + nt;
     p.max_gfanout = h->d_tenant_tab.p + 2 * nt;
+    p.n_tenants = n_tenants;
     p.n_topics = n;
-    p.span_begin = h->d_span_begin.p;
-    p.span_count = h->d_span_count.p;
-    p.route_count = h->d_route_count.p;
-    p.overflow_list = h->d_overflow.p;
-    p.defer_list = h->d_defer.p;
-    p.flagged_list = h->d_flagged.p;
-    p.counters = h->d_counters.p;
+    p.span_begin = h->d_span_begin.p + b;
+    p.span_count = h->d_span_count.p + b;
+    p.route_count = h->d_route_count.p + b;
+    p.overflow_list = h->d_overflow.p + b;
+    p.defer_list = h->d_defer.p + b;
+    p.flagged_list = h->d_flagged.p + b;
+    unsigned long long* d_ctr = h->d_counters.p + (size_t) sb.chunk * CTR_COUNT;
+    unsigned long long* hc = h->h_counters.p + (size_t) sb.chunk * CTR_COUNT;
+    p.counters = d_ctr;
+    // range indices are relative to the sub-batch's first inline slot
+    p.ranges = h->d_ranges.p + (uint64_t) b * INLINE_RANGES;
+    p.dyn_base = (uint64_t) (sb.n_total - b) * INLINE_RANGES + sb.dyn_off;
+    p.ranges_cap = p.dyn_base + sb.dyn_cap;
 
     if (h->l2_window_bytes > 0) {
         cudaStreamAttrValue attr{};
@@ -211,102 +251,119 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
         cudaGetLastError();
     }
-    unsigned long long* hc = h->h_counters.p;
-    for (int attempt = 0; attempt < 8; attempt++) {
-        p.ranges = h->d_ranges.p;
-        p.ranges_cap = h->d_ranges.cap;
-        p.dyn_base = dyn_base;
-        CUDA_TRY(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), stream));
-        p.work_list = nullptr;
-        p.n_work = 0;
-        if (n > 0) {
-            // tier 0 (one lane per topic) over the whole batch, then tier 1 (one warp per topic) over whatever tier 0
-            // deferred — its count is read on the device, so both launches go out back to back
-            CUDA_TRY(cudaEventRecord(h->evk[0], stream));
-            launch_match_lanes(p, stream);
-            CUDA_TRY(cudaEventRecord(h->evk[1], stream));
-            p.work_list = h->d_defer.p;
-            p.n_work = -1;
-            launch_match(p, false, 0, stream);
-            out->n_launches += 2;
-        }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        out->n_overflow = (int64_t) hc[CTR_OVERFLOW];
-        out->n_deferred = (int64_t) hc[CTR_DEFER];
-        if (n > 0) {
-            float kms = 0;
-            cudaEventElapsedTime(&kms, h->evk[0], h->evk[1]);
-            h->last_kernel_ms = kms;
-        }
-        if (hc[CTR_OVERFLOW] > 0) {
-            // ---- tier 2: per-warp global scratch sized from the index statistics (exact upper bounds)
-            const uint64_t capF = (uint64_t) h->flat.max_nodes_per_depth + 2;
-            const uint64_t capR = 2 * ((uint64_t) h->flat.max_tenant_nodes + 2) + 2;
-            const uint64_t per_warp = 4 * capF + capR;   // uint2 units: two frontier buffers of uint4 entries + ranges
-            uint64_t warps = std::min<uint64_t>(hc[CTR_OVERFLOW], std::max<uint64_t>(8, (1ull << 31) / (per_warp * sizeof(uint2))));
-            warps = std::min<uint64_t>(warps, 148 * 8);
-            warps = (warps + 7) / 8 * 8;
-            CUDA_TRY(h->d_scratch.reserve((size_t) (warps * per_warp)));
-            p.scratch = h->d_scratch.p;
-            p.scratch_frontier_cap = capF;
-            p.scratch_ranges_cap = capR;
-            p.work_list = h->d_overflow.p;
-            p.n_work = (int64_t) hc[CTR_OVERFLOW];
-            launch_match(p, true, (int) warps, stream);
-            out->n_launches++;
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            if (hc[CTR_ERROR] != 0) return fail(BFQ_E_STATE, "tier-2 scratch exhausted (index statistics inconsistent)");
-        }
-        if (dyn_base + hc[CTR_RANGES] <= h->d_ranges.cap) break;
-        // the range buffer was too small: grow and redo the batch
-        const size_t want = (size_t) (dyn_base + hc[CTR_RANGES] + hc[CTR_RANGES] / 4 + 1024);
-        if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
-        CUDA_TRY(h->d_ranges.reserve(want));
-        if (attempt == 7) return fail(BFQ_E_STATE, "range buffer sizing did not converge");
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), stream));
+    p.work_list = nullptr;
+    p.n_work = 0;
+    if (n > 0) {
+        // tier 0 (one lane per topic) over the whole sub-batch, then tier 1 (one warp per topic) over whatever tier 0
+        // deferred — its count is read on the device, so both launches go out back to back
+        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(h->evk[0], stream));
+        launch_match_lanes(p, stream);
+        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(h->evk[1], stream));
+        p.work_list = p.defer_list;
+        p.n_work = -1;
+        launch_match(p, false, 0, stream);
+        out->n_launches += 2;
     }
-    out->n_ranges = (int64_t) (dyn_base + hc[CTR_RANGES]);   // extent of the sparse range array
-    out->n_flagged = (int64_t) hc[CTR_FLAGGED];
-    out->n_throttled = 0;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    out->n_overflow += (int64_t) hc[CTR_OVERFLOW];
+    out->n_deferred += (int64_t) hc[CTR_DEFER];
+    if (n > 0 && sb.chunk == 0) {
+        float kms = 0;
+        cudaEventElapsedTime(&kms, h->evk[0], h->evk[1]);
+        h->last_kernel_ms = kms;
+    }
+    if (hc[CTR_OVERFLOW] > 0) {
+        // ---- tier 2: per-warp global scratch sized from the index statistics (exact upper bounds)
+        const uint64_t capF = (uint64_t) h->flat.max_nodes_per_depth + 2;
+        const uint64_t capR = 2 * ((uint64_t) h->flat.max_tenant_nodes + 2) + 2;
+        const uint64_t per_warp = 4 * capF + capR;   // uint2 units: two frontier buffers of uint4 entries + ranges
+        uint64_t warps = std::min<uint64_t>(hc[CTR_OVERFLOW], std::max<uint64_t>(8, (1ull << 31) / (per_warp * sizeof(uint2))));
+        warps = std::min<uint64_t>(warps, 148 * 8);
+        warps = (warps + 7) / 8 * 8;
+        CUDA_TRY(cudaDeviceSynchronize());   // the scratch is shared: no other sub-batch may be in tier 2 (or running at all)
+        CUDA_TRY(h->d_scratch.reserve((size_t) (warps * per_warp)));
+        p.scratch = h->d_scratch.p;
+        p.scratch_frontier_cap = capF;
+        p.scratch_ranges_cap = capR;
+        p.work_list = p.overflow_list;
+        p.n_work = (int64_t) hc[CTR_OVERFLOW];
+        launch_match(p, true, (int) warps, stream);
+        out->n_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (hc[CTR_ERROR] != 0) return fail(BFQ_E_STATE, "tier-2 scratch exhausted (index statistics inconsistent)");
+    }
+    if (hc[CTR_RANGES] > sb.dyn_cap) {
+        out->want_dyn = std::max<uint64_t>(out->want_dyn, hc[CTR_RANGES]);
+        return BFQ_RETRY_GROW;
+    }
+    out->n_ranges += (int64_t) hc[CTR_RANGES];
+    out->n_flagged += (int64_t) hc[CTR_FLAGGED];
     if (hc[CTR_FLAGGED] > 0) {
         CapsParams c{};
-        c.flagged_list = h->d_flagged.p;
+        c.flagged_list = p.flagged_list;
         c.n_flagged = (int64_t) hc[CTR_FLAGGED];
-        c.topic_tenant = d_topic_tenant;
-        c.max_pfanout = h->d_tenant_tab.p + nt;
-        c.max_gfanout = h->d_tenant_tab.p + 2 * nt;
-        c.span_begin = h->d_span_begin.p;
-        c.span_count = h->d_span_count.p;
-        c.ranges = h->d_ranges.p;
+        c.topic_tenant = p.topic_tenant;
+        c.max_pfanout = p.max_pfanout;
+        c.max_gfanout = p.max_gfanout;
+        c.span_begin = p.span_begin;
+        c.span_count = p.span_count;
+        c.ranges = p.ranges;
         c.segs = h->d_segs.p;
         c.rkind = h->d_rkind.p;
         c.pfx_persistent = h->d_pfxP.p;
         c.pfx_group = h->d_pfxG.p;
-        c.kept_count = h->d_kept.p;
-        c.counters = h->d_counters.p;
-        for (int attempt = 0; attempt < 4; attempt++) {
-            c.throttled = h->d_throttled.p;
-            c.throttled_cap = h->d_throttled.cap;
-            CUDA_TRY(cudaMemsetAsync(h->d_counters.p + CTR_THROTTLED, 0, sizeof(unsigned long long), stream));
-            launch_caps(c, stream);
-            out->n_launches++;
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            if (hc[CTR_THROTTLED] <= h->d_throttled.cap) break;
-            CUDA_TRY(h->d_throttled.reserve((size_t) (hc[CTR_THROTTLED] + hc[CTR_THROTTLED] / 4 + 1024)));
+        c.kept_count = h->d_kept.p + b;
+        c.counters = d_ctr;
+        c.throttled = h->d_throttled.p + sb.thr_off;
+        c.throttled_cap = sb.thr_cap;
+        c.topic_base = (uint32_t) b;
+        launch_caps(c, stream);
+        out->n_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (hc[CTR_THROTTLED] > sb.thr_cap) {
+            out->want_thr = std::max<uint64_t>(out->want_thr, hc[CTR_THROTTLED]);
+            return BFQ_RETRY_GROW;
         }
-        out->n_throttled = (int64_t) hc[CTR_THROTTLED];
+        out->chunk_throttled[sb.chunk] = (int64_t) hc[CTR_THROTTLED];
+        out->n_throttled += (int64_t) hc[CTR_THROTTLED];
     }
-    h->launches += out->n_launches;
-    h->overflow_topics += out->n_overflow;
-    h->deferred_topics += out->n_deferred;
-    h->flagged_topics += out->n_flagged;
-    h->last_n_topics = n;
     return BFQ_OK;
+}
+
+// un-chunked match with automatic buffer growth (device path, and the host path's fallback)
+int32_t match_whole(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant, int64_t n,
+                    int32_t n_tenants, cudaStream_t stream, CoreOut* out) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int32_t rc = prepare_workspace(h, n, 1);
+        if (rc != BFQ_OK) return rc;
+        *out = CoreOut();
+        rc = match_core(h, d_topics, d_topic_off, d_topic_tenant, n_tenants, stream, whole_batch(h, n), out);
+        if (rc != BFQ_RETRY_GROW) {
+            if (rc == BFQ_OK) {
+                h->launches += out->n_launches;
+                h->overflow_topics += out->n_overflow;
+                h->deferred_topics += out->n_deferred;
+                h->flagged_topics += out->n_flagged;
+                h->last_n_topics = n;
+            }
+            return rc;
+        }
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (out->want_dyn) {
+            const size_t want = (size_t) ((uint64_t) n * INLINE_RANGES + out->want_dyn + out->want_dyn / 4 + 1024);
+            if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
+            CUDA_TRY(h->d_ranges.reserve(want));
+        }
+        if (out->want_thr) CUDA_TRY(h->d_throttled.reserve((size_t) (out->want_thr + out->want_thr / 4 + 1024)));
+    }
+    return fail(BFQ_E_STATE, "buffer sizing did not converge");
 }
 
 int64_t emit_bytes(const std::string& s, uint8_t* out, int64_t cap) {
@@ -335,6 +392,11 @@ int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
         if (e == cudaSuccess) e = cudaEventCreate(&ev);
     for (auto& ev : h->evk)
         if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto& ev : h->ev_h2d)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (auto& w : h->work_stream)
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete h;
         return fail(BFQ_E_CUDA, cudaGetErrorString(e));
@@ -540,75 +602,153 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     if (n > 0 && (!topics || !topic_off || !topic_tenant || !tenants || !tenant_off)) return fail(BFQ_E_INVALID, "NULL input");
     std::lock_guard<std::mutex> g(h->mu);
     if (!h->have_snapshot) return fail(BFQ_E_STATE, "bfq_match before the first bfq_index_commit");
-    for (int64_t i = 0; i < n; i++)
-        if (topic_tenant[i] < 0 || topic_tenant[i] >= n_tenants) return fail(BFQ_E_RANGE, "topic_tenant out of range");
+    // topic_tenant[i] is range-checked on the device (an index outside [0, n_tenants) yields an empty result)
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
     auto t0 = std::chrono::steady_clock::now();
     const size_t nn = (size_t) std::max<int64_t>(n, 1);
-    const int64_t blob_b = n ? topic_off[0] : 0, blob_e = n ? topic_off[n] : 0;
-    CUDA_TRY(h->d_topics.reserve((size_t) std::max<int64_t>(blob_e, 1)));
+    const int64_t blob_e = n ? topic_off[n] : 0;
+    CUDA_TRY(h->d_topics.reserve((size_t) std::max<int64_t>(blob_e, 1) + 64));
     CUDA_TRY(h->d_topic_off.reserve(nn + 1));
     CUDA_TRY(h->d_topic_tenant.reserve(nn));
-    CUDA_TRY(cudaEventRecord(h->ev[0], st));
-    if (n > 0) {
-        CUDA_TRY(cudaMemcpyAsync(h->d_topics.p + blob_b, topics + blob_b, (size_t) (blob_e - blob_b), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(h->d_topic_off.p, topic_off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(h->d_topic_tenant.p, topic_tenant, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    }
-    int32_t rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
-    if (rc != BFQ_OK) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev[1], st));
-    CoreOut co;
-    rc = match_core(h, h->d_topics.p, h->d_topic_off.p, h->d_topic_tenant.p, n, n_tenants, st, &co);
-    if (rc != BFQ_OK) return rc;
-    // ---- compact the sparse (inline + dynamic) ranges on the device, then D2H into the pinned result buffers
     CUDA_TRY(h->d_cnt.reserve(nn));
     CUDA_TRY(h->d_new_begin.reserve(nn));
-    CUDA_TRY(h->d_ranges_c.reserve((size_t) std::max<int64_t>(co.n_ranges, 1)));
-    CompactParams cp{};
-    cp.n_topics = n;
-    cp.span_begin = h->d_span_begin.p;
-    cp.span_count = h->d_span_count.p;
-    cp.ranges = h->d_ranges.p;
-    cp.counts = h->d_cnt.p;
-    cp.new_begin = h->d_new_begin.p;
-    cp.ranges_out = h->d_ranges_c.p;
-    cp.ranges_out_cap = h->d_ranges_c.cap;
-    cp.total_out = h->d_counters.p + CTR_ROUTES;
-    int64_t n_compact = 0;
-    if (n > 0) {
-        size_t tmp_bytes = 0;
-        CUDA_TRY(launch_compact(cp, nullptr, &tmp_bytes, st));
-        CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes));
-        CUDA_TRY(launch_compact(cp, h->d_scan_tmp.p, &tmp_bytes, st));
-        co.n_launches += 3;
-        h->launches += 3;
-        CUDA_TRY(cudaMemcpyAsync(h->h_counters.p, h->d_counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        n_compact = (int64_t) h->h_counters.p[CTR_ROUTES];
-    }
-    co.n_ranges = n_compact;
-    CUDA_TRY(cudaEventRecord(h->ev[2], st));
     CUDA_TRY(h->h_span_begin.reserve(nn));
     CUDA_TRY(h->h_span_count.reserve(nn));
     CUDA_TRY(h->h_route_count.reserve(nn));
-    CUDA_TRY(h->h_ranges.reserve((size_t) std::max<int64_t>(co.n_ranges, 1)));
-    CUDA_TRY(h->h_throttled.reserve((size_t) std::max<int64_t>(co.n_throttled, 1)));
-    if (n > 0) {
-        CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p, h->d_new_begin.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h->h_span_count.p, h->d_span_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h->h_route_count.p, h->d_route_count.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+
+    // Large batches are cut into sub-batches that flow through three streams: all H2D copies on one, the kernels +
+    // compaction + D2H of consecutive sub-batches alternating on two others, so the copy of sub-batch c+1 and the
+    // result read-back of c-1 overlap the kernels of c (PCIe is full duplex; the copies dominate the host path).
+    int C = n >= (1 << 17) ? 4 : 1;
+    CoreOut co;
+    int64_t rbase = 0, tbase = 0;
+    for (int attempt = 0;; attempt++) {
+        if (attempt == 8) return fail(BFQ_E_STATE, "buffer sizing did not converge");
+        int32_t rc = prepare_workspace(h, n, C);
+        if (rc != BFQ_OK) return rc;
+        CUDA_TRY(h->d_ranges_c.reserve(h->d_ranges.cap));
+        const uint64_t dyn_total = h->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
+        const uint64_t dyn_slice = dyn_total / (uint64_t) C, thr_slice = h->d_throttled.cap / (uint64_t) C;
+        size_t tmp_bytes = 0;
+        {
+            CompactParams q{};
+            q.n_topics = (n + C - 1) / C + 1;
+            q.counts = h->d_cnt.p;
+            q.new_begin = h->d_new_begin.p;
+            CUDA_TRY(launch_compact(q, nullptr, &tmp_bytes, h->stream, 1));
+            CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes * 2 + 512));   // one scratch per compute stream
+        }
+        co = CoreOut();
+        rbase = tbase = 0;
+        // ---- H2D of every sub-batch, back to back on the copy stream
+        CUDA_TRY(cudaEventRecord(h->ev[0], h->copy_stream));
+        rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, h->copy_stream);
+        if (rc != BFQ_OK) return rc;
+        int64_t bounds[MAX_CHUNKS + 1];
+        for (int c = 0; c <= C; c++) bounds[c] = n * c / C;
+        for (int c = 0; c < C && n > 0; c++) {
+            const int64_t b = bounds[c], e = bounds[c + 1];
+            const int64_t ob = topic_off[b], oe = topic_off[e];
+            CUDA_TRY(cudaMemcpyAsync(h->d_topic_off.p + b, topic_off + b, (size_t) (e - b + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_topic_tenant.p + b, topic_tenant + b, (size_t) (e - b) * sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_topics.p + ob, topics + ob, (size_t) (oe - ob), cudaMemcpyHostToDevice, h->copy_stream));
+            CUDA_TRY(cudaEventRecord(h->ev_h2d[c], h->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(h->ev[1], h->copy_stream));
+        bool retry = false;
+        for (int c = 0; c < C && n > 0; c++) {
+            cudaStream_t st = C == 1 ? h->stream : h->work_stream[c & 1];
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[c], 0));
+            SubBatch sb;
+            sb.begin = bounds[c];
+            sb.n = bounds[c + 1] - bounds[c];
+            sb.n_total = n;
+            sb.chunk = c;
+            sb.dyn_off = (uint64_t) c * dyn_slice;
+            sb.dyn_cap = dyn_slice;
+            sb.thr_off = (uint64_t) c * thr_slice;
+            sb.thr_cap = thr_slice;
+            rc = match_core(h, h->d_topics.p, h->d_topic_off.p, h->d_topic_tenant.p, n_tenants, st, sb, &co);
+            if (rc == BFQ_RETRY_GROW) {
+                retry = true;
+                break;
+            }
+            if (rc != BFQ_OK) {
+                cudaDeviceSynchronize();
+                return rc;
+            }
+            // ---- compaction of this sub-batch: counts + scan + total, then gather into the dense result position
+            unsigned long long* d_ctr = h->d_counters.p + (size_t) c * CTR_COUNT;
+            unsigned long long* hc = h->h_counters.p + (size_t) c * CTR_COUNT;
+            const uint64_t region = (uint64_t) sb.begin * INLINE_RANGES + sb.dyn_off;   // this sub-batch's private slice of d_ranges_c
+            CompactParams cp{};
+            cp.n_topics = sb.n;
+            cp.span_begin = h->d_span_begin.p + sb.begin;
+            cp.span_count = h->d_span_count.p + sb.begin;
+            cp.ranges = h->d_ranges.p + (uint64_t) sb.begin * INLINE_RANGES;
+            cp.counts = h->d_cnt.p + sb.begin;
+            cp.new_begin = h->d_new_begin.p + sb.begin;
+            cp.ranges_out = h->d_ranges_c.p + region;
+            cp.ranges_out_cap = (uint64_t) sb.n * INLINE_RANGES + sb.dyn_cap;
+            cp.total_out = d_ctr + CTR_ROUTES;
+            uint8_t* scan_tmp = h->d_scan_tmp.p + (size_t) (c & 1) * (tmp_bytes + 256) / 256 * 256;
+            CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 1));
+            CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const int64_t total_c = (int64_t) hc[CTR_ROUTES], thr_c = co.chunk_throttled[c];
+            // host result buffers grow by reallocation: wait for the copies in flight before moving them
+            if ((size_t) (rbase + total_c) > h->h_ranges.cap || (size_t) (tbase + thr_c) > h->h_throttled.cap) {
+                CUDA_TRY(cudaDeviceSynchronize());
+                if ((size_t) (rbase + total_c) > h->h_ranges.cap) {
+                    PinBuf<uint2> nb;
+                    CUDA_TRY(nb.reserve((size_t) ((rbase + total_c) * (C - c > 1 ? 2 : 1) + (1 << 16))));
+                    if (rbase) memcpy(nb.p, h->h_ranges.p, (size_t) rbase * sizeof(uint2));
+                    h->h_ranges.release();
+                    h->h_ranges = nb;
+                }
+                if ((size_t) (tbase + thr_c) > h->h_throttled.cap) {
+                    PinBuf<uint3> nb;
+                    CUDA_TRY(nb.reserve((size_t) ((tbase + thr_c) * 2 + 1024)));
+                    if (tbase) memcpy(nb.p, h->h_throttled.p, (size_t) tbase * sizeof(uint3));
+                    h->h_throttled.release();
+                    h->h_throttled = nb;
+                }
+            }
+            cp.out_base = (uint32_t) rbase;
+            CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 2));
+            co.n_launches += 4;
+            CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p + sb.begin, h->d_new_begin.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h->h_span_count.p + sb.begin, h->d_cnt.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h->h_route_count.p + sb.begin, h->d_route_count.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            if (total_c > 0)
+                CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p + rbase, h->d_ranges_c.p + region, (size_t) total_c * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+            if (thr_c > 0)
+                CUDA_TRY(cudaMemcpyAsync(h->h_throttled.p + tbase, h->d_throttled.p + sb.thr_off, (size_t) thr_c * sizeof(uint3), cudaMemcpyDeviceToHost, st));
+            rbase += total_c;
+            tbase += thr_c;
+        }
+        if (!retry) break;
+        // a slice of the range / throttled buffers was too small: grow them and redo the batch un-chunked
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (co.want_dyn) {
+            const size_t want = (size_t) ((uint64_t) n * INLINE_RANGES + (co.want_dyn + co.want_dyn / 4 + 1024) * (uint64_t) C);
+            if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
+            CUDA_TRY(h->d_ranges.reserve(want));
+        }
+        if (co.want_thr) CUDA_TRY(h->d_throttled.reserve((size_t) ((co.want_thr + co.want_thr / 4 + 1024) * (uint64_t) C)));
+        C = 1;
     }
-    if (co.n_ranges > 0)
-        CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p, h->d_ranges_c.p, (size_t) co.n_ranges * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-    if (co.n_throttled > 0)
-        CUDA_TRY(cudaMemcpyAsync(h->h_throttled.p, h->d_throttled.p, (size_t) co.n_throttled * sizeof(uint3), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(h->ev[3], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    // resolve multi-segment ranges? they are kept as-is; bfq_result_expand resolves them through the host segs copy.
-    // strip internal flag bits from the span counts
-    for (int64_t i = 0; i < n; i++) h->h_span_count.p[i] &= SPAN_COUNT_MASK;
+    CUDA_TRY(cudaStreamSynchronize(h->work_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->work_stream[1]));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    h->launches += co.n_launches;
+    h->overflow_topics += co.n_overflow;
+    h->deferred_topics += co.n_deferred;
+    h->flagged_topics += co.n_flagged;
+    h->last_n_topics = n;
+    co.n_ranges = rbase;
+    co.n_throttled = tbase;
     if (co.n_throttled > 1) {
         uint3* th = h->h_throttled.p;
         std::sort(th, th + co.n_throttled, [](const uint3& a, const uint3& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
@@ -623,13 +763,11 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     r->route_count = h->h_route_count.p;
     r->ranges = reinterpret_cast<const bfq_range*>(h->h_ranges.p);
     r->throttled = reinterpret_cast<const bfq_throttled*>(h->h_throttled.p);
-    float a = 0, b = 0, c = 0;
+    float a = 0;
     cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
-    r->ms[0] = a;
-    r->ms[1] = b;
-    r->ms[2] = c;
+    r->ms[0] = a;                       // H2D stream busy time (overlapped with the kernels of earlier sub-batches)
+    r->ms[1] = h->last_kernel_ms;       // tier-0 kernel of the first sub-batch
+    r->ms[2] = (double) C;              // number of sub-batches
     r->ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = r;
     return BFQ_OK;
@@ -701,14 +839,14 @@ int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* te
     int32_t rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
     if (rc != BFQ_OK) return rc;
     CoreOut co;
-    rc = match_core(h, d_topics, d_topic_off, d_topic_tenant, n, n_tenants, st, &co);
+    rc = match_whole(h, d_topics, d_topic_off, d_topic_tenant, n, n_tenants, st, &co);
     if (rc != BFQ_OK) return rc;
     out->d_span_begin = h->d_span_begin.p;
     out->d_span_count = h->d_span_count.p;
     out->d_route_count = h->d_route_count.p;
     out->d_ranges = reinterpret_cast<const bfq_range*>(h->d_ranges.p);
     out->d_throttled = reinterpret_cast<const bfq_throttled*>(h->d_throttled.p);
-    out->n_ranges = co.n_ranges;
+    out->n_ranges = (int64_t) ((uint64_t) n * INLINE_RANGES) + co.n_ranges;   // extent of the sparse range array
     out->n_throttled = co.n_throttled;
     out->n_routes = -1;
     out->n_overflow_topics = co.n_overflow;

@@ -55,8 +55,10 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
     __syncwarp();
     auto byte_at = [&](int i) -> uint32_t { return staged ? (uint32_t) ws.stage[i] : (uint32_t) src[i]; };
 
-    const int tenant = p.topic_tenant[t];
-    const int root_ord = p.tenant_root[tenant];
+    int tenant = p.topic_tenant[t];
+    const bool tenant_ok = tenant >= 0 && tenant < p.n_tenants;
+    if (!tenant_ok) tenant = 0;
+    const int root_ord = tenant_ok ? p.tenant_root[tenant] : -1;
     uint32_t n_rg = 0;
     uint32_t acc_r = 0;
     uint64_t acc_p = 0, acc_g = 0;
@@ -362,11 +364,13 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     __syncwarp();
                     for (int i = lane; i < (int) (end - cstart); i += 32) {
                         const int64_t o = p.topic_off[cstart + i], o2 = p.topic_off[cstart + i + 1];
-                        const int tn = p.topic_tenant[cstart + i];
+                        int tn = p.topic_tenant[cstart + i];
+                        const bool tn_ok = tn >= 0 && tn < p.n_tenants;
+                        if (!tn_ok) tn = 0;
                         ws.m_off[i] = (uint32_t) (o - cbase);
                         ws.m_len[i] = (uint32_t) min((int64_t) 0x7FFFFFFF, o2 - o);
                         ws.m_tenant[i] = tn;
-                        ws.m_root[i] = p.tenant_root[tn];
+                        ws.m_root[i] = tn_ok ? p.tenant_root[tn] : -1;
                     }
                     __syncwarp();
                     if (kPrefetch) {
@@ -540,13 +544,16 @@ __global__ void compact_counts_kernel(int64_t n, const uint32_t* span_count, uin
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) counts[i] = span_count[i] & SPAN_COUNT_MASK;
 }
+__global__ void compact_total_kernel(const CompactParams p) {
+    *p.total_out = (unsigned long long) p.new_begin[p.n_topics - 1] + p.counts[p.n_topics - 1];
+}
 __global__ void compact_gather_kernel(const CompactParams p) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_topics) return;
     const uint32_t c = p.counts[i], nb = p.new_begin[i], ob = p.span_begin[i];
     if ((uint64_t) nb + c <= p.ranges_out_cap)
         for (uint32_t j = 0; j < c; j++) p.ranges_out[nb + j] = p.ranges[ob + j];
-    if (i == p.n_topics - 1) *p.total_out = (unsigned long long) nb + c;
+    p.new_begin[i] = nb + p.out_base;   // final position in the concatenated result
 }
 
 // ------------------------------------------------------------------------------------------------ caps
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(CAPS_THREADS) caps_kernel(const CapsParams p) 
                 else if (kind == 2 && baseG + (p.pfx_group[r] - p.pfx_group[first]) >= maxG) drop = 2;
                 if (drop) {
                     const unsigned long long idx = atomicAdd(&p.counters[CTR_THROTTLED], 1ull);
-                    if (idx < p.throttled_cap) p.throttled[idx] = make_uint3(t, r, drop);
+                    if (idx < p.throttled_cap) p.throttled[idx] = make_uint3(t + p.topic_base, r, drop);
                 } else {
                     my_kept++;
                 }
@@ -674,14 +681,18 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
 }
 
-cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream) {
+cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase) {
     if (!d_scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
     if (p.n_topics <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned) ((p.n_topics + 255) / 256);
-    compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
-    if (e != cudaSuccess) return e;
-    compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
+    if (phase == 1) {   // clean counts, exclusive scan, total
+        compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
+        if (e != cudaSuccess) return e;
+        compact_total_kernel<<<1, 1, 0, stream>>>(p);
+    } else {            // gather into the dense array at p.ranges_out (already offset by the caller), rebase new_begin
+        compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ struct MatchParams {
     const int32_t* tenant_root;     // [n_tenants] root ordinal or -1 (tenant has no routes)
     const int32_t* max_pfanout;     // [n_tenants]
     const int32_t* max_gfanout;     // [n_tenants]
+    int32_t n_tenants;
     int64_t n_topics;
     // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
@@ -73,6 +74,7 @@ struct CapsParams {
     const uint32_t* pfx_persistent;
     const uint32_t* pfx_group;
     uint3* throttled;               // {topic, rank, kind}
+    uint32_t topic_base;            // added to the (sub-batch relative) topic index
     uint64_t throttled_cap;
     uint32_t* kept_count;           // [n] (optional) routes surviving per flagged topic
     unsigned long long* counters;
@@ -111,9 +113,11 @@ struct CompactParams {
     uint32_t* new_begin;            // out [n]
     uint2* ranges_out;              // out [total]
     uint64_t ranges_out_cap;
-    unsigned long long* total_out;  // device scalar: total number of ranges
+    uint32_t out_base;              // index of ranges_out[0] in the concatenated result (added to new_begin in phase 2)
+    unsigned long long* total_out;  // device scalar: total number of ranges (phase 1)
 };
-cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream);
+// phase 1: counts + exclusive scan + total; phase 2: gather (after the caller has read the total and placed ranges_out)
+cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase);
 int match_kernel_smem_bytes();
 
 }  // namespace bfq

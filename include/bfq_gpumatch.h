@@ -98,7 +98,9 @@ int32_t bfq_route_kinds(bfq_index* h, const int64_t* ranks, int64_t n, uint8_t* 
  * DW/cache/TenantRouteMatcher.java:68-161 + caps of DW/cache/MatchedRoutes.java:87-141),
  * batched over tenants. Topic i belongs to tenant topic_tenant[i] (index into the tenants list);
  * max_pfanout/max_gfanout are per tenant (Setting.MaxPersistentFanout / MaxGroupFanout).
- * Host buffers in, host result out (H2D + kernels + D2H inside the call).
+ * Host buffers in, host result out (H2D + kernels + D2H inside the call; batches of >= 128k topics are cut into four
+ * sub-batches pipelined over three streams so the copies overlap the kernels). A topic whose topic_tenant[i] is outside
+ * [0, n_tenants) simply matches nothing. Pinned (page-locked) host buffers give the best H2D rate.
  * ---------------------------------------------------------------------------------------------- */
 int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                   const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n_topics,
@@ -122,7 +124,8 @@ const bfq_throttled* bfq_result_throttled(const bfq_result* r, int64_t* n_thrott
 /* Convenience: flatten to CSR of surviving ranks, ascending per topic. offsets[n_topics+1]; returns the
  * total, copies only if it fits rank_cap. */
 int64_t bfq_result_expand(const bfq_result* r, int64_t* offsets, int64_t* ranks, int64_t rank_cap);
-/* timings of the call in milliseconds: 0 h2d, 1 kernels, 2 d2h, 3 total */
+/* timings of the call in milliseconds: 0 busy time of the H2D copy stream (overlapped with kernels), 1 device time
+ * of the tier-0 kernel of the first sub-batch, 2 number of pipelined sub-batches, 3 wall time of the whole call */
 int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n);
 void bfq_result_free(bfq_result* r);
 
@@ -135,7 +138,8 @@ typedef struct {
     const uint32_t* d_span_begin;   /* [n_topics] */
     const uint32_t* d_span_count;   /* [n_topics] */
     const uint32_t* d_route_count;  /* [n_topics] */
-    const bfq_range* d_ranges;      /* [n_ranges] */
+    const bfq_range* d_ranges;      /* sparse: topic i's ranges are d_ranges[d_span_begin[i] ... + d_span_count[i] & 0x3FFFFFFF);
+                                       n_ranges is the extent of the array, not the number of ranges */
     const bfq_throttled* d_throttled; /* [n_throttled] */
     int64_t n_ranges, n_throttled, n_routes;
     int64_t n_overflow_topics, n_flagged_topics, n_launches;
