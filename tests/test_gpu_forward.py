@@ -426,3 +426,39 @@ def test_baseline_configs_vs_oracle(B, config, scale, caps):
     hit = float((np.diff(offsets) > 0).mean())
     assert hit > 0.5, "workload should mostly hit (got %.2f)" % hit
     res.close()
+
+
+@pytest.mark.parametrize("caps", [(2 ** 31 - 1, 2 ** 31 - 1), (3, 1)])
+def test_pipelined_host_path_large_batch(B, caps):
+    """batches >= 128k topics go through the 4-sub-batch, 3-stream pipeline of bfq_match: same results, same throttle
+    events (absolute topic indices), dense ranges in topic order"""
+    w = B.workload.Workload("C3", scale=0.02)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    reps = (140000 + w.n_topics - 1) // w.n_topics
+    topics = w.topic_list() * reps
+    tt = np.tile(np.asarray(w.topic_tenant[:w.n_topics]), reps).astype(np.int32)
+    # shuffle so that sub-batches are not periodic copies of each other
+    perm = np.random.RandomState(5).permutation(len(topics))
+    topics = [topics[i] for i in perm]
+    tt = np.ascontiguousarray(tt[perm])
+    assert len(topics) >= 131072
+    tenants = w.tenants
+    nt = len(tenants)
+    res = idx.match_topics(tenants, topics, tt, [caps[0]] * nt, [caps[1]] * nt)
+    assert int(res.timings_ms["d2h"]) == 4   # number of pipelined sub-batches
+    offsets, ranks = res.expand()
+    # dense, topic-ordered ranges
+    sb, sc = res.span_begin.astype(np.int64), res.span_count.astype(np.int64)
+    assert (sb[1:] == sb[:-1] + sc[:-1]).all() and sb[0] == 0 and sb[-1] + sc[-1] == len(res.ranges)
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    want = kv.match_batch(tenants, topics, tt, caps[0], caps[1], O.MODE_TRIE, False, 8)
+    assert offsets.tolist() == want.offsets.tolist()
+    assert ranks.tolist() == want.ranks.tolist()
+    got_events = sorted((int(k), int(t), int(r)) for t, r, k in res.throttled.tolist())
+    assert got_events == sorted((k, t, r) for k, t, r, _ in want.events)
+    if caps[0] == 3:
+        assert len(got_events) > 1000 and max(e[1] for e in got_events) > 100000
+    res.close()
