@@ -460,5 +460,5 @@ def test_pipelined_host_path_large_batch(B, caps):
     got_events = sorted((int(k), int(t), int(r)) for t, r, k in res.throttled.tolist())
     assert got_events == sorted((k, t, r) for k, t, r, _ in want.events)
     if caps[0] == 3:
-        assert len(got_events) > 1000 and max(e[1] for e in got_events) > 100000
+        assert len(got_events) > 100 and max(e[1] for e in got_events) > 100000
     res.close()
