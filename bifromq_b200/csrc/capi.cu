@@ -122,14 +122,17 @@ struct bfq_index {
     // statistics
     int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0;
     // last device result (for bfq_expand_device)
-    int64_t last_n_topics = 0;
+    int64_t last_n_topics = 0, last_n_flagged = 0;
+    int32_t last_n_tenants = 0;
+    const int32_t* last_topic_tenant = nullptr;   // device pointer of the latest bfq_match_device call
+    DevBuf<unsigned long long> d_exp_counts;
 
     ~bfq_index() {
         cudaSetDevice(device);
         d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release(); d_tags.release();
         d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
-        d_flagged.release(); d_kept.release(); d_defer.release(); d_ranges_c.release(); d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
+        d_flagged.release(); d_kept.release(); d_defer.release(); d_exp_counts.release(); d_ranges_c.release(); d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
         d_counters.release(); h_counters.release(); h_tenant_tab.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -841,6 +844,9 @@ int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* te
     CoreOut co;
     rc = match_whole(h, d_topics, d_topic_off, d_topic_tenant, n, n_tenants, st, &co);
     if (rc != BFQ_OK) return rc;
+    h->last_topic_tenant = d_topic_tenant;
+    h->last_n_tenants = n_tenants;
+    h->last_n_flagged = co.n_flagged;
     out->d_span_begin = h->d_span_begin.p;
     out->d_span_count = h->d_span_count.p;
     out->d_route_count = h->d_route_count.p;
@@ -855,8 +861,50 @@ int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* te
     return BFQ_OK;
 }
 
-int32_t bfq_expand_device(bfq_index*, int64_t, int64_t*, int64_t*, int64_t, void*, int64_t*) {
-    return fail(BFQ_E_STATE, "bfq_expand_device: not available in this build");
+int32_t bfq_expand_device(bfq_index* h, int64_t n_topics, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap, void* stream,
+                          int64_t* n_ranks) {
+    if (!h || !d_offsets || n_topics < 0) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->have_snapshot || n_topics != h->last_n_topics || !h->last_topic_tenant)
+        return fail(BFQ_E_STATE, "bfq_expand_device must follow a bfq_match_device of the same batch");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t nt = (size_t) std::max(h->last_n_tenants, 1);
+    CUDA_TRY(h->d_exp_counts.reserve((size_t) n_topics + 1));
+    ExpandParams p{};
+    p.n_topics = n_topics;
+    p.span_begin = h->d_span_begin.p;
+    p.span_count = h->d_span_count.p;
+    p.route_count = h->d_route_count.p;
+    p.kept_count = h->d_kept.p;
+    p.ranges = h->d_ranges.p;
+    p.segs = h->d_segs.p;
+    p.counts = h->d_exp_counts.p;
+    p.offsets = d_offsets;
+    p.ranks = d_ranks;
+    p.rank_cap = d_ranks ? rank_cap : 0;
+    p.flagged_list = h->d_flagged.p;
+    p.n_flagged = h->last_n_flagged;
+    p.topic_tenant = h->last_topic_tenant;
+    p.max_pfanout = h->d_tenant_tab.p + nt;
+    p.max_gfanout = h->d_tenant_tab.p + 2 * nt;
+    p.rkind = h->d_rkind.p;
+    p.pfx_persistent = h->d_pfxP.p;
+    p.pfx_group = h->d_pfxG.p;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(launch_expand(p, nullptr, &tmp_bytes, st, 1));
+    CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes + 256));
+    CUDA_TRY(launch_expand(p, h->d_scan_tmp.p, &tmp_bytes, st, 1));
+    long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_offsets + n_topics, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_ranks) *n_ranks = (int64_t) total;
+    h->launches += 2;
+    if (d_ranks && total <= rank_cap) {
+        CUDA_TRY(launch_expand(p, h->d_scan_tmp.p, &tmp_bytes, st, 2));
+        h->launches += 2;
+    }
+    return BFQ_OK;
 }
 
 // ---------------------------------------------------------------- codec exports

@@ -29,6 +29,16 @@ __device__ __forceinline__ void load_slot(const Slot* s, uint32_t (&w)[16]) {
     w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
 }
 
+// payload half only (words 8..15): a '+' child or a tenant root is addressed directly, its key words are not needed —
+// one 32-byte sector instead of two
+template <bool kNA = false>
+__device__ __forceinline__ void load_payload(const Slot* s, uint32_t (&w)[16]) {
+    const uint4* p = reinterpret_cast<const uint4*>(s);
+    uint4 c = ld16<kNA>(p + 2), d = ld16<kNA>(p + 3);
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
+}
+
 // bytes of w equal to fp -> 0x80 in that byte (SWAR zero-byte test; it can also flag a byte just above a true
 // match — such a false candidate only costs one extra slot compare, a true match is never missed)
 __device__ __forceinline__ uint32_t match_bytes(uint32_t w, uint32_t fp4) {

@@ -81,7 +81,7 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
 
     if (root_ord >= 0) {
         uint32_t rw[16];
-        load_slot(p.roots + root_ord, rw);
+        load_payload(p.roots + root_ord, rw);
         const bool sys = len > 0 && byte_at(0) == '$';
         // "#" at level 0 matches every non-'$' topic
         emit(lane == 0 && !sys && rw[W_HASH_COUNT] > 0, rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI,
@@ -121,7 +121,7 @@ __device__ __forceinline__ void match_one(const MatchParams& p, WarpSmem& ws, ui
                 // '+' child record: independent of the token, issue its load first
                 const bool has_plus = active && plus != NONE31;
                 uint32_t pw[16];
-                if (has_plus) load_slot(p.slots + plus, pw);
+                if (has_plus) load_payload(p.slots + plus, pw);
                 // exact child: one probe per 24-byte chunk of the token (one chunk unless the level is > 24 B)
                 bool alive = active && (fe.z & FLAG_HAS_EXACT);
                 uint32_t node = fe.x, node_meta = fe.z, cid = 0;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     } else if (!kRootStep) {
                         // expand the tenant root right here instead of spending a lock-step DFS step on it
                         uint32_t rw[16];
-                        load_slot(p.roots + root_ord, rw);
+                        load_payload(p.roots + root_ord, rw);
                         const bool sys = len > 0 && p.topics[my_off] == '$';
                         if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI, (rw[W_CAPS] >> 16));
                         const uint32_t rplus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             const bool has_plus = rootstep || plus != NONE31;
             uint32_t pw[16];
             if (has_plus) {
-                if (rootstep) load_slot<false>(p.roots + node, pw);
-                else load_slot<kNA>(p.slots + plus, pw);
+                if (rootstep) load_payload<false>(p.roots + node, pw);
+                else load_payload<kNA>(p.slots + plus, pw);
             }
             uint32_t k[7];
 #pragma unroll
@@ -626,6 +626,59 @@ __global__ void __launch_bounds__(CAPS_THREADS) caps_kernel(const CapsParams p) 
     if (threadIdx.x == 0 && p.kept_count) p.kept_count[t] = (uint32_t) kept;
 }
 
+// ------------------------------------------------------------------------------------------------ expand (device CSR)
+__global__ void expand_counts_kernel(const ExpandParams p) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n_topics) p.counts[i] = (p.span_count[i] & SPAN_FLAGGED) ? p.kept_count[i] : p.route_count[i];
+    if (i == p.n_topics) p.counts[i] = 0;
+}
+// one warp per topic that needs no caps: every rank of every range
+__global__ void __launch_bounds__(256) expand_plain_kernel(const ExpandParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= p.n_topics || (p.span_count[t] & SPAN_FLAGGED)) return;
+    SegIter it{p.ranges + p.span_begin[t], p.segs, p.span_count[t] & SPAN_COUNT_MASK};
+    int64_t pos = p.offsets[t];
+    for (uint32_t j = 0; j < it.n; j++)
+        it.for_range(j, [&](uint32_t first, uint32_t count) {
+            for (uint32_t x = lane; x < count; x += 32)
+                if (pos + x < p.rank_cap) p.ranks[pos + x] = (int64_t) first + x;
+            pos += count;
+        });
+}
+// one CTA per cap-flagged topic: same classification as caps_kernel, the survivors are written
+__global__ void __launch_bounds__(CAPS_THREADS) expand_flagged_kernel(const ExpandParams p) {
+    const uint32_t t = p.flagged_list[blockIdx.x];
+    const int tenant = p.topic_tenant[t];
+    const uint64_t maxP = (uint64_t) max(p.max_pfanout[tenant], 0), maxG = (uint64_t) max(p.max_gfanout[tenant], 0);
+    SegIter it{p.ranges + p.span_begin[t], p.segs, p.span_count[t] & SPAN_COUNT_MASK};
+    __shared__ unsigned long long cursor;
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    const int64_t base = p.offsets[t];
+    for (uint32_t j = threadIdx.x; j < it.n; j += CAPS_THREADS) {
+        it.for_range(j, [&](uint32_t first, uint32_t count) {
+            uint64_t baseP = 0, baseG = 0;
+            for (uint32_t q = 0; q < it.n; q++)
+                it.for_range(q, [&](uint32_t f2, uint32_t c2) {
+                    if (f2 < first) {
+                        baseP += p.pfx_persistent[f2 + c2] - p.pfx_persistent[f2];
+                        baseG += p.pfx_group[f2 + c2] - p.pfx_group[f2];
+                    }
+                });
+            for (uint32_t r = first; r < first + count; r++) {
+                const uint8_t kind = p.rkind[r];
+                const bool drop = (kind == 1 && baseP + (p.pfx_persistent[r] - p.pfx_persistent[first]) >= maxP) ||
+                                  (kind == 2 && baseG + (p.pfx_group[r] - p.pfx_group[first]) >= maxG);
+                if (!drop) {
+                    const unsigned long long k = atomicAdd(&cursor, 1ull);
+                    if (base + (int64_t) k < p.rank_cap) p.ranks[base + k] = (int64_t) r;
+                }
+            }
+        });
+    }
+}
+
 }  // namespace
 
 int match_kernel_smem_bytes() { return (int) sizeof(WarpSmem) * WARPS_PER_CTA; }
@@ -693,6 +746,18 @@ cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp
     } else {            // gather into the dense array at p.ranges_out (already offset by the caller), rebase new_begin
         compact_gather_kernel<<<blocks, 256, 0, stream>>>(p);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand(const ExpandParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase) {
+    const int n1 = (int) p.n_topics + 1;
+    if (!d_scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, p.counts, reinterpret_cast<unsigned long long*>(p.offsets), n1, stream);
+    if (phase == 1) {
+        expand_counts_kernel<<<(unsigned) ((p.n_topics + 256) / 256), 256, 0, stream>>>(p);
+        return cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, reinterpret_cast<unsigned long long*>(p.offsets), n1, stream);
+    }
+    if (p.n_topics > 0) expand_plain_kernel<<<(unsigned) ((p.n_topics * 32 + 255) / 256), 256, 0, stream>>>(p);
+    if (p.n_flagged > 0) expand_flagged_kernel<<<(unsigned) p.n_flagged, CAPS_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -83,17 +83,28 @@ struct CapsParams {
 struct ExpandParams {
     int64_t n_topics;
     const uint32_t* span_begin;
-    const uint32_t* span_count;
-    const uint2* ranges;
+    const uint32_t* span_count;     // with SPAN_FLAGGED bits
+    const uint32_t* route_count;    // matched routes before caps
+    const uint32_t* kept_count;     // surviving routes of cap-flagged topics (written by the caps kernel)
+    const uint2* ranges;            // sparse
     const uint32_t* segs;
-    const int64_t* offsets;         // [n+1] exclusive scan of kept counts
-    int64_t* ranks;
+    unsigned long long* counts;     // scratch [n+1]
+    int64_t* offsets;               // out [n+1]
+    int64_t* ranks;                 // out
     int64_t rank_cap;
-    // throttled routes sorted by (topic, rank) for removal
-    const uint3* throttled;
-    int64_t n_throttled;
-    const uint32_t* thr_topic_begin; // [n+1] index into throttled per topic (only valid if n_throttled > 0)
+    // caps inputs for the flagged topics
+    const uint32_t* flagged_list;
+    int64_t n_flagged;
+    const int32_t* topic_tenant;
+    const int32_t* max_pfanout;
+    const int32_t* max_gfanout;
+    const uint8_t* rkind;
+    const uint32_t* pfx_persistent;
+    const uint32_t* pfx_group;
 };
+// device CSR of the surviving routes: phase 1 = per-topic counts + exclusive scan into offsets (offsets[n] = total),
+// phase 2 = write the ranks (unordered within a topic). tmp as for launch_compact.
+cudaError_t launch_expand(const ExpandParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase);
 
 // tier 0: one LANE per topic (DFS, bounded smem); tier 1: one WARP per topic; tier 2: warp per topic, global scratch
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream);

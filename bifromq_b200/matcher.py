@@ -171,6 +171,13 @@ class GpuRouteIndex:
         return out
 
 
+    def expand_device(self, n, d_offsets_ptr, d_ranks_ptr, rank_cap, stream=0):
+        """device CSR of the latest match_device result; returns the total number of surviving routes"""
+        total = C.c_int64(0)
+        N.check(N.lib.bfq_expand_device(self._h, n, d_offsets_ptr, d_ranks_ptr, rank_cap, stream, C.byref(total)))
+        return total.value
+
+
 class MatchedRoutes:
     """Read side of IMatchedRoutes for one (tenant, topic)."""
 

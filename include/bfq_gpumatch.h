@@ -148,8 +148,9 @@ int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* te
                          const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
                          int64_t n_topics, const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream,
                          bfq_device_result* out);
-/* Flatten a device result into device CSR (d_offsets[n_topics+1] int64, d_ranks int64 capacity rank_cap)
- * on the same stream; caps are applied (throttled routes removed). Returns total via *n_ranks. */
+/* Flatten the result of the latest bfq_match_device into a device CSR: d_offsets[n_topics+1] (int64) is always
+ * written, the surviving ranks (caps applied, unordered within a topic) are written to d_ranks if the total fits
+ * rank_cap (pass d_ranks = NULL to only size). Returns the total via *n_ranks. */
 int32_t bfq_expand_device(bfq_index* h, int64_t n_topics, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap,
                           void* stream, int64_t* n_ranks);
 

@@ -462,3 +462,34 @@ def test_pipelined_host_path_large_batch(B, caps):
     if caps[0] == 3:
         assert len(got_events) > 100 and max(e[1] for e in got_events) > 100000
     res.close()
+
+
+@pytest.mark.parametrize("caps", [(2 ** 31 - 1, 2 ** 31 - 1), (3, 1)])
+def test_device_resident_match_and_expand(B, caps):
+    """bfq_match_device (batch already in HBM, result left there) + bfq_expand_device == the host path"""
+    import torch
+    w = B.workload.Workload("C3", scale=0.01)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    tenants = w.tenants
+    nt, n = len(tenants), w.n_topics
+    dev = torch.device("cuda", 0)
+    d_topics = torch.from_numpy(np.ascontiguousarray(w.topics)).to(dev)
+    d_off = torch.from_numpy(np.ascontiguousarray(w.topic_off)).to(dev)
+    d_tt = torch.from_numpy(np.ascontiguousarray(w.topic_tenant[:n])).to(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, [caps[0]] * nt, [caps[1]] * nt, stream)
+    d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    total = idx.expand_device(n, d_offsets.data_ptr(), None, 0, stream)
+    d_ranks = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+    assert idx.expand_device(n, d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream) == total
+    torch.cuda.synchronize()
+    res = idx.match(tenants, w.topics, w.topic_off, w.topic_tenant[:n], [caps[0]] * nt, [caps[1]] * nt)
+    offsets, ranks = res.expand()
+    assert d_offsets.cpu().numpy().tolist() == offsets.tolist()
+    got = d_ranks.cpu().numpy()[:total]
+    for i in range(n):   # unordered within a topic on the device
+        assert sorted(got[offsets[i]:offsets[i + 1]].tolist()) == ranks[offsets[i]:offsets[i + 1]].tolist()
+    assert out.n_throttled == len(res.throttled)
+    res.close()
