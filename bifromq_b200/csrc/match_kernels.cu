@@ -286,7 +286,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 constexpr int L_WARPS = 4;
 constexpr int L_MAXLV = 12;
 constexpr int L_CHUNK = 64;
-constexpr int L_REFILL_MIN = 6;
 
 struct LaneSmem {
     uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
@@ -361,7 +360,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
         const unsigned idle = __ballot_sync(FULL, !have);
         // refill (and flush finished topics) only when enough lanes are idle: the refill path runs with few lanes active,
         // batching it amortises its instructions (ncu: ~180 of ~660 warp instructions per step sat in 2-lane blocks)
-        if (idle && (__popc(idle) >= L_REFILL_MIN || idle == FULL || !__any_sync(FULL, have))) {
+        if (idle && (__popc(idle) >= p.refill_min || idle == FULL || !__any_sync(FULL, have))) {
             if (done) flush();
             if (next >= end && !exhausted) {
                 unsigned long long c = 0;
@@ -744,7 +743,15 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int64_t ctas = (int64_t) sms * ctas_per_sm;
     const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;
-    kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
+    static int refill_min = -1;
+    if (refill_min < 0) {
+        const char* rm = getenv("BFQ_REFILL_MIN");
+        refill_min = rm ? atoi(rm) : 1;
+        if (refill_min < 1) refill_min = 1;
+    }
+    MatchParams q = p;
+    q.refill_min = refill_min;
+    kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(q);
 }
 
 cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase) {
