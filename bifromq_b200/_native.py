@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfq_gpumatch.so")
+LIB_PATH = os.environ.get("BFQ_LIB") or os.path.join(_HERE, "libbfq_gpumatch.so")   # BFQ_LIB: A/B experiments only
 WORKLOAD_LIB_PATH = os.path.join(_HERE, "libbfq_workload.so")
 
 
