@@ -165,8 +165,19 @@ void* orc_match_batch(void* h, int32_t mode, int32_t singleton, const uint8_t* t
     } else {
         std::vector<std::vector<int64_t>> per(n_tenants);
         for (int64_t i = 0; i < n; i++) per[topic_tenant[i]].push_back(i);
-        for (int64_t t = 0; t < n_tenants; t++)
-            if (!per[t].empty()) items.push_back({(int) t, std::move(per[t])});
+        // topics are independent: for the per-topic matchers (brute force, trie walk) split a tenant's topics into
+        // pieces so that one huge tenant does not serialise on a single thread; the literal algorithm keeps the
+        // whole-tenant batch (its topic trie is per matchAll call)
+        const size_t piece = mode == 0 ? (size_t) -1 : 512;
+        for (int64_t t = 0; t < n_tenants; t++) {
+            if (per[t].empty()) continue;
+            if (per[t].size() <= piece) {
+                items.push_back({(int) t, std::move(per[t])});
+            } else {
+                for (size_t b = 0; b < per[t].size(); b += piece)
+                    items.push_back({(int) t, std::vector<int64_t>(per[t].begin() + b, per[t].begin() + std::min(per[t].size(), b + piece))});
+            }
+        }
     }
     std::atomic<size_t> cursor{0};
     const int T = std::max(1, nthreads);

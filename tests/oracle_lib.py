@@ -313,8 +313,11 @@ class KV:
         return self.match_blobs(tb, toff, pb, poff, tt, n, max_persistent, max_group, mode, singleton, nthreads)
 
     def match_blobs(self, tb, toff, pb, poff, tt, n, max_persistent, max_group, mode, singleton, nthreads):
+        import time as _time
+        _t0 = _time.perf_counter()
         r = lib.orc_match_batch(self.h, mode, int(singleton), tb.ctypes.data, toff, len(toff) - 1, pb.ctypes.data, poff,
                                 tt, n, max_persistent, max_group, nthreads)
+        self.last_match_seconds = _time.perf_counter() - _t0   # the matcher alone, without copying the result out
         try:
             total = lib.orc_result_total_routes(r)
             offsets = np.zeros(n + 1, np.int64)
