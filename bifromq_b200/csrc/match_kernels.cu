@@ -310,28 +310,21 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     int64_t next = 0, end = 0, cstart = 0, cbase = 0;
     bool exhausted = false;
     // per-lane topic state; level < 0: the tenant root has not been expanded yet (`node` holds the root ordinal)
-    bool have = false, bad = false, done = false;   // done: walk finished, outputs not yet written (flushed at the next refill)
+    bool have = false, bad = false;
     uint32_t t = 0, node = 0 /* child ref a (root ordinal while level < 0) */, plusf = NONE31, meta = 0, pending = 0, n_rg = 0, acc_r = 0;
-    uint32_t acc_p = 0, acc_g = 0;                  // sums of the saturating per-node bytes; bit 31 = some byte was saturated
-    uint2* outp = p.ranges;                         // the topic's inline range slots
+    uint64_t acc_p = 0, acc_g = 0;
     int64_t my_off = 0;
     int len = 0, level = 0, tenant = 0;
 
     auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
-        if (n_rg < INLINE_RANGES) outp[n_rg] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
+        if (n_rg < INLINE_RANGES) p.ranges[(uint64_t) t * INLINE_RANGES + n_rg] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
         else bad = true;
         n_rg++;
         acc_r += count;
-        const uint32_t cp = caps & 0xFFu, cg = (caps >> 8) & 0xFFu;
-        acc_p += cp | (cp == 0xFFu ? 0x80000000u : 0u);
-        acc_g += cg | (cg == 0xFFu ? 0x80000000u : 0u);
+        acc_p += caps_value(caps & 0xFFu);
+        acc_g += caps_value((caps >> 8) & 0xFFu);
     };
-    // the walk of this lane's topic is over: outputs are written when the warp next refills (amortised over several lanes)
     auto finish = [&]() {
-        have = false;
-        done = true;
-    };
-    auto flush = [&]() {
         if (bad) {
             const unsigned long long idx = atomicAdd(&p.counters[CTR_DEFER], 1ull);
             p.defer_list[idx] = t;
@@ -340,9 +333,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             p.route_count[t] = 0;
         } else {
             const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
-            // a saturated byte (bit 31 set) means "at least this many": let the exact caps kernel decide
-            const bool flag_p = maxP != 0x7FFFFFFF && ((acc_p >> 31) || (acc_p & 0x7FFFFFFFu) > (uint32_t) (maxP < 0 ? 0 : maxP));
-            const bool flag_g = maxG != 0x7FFFFFFF && ((acc_g >> 31) || (acc_g & 0x7FFFFFFFu) > (uint32_t) (maxG < 0 ? 0 : maxG));
+            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint64_t) (maxP < 0 ? 0 : maxP);
+            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint64_t) (maxG < 0 ? 0 : maxG);
             const bool flagged = flag_p || flag_g;
             p.span_begin[t] = t * INLINE_RANGES;
             p.span_count[t] = n_rg | (flagged ? SPAN_FLAGGED : 0u);
@@ -352,16 +344,13 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 p.flagged_list[idx] = t;
             }
         }
-        done = false;
+        have = false;
     };
 
     while (true) {
         // ---- refill idle lanes with the next unclaimed topics
         const unsigned idle = __ballot_sync(FULL, !have);
-        // refill (and flush finished topics) only when enough lanes are idle: the refill path runs with few lanes active,
-        // batching it amortises its instructions (ncu: ~180 of ~660 warp instructions per step sat in 2-lane blocks)
-        if (idle && (__popc(idle) >= p.refill_min || idle == FULL || !__any_sync(FULL, have))) {
-            if (done) flush();
+        if (idle) {
             if (next >= end && !exhausted) {
                 unsigned long long c = 0;
                 if (lane == 0) c = atomicAdd(&p.counters[CTR_CHUNK], (unsigned long long) L_CHUNK);
@@ -400,7 +389,6 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 if (take) {
                     const int i = (int) (idx - cstart);
                     t = (uint32_t) idx;
-                    outp = p.ranges + (uint64_t) t * INLINE_RANGES;
                     my_off = cbase + (int64_t) ws.m_off[i];
                     len = (int) ws.m_len[i];
                     tenant = ws.m_tenant[i];
@@ -743,15 +731,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int64_t ctas = (int64_t) sms * ctas_per_sm;
     const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;
-    static int refill_min = -1;
-    if (refill_min < 0) {
-        const char* rm = getenv("BFQ_REFILL_MIN");
-        refill_min = rm ? atoi(rm) : 1;
-        if (refill_min < 1) refill_min = 1;
-    }
-    MatchParams q = p;
-    q.refill_min = refill_min;
-    kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(q);
+    kerns[variant]<<<(unsigned) ctas, L_WARPS * 32, 0, stream>>>(p);
 }
 
 cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase) {

@@ -38,7 +38,6 @@ struct MatchParams {
     const int32_t* max_pfanout;     // [n_tenants]
     const int32_t* max_gfanout;     // [n_tenants]
     int32_t n_tenants;
-    int32_t refill_min;             // tier 0: idle lanes needed before the warp refills (set by launch_match_lanes)
     int64_t n_topics;
     // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
