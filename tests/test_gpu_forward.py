@@ -493,3 +493,27 @@ def test_device_resident_match_and_expand(B, caps):
         assert sorted(got[offsets[i]:offsets[i + 1]].tolist()) == ranks[offsets[i]:offsets[i + 1]].tolist()
     assert out.n_throttled == len(res.throttled)
     res.close()
+
+
+def test_caps_with_saturated_node_counters(B):
+    """a node with >= 255 persistent / group routes saturates its one-byte caps counter: the topic must be handed to the
+    exact caps kernel, which then decides (no drops when the real count is below the cap)"""
+    pairs = []
+    for i in range(400):
+        normal(B, pairs, "t", "big/+", 1, "p%d" % i, "d", 1)
+    for i in range(300):
+        group(B, pairs, "t", "big/#", "g%03d" % i, {B.schema.receiver_url(0, "m", "d"): 1})
+    for i in range(10):
+        normal(B, pairs, "t", "big/x", 0, "n%d" % i, "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    topics = ["big/x", "big/y", "small"]
+    tt = np.zeros(3, np.int32)
+    for caps in [(1000, 1000), (400, 300), (399, 299), (100, 7), (0, 0), (2 ** 31 - 1, 100)]:
+        compare_with_oracle(B, idx, kv, ["t"], topics, tt, caps[0], caps[1], O.MODE_BRUTE)
+    before = idx.stats()["flagged_topics"]
+    res = idx.match_topics(["t"], topics, tt, [1000], [1000])
+    assert len(res.throttled) == 0 and res.route_count.tolist() == [710, 700, 0]
+    res.close()
+    assert idx.stats()["flagged_topics"] == before + 2   # saturated counters force the exact path even though nothing drops
