@@ -228,7 +228,7 @@ def main():
     idx.commit()
     t_build = time.perf_counter() - t_build
     stats = idx.stats()
-    tenants = w.tenants
+    tenants = idx.tenant_blob(w.tenants)   # marshalled once: the same tenant list serves every batch
     n = w.n_topics
     blob_bytes = int(w.topic_off[-1])
 

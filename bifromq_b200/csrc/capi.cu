@@ -99,6 +99,9 @@ struct bfq_index {
     cudaEvent_t evk[2] = {nullptr, nullptr};
     double last_kernel_ms = 0;
     size_t l2_window_bytes = 0;
+    bool tenant_tab_valid = false;     // resolved tenant table cached on the device (invalidated by commit)
+    uint64_t tenant_tab_fp = 0;
+    int32_t tenant_tab_n = 0;
     // snapshot on device
     DevBuf<Slot> d_slots, d_roots;
     DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
@@ -157,6 +160,21 @@ int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* ten
                         const int32_t* max_p, const int32_t* max_g, cudaStream_t stream) {
     if (n_tenants < 0) return fail(BFQ_E_INVALID, "n_tenants < 0");
     const size_t nt = (size_t) std::max(n_tenants, 1);
+    // the same tenant list + caps usually accompany every batch: fingerprint it and keep the device table
+    uint64_t fp = 0xcbf29ce484222325ull ^ (uint64_t) n_tenants;
+    auto mixin = [&](const void* p, size_t n) {
+        const uint8_t* b = (const uint8_t*) p;
+        for (size_t i = 0; i < n; i++) fp = (fp ^ b[i]) * 0x100000001b3ull;
+    };
+    if (n_tenants > 0) {
+        mixin(tenant_off, (size_t) (n_tenants + 1) * sizeof(int64_t));
+        mixin(tenants + tenant_off[0], (size_t) (tenant_off[n_tenants] - tenant_off[0]));
+        if (max_p) mixin(max_p, (size_t) n_tenants * 4);
+        if (max_g) mixin(max_g, (size_t) n_tenants * 4);
+        fp ^= (max_p ? 1u : 0u) | (max_g ? 2u : 0u);
+    }
+    if (h->tenant_tab_valid && h->tenant_tab_fp == fp && h->tenant_tab_n == n_tenants) return BFQ_OK;
+    CUDA_TRY(cudaStreamSynchronize(stream));   // the pinned staging table may still be in flight
     CUDA_TRY(h->h_tenant_tab.reserve(3 * nt));
     CUDA_TRY(h->d_tenant_tab.reserve(3 * nt));
     for (int32_t i = 0; i < n_tenants; i++) {
@@ -167,6 +185,10 @@ int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* ten
         h->h_tenant_tab.p[2 * nt + i] = max_g ? max_g[i] : 0x7FFFFFFF;
     }
     CUDA_TRY(cudaMemcpyAsync(h->d_tenant_tab.p, h->h_tenant_tab.p, 3 * nt * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));   // other streams of this handle read the table without an event
+    h->tenant_tab_valid = true;
+    h->tenant_tab_fp = fp;
+    h->tenant_tab_n = n_tenants;
     return BFQ_OK;
 }
 
@@ -481,6 +503,7 @@ int32_t bfq_index_commit(bfq_index* h) {
     h->flat = std::move(flat);
     h->committed = kv;
     h->have_snapshot = true;
+    h->tenant_tab_valid = false;
     // Keep the tag array resident in L2 (persisting access window): every lookup starts with a tag read and the
     // array (~1/64 of the table) competes for L2 with the streaming slot traffic. BFQ_L2PERSIST=0 disables.
     {

@@ -141,11 +141,24 @@ class GpuRouteIndex:
         return out[:len(ranks)]
 
     # ---- match
-    def match(self, tenants, topics_blob, topic_off, topic_tenant, max_pfanout=None, max_gfanout=None):
-        """tenants: list[str]; topics as (uint8 blob, int64 offsets[n+1]); topic_tenant int32[n]; caps per tenant."""
+    @staticmethod
+    def tenant_blob(tenants):
+        """pre-marshal a tenant list once when the same list is used for many batches"""
         tb, toff = N.as_blob(tenants)
+        return ("blob", tb, toff, len(tenants))
+
+    @staticmethod
+    def _tenants(tenants):
+        if isinstance(tenants, tuple) and tenants and tenants[0] == "blob":
+            return tenants[1], tenants[2], tenants[3]
+        tb, toff = N.as_blob(tenants)
+        return tb, toff, len(tenants)
+
+    def match(self, tenants, topics_blob, topic_off, topic_tenant, max_pfanout=None, max_gfanout=None):
+        """tenants: list[str] (or tenant_blob(...)); topics as (uint8 blob, int64 offsets[n+1]); topic_tenant int32[n];
+        caps per tenant."""
+        tb, toff, nt = self._tenants(tenants)
         n = len(topic_off) - 1
-        nt = len(tenants)
         mp = np.full(max(nt, 1), INT_MAX, np.int32) if max_pfanout is None else np.ascontiguousarray(max_pfanout, dtype=np.int32)
         mg = np.full(max(nt, 1), INT_MAX, np.int32) if max_gfanout is None else np.ascontiguousarray(max_gfanout, dtype=np.int32)
         tt = np.ascontiguousarray(topic_tenant, dtype=np.int32)
@@ -161,8 +174,7 @@ class GpuRouteIndex:
 
     def match_device(self, tenants, d_topics_ptr, d_topic_off_ptr, d_topic_tenant_ptr, n, max_pfanout=None,
                      max_gfanout=None, stream=0):
-        tb, toff = N.as_blob(tenants)
-        nt = len(tenants)
+        tb, toff, nt = self._tenants(tenants)
         mp = np.full(max(nt, 1), INT_MAX, np.int32) if max_pfanout is None else np.ascontiguousarray(max_pfanout, dtype=np.int32)
         mg = np.full(max(nt, 1), INT_MAX, np.int32) if max_gfanout is None else np.ascontiguousarray(max_gfanout, dtype=np.int32)
         out = N.BfqDeviceResult()
