@@ -88,7 +88,8 @@ struct bfq_result {
 
 struct bfq_index {
     int device = 0;
-    std::mutex mu;
+    std::mutex mu;         // device snapshot + workspace: matches, lookups, the snapshot swap of commit
+    std::mutex stage_mu;   // staging area: reset / load / apply and the (long) host-side rebuild of commit
     Staging staging;
     FlatIndex flat;          // host copy of the committed snapshot (segs / tenant map / stats are used on the host)
     KVBlob committed;        // committed KV (for bfq_route_lookup)
@@ -434,7 +435,7 @@ void bfq_index_destroy(bfq_index* h) { delete h; }
 
 int32_t bfq_index_reset(bfq_index* h) {
     if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
-    std::lock_guard<std::mutex> g(h->mu);
+    std::lock_guard<std::mutex> g(h->stage_mu);
     h->staging.reset();
     return BFQ_OK;
 }
@@ -442,7 +443,7 @@ int32_t bfq_index_reset(bfq_index* h) {
 int32_t bfq_index_load(bfq_index* h, const uint8_t* keys, const int64_t* key_off, const uint8_t* vals,
                        const int64_t* val_off, int64_t n) {
     if (!h || n < 0 || (n > 0 && (!keys || !key_off || !vals || !val_off))) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
+    std::lock_guard<std::mutex> g(h->stage_mu);
     std::string err;
     if (!h->staging.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
     return BFQ_OK;
@@ -452,7 +453,7 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
                         const int64_t* add_val_off, int64_t n_add, const uint8_t* del_keys, const int64_t* del_key_off,
                         int64_t n_del) {
     if (!h || n_add < 0 || n_del < 0) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
+    std::lock_guard<std::mutex> g(h->stage_mu);
     for (int64_t i = 0; i < n_add; i++) {
         sv k((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i]));
         DecodedKey d;
@@ -466,30 +467,43 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
 
 int32_t bfq_index_commit(bfq_index* h) {
     if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
-    std::lock_guard<std::mutex> g(h->mu);
+    // The rebuild runs under the staging lock only: matches keep running on the previous snapshot meanwhile and the
+    // new one is swapped in under the snapshot lock at the very end (two snapshots are resident for a moment).
+    std::lock_guard<std::mutex> gs(h->stage_mu);
     CUDA_TRY(cudaSetDevice(h->device));
     const KVBlob& kv = h->staging.materialize();
     FlatIndex flat;
     std::string err;
     if (!build_flat_index(kv, &flat, &err)) return fail(BFQ_E_INVALID, err);
-    // upload the new snapshot, then swap (matches are serialised by the handle mutex)
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(h->d_slots.reserve(flat.slots.size()));
-    CUDA_TRY(h->d_tags.reserve(flat.tags.size()));
-    CUDA_TRY(h->d_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
-    CUDA_TRY(h->d_segs.reserve(flat.segs.size()));
-    CUDA_TRY(h->d_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
-    CUDA_TRY(h->d_pfxP.reserve(flat.pfx_persistent.size()));
-    CUDA_TRY(h->d_pfxG.reserve(flat.pfx_group.size()));
-    CUDA_TRY(cudaMemcpy(h->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
+    DevBuf<Slot> n_slots, n_roots;
+    DevBuf<uint32_t> n_segs, n_pfxP, n_pfxG;
+    DevBuf<uint8_t> n_rkind, n_tags;
+    auto drop_new = [&]() { n_slots.release(); n_roots.release(); n_segs.release(); n_pfxP.release(); n_pfxG.release(); n_rkind.release(); n_tags.release(); };
+#define COMMIT_TRY(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            drop_new();                                                                             \
+            return fail(BFQ_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+        }                                                                                           \
+    } while (0)
+    COMMIT_TRY(n_slots.reserve(flat.slots.size()));
+    COMMIT_TRY(n_tags.reserve(flat.tags.size()));
+    COMMIT_TRY(n_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
+    COMMIT_TRY(n_segs.reserve(flat.segs.size()));
+    COMMIT_TRY(n_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
+    COMMIT_TRY(n_pfxP.reserve(flat.pfx_persistent.size()));
+    COMMIT_TRY(n_pfxG.reserve(flat.pfx_group.size()));
+    COMMIT_TRY(cudaMemcpy(n_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    COMMIT_TRY(cudaMemcpy(n_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
     if (!flat.roots.empty())
-        CUDA_TRY(cudaMemcpy(h->d_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        COMMIT_TRY(cudaMemcpy(n_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    COMMIT_TRY(cudaMemcpy(n_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!flat.rkind.empty())
-        CUDA_TRY(cudaMemcpy(h->d_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        COMMIT_TRY(cudaMemcpy(n_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
+    COMMIT_TRY(cudaMemcpy(n_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    COMMIT_TRY(cudaMemcpy(n_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+#undef COMMIT_TRY
     // the host keeps only what it needs after the upload
     flat.slots.clear();
     flat.slots.shrink_to_fit();
@@ -500,8 +514,18 @@ int32_t bfq_index_commit(bfq_index* h) {
     flat.pfx_persistent.shrink_to_fit();
     flat.pfx_group.clear();
     flat.pfx_group.shrink_to_fit();
+    KVBlob committed = kv;   // snapshot of the raw KV for bfq_route_lookup
+    // ---- swap under the snapshot lock (no match is in flight while we hold it)
+    std::unique_lock<std::mutex> g(h->mu);
+    std::swap(h->d_slots, n_slots);
+    std::swap(h->d_tags, n_tags);
+    std::swap(h->d_roots, n_roots);
+    std::swap(h->d_segs, n_segs);
+    std::swap(h->d_rkind, n_rkind);
+    std::swap(h->d_pfxP, n_pfxP);
+    std::swap(h->d_pfxG, n_pfxG);
     h->flat = std::move(flat);
-    h->committed = kv;
+    h->committed = std::move(committed);
     h->have_snapshot = true;
     h->tenant_tab_valid = false;
     // Keep the tag array resident in L2 (persisting access window): every lookup starts with a tag read and the
@@ -518,6 +542,8 @@ int32_t bfq_index_commit(bfq_index* h) {
             cudaGetLastError();
         }
     }
+    g.unlock();
+    drop_new();   // the previous snapshot's buffers
     return BFQ_OK;
 }
 

@@ -65,7 +65,8 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
                         const int64_t* add_val_off, int64_t n_add, const uint8_t* del_keys, const int64_t* del_key_off,
                         int64_t n_del);
 
-/* Publish the staged state as a new immutable device snapshot (matches always see a whole snapshot). */
+/* Publish the staged state as a new immutable device snapshot. The host-side rebuild and the upload run while matches
+ * continue on the previous snapshot; the swap is atomic with respect to matches (they always see a whole snapshot). */
 int32_t bfq_index_commit(bfq_index* h);
 
 /* stats[k], k < n: 0 routes, 1 tenants, 2 trie nodes, 3 hash-table slots, 4 device bytes, 5 max nodes per
@@ -106,7 +107,8 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
                   const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n_topics,
                   const int32_t* max_pfanout, const int32_t* max_gfanout, bfq_result** out);
 
-/* Result layout (all arrays live as long as the result):
+/* Result layout. The arrays live in pinned memory owned by the index: they are valid until bfq_result_free() or the
+ * NEXT bfq_match on the same handle, whichever comes first (copy what must outlive that):
  *   span_begin[i], span_count[i]   topic i's matched route RANGES are ranges[span_begin[i] ... +span_count[i])
  *   ranges[j] = {first rank, count} a run of consecutive route ranks (one matched filter's routes)
  *   route_count[i]                 routes matched by topic i before caps

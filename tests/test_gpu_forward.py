@@ -517,3 +517,43 @@ def test_caps_with_saturated_node_counters(B):
     assert len(res.throttled) == 0 and res.route_count.tolist() == [710, 700, 0]
     res.close()
     assert idx.stats()["flagged_topics"] == before + 2   # saturated counters force the exact path even though nothing drops
+
+
+def test_matches_keep_running_during_commit(B):
+    """bfq_index_commit rebuilds under the staging lock only: concurrent matches keep answering from the previous snapshot and
+    every answer is a whole-snapshot answer (old or new, never a mix)"""
+    import threading
+    w = B.workload.Workload("C3", scale=0.02)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    tenants = w.tenants
+    topics = w.topic_list()[:2000]
+    tt = np.ascontiguousarray(w.topic_tenant[:2000])
+
+    def snapshot_answer():
+        r = idx.match_topics(tenants, topics, tt)
+        rc = r.route_count.copy()
+        r.close()
+        return rc.tolist()
+    old = snapshot_answer()
+    # the delta: a catch-all '#' route for every tenant -> every non-'$' topic gains exactly one route
+    extra = [(B.schema.route_key(t, "#", B.schema.receiver_url(0, "catchall", "d")), B.schema.incarnation_bytes(1)) for t in tenants]
+    idx.apply(adds=extra)
+    new_expected = [c + 1 for c in old]
+    seen, stop, errs = [], threading.Event(), []
+
+    def matcher():
+        try:
+            while not stop.is_set():
+                seen.append(snapshot_answer())
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+    th = threading.Thread(target=matcher)
+    th.start()
+    idx.commit()
+    stop.set()
+    th.join()
+    assert not errs
+    assert snapshot_answer() == new_expected
+    assert seen and all(s == old or s == new_expected for s in seen)
