@@ -51,36 +51,50 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (the sampler is started early so that its
+    first samples exist before the region begins; rows are then filtered by timestamp)."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:   # wait for the first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        inside = [r for ts, r in self.rows if self.t_begin is not None and self.t_begin - 0.02 <= ts <= (self.t_end or ts) + 0.04]
+        rows = inside or [r for _, r in self.rows[-3:]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -90,7 +104,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 def make_workload(args, rank, world):
@@ -250,13 +264,14 @@ def main():
         r.close()
         return d2h, tm
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms, launches, n_ranges, n_overflow = [], 0, 0, 0
     torch.cuda.synchronize(dev)
@@ -286,6 +301,7 @@ def main():
         t0 = time.perf_counter()
         d2h_bytes, e2e_tm = step_e2e()
         e2e_t.append(time.perf_counter() - t0)
+    sampler.end()
     clocks = sampler.stop()
     e2e_total = float(sum(e2e_t))
     h2d_bytes = blob_bytes + 8 * (n + 1) + 4 * n
