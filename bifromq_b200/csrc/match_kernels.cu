@@ -278,14 +278,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 //     '/' with a SWAR zero-byte test — the level table is filled lazily, there is no tokenising pre-pass —,
 //     issues the exact-child probe and the '+' child load together (eight independent LDG.128) and writes the
 //     discovered ranges straight to the topic's INLINE_RANGES inline slots: no staging, no output atomics;
-//   * a lane that finishes takes the next topic at once (warp-uniform refill from 128-topic chunks claimed with
+//   * a lane that finishes takes the next topic at once (warp-uniform refill from 32-topic chunks claimed with
 //     one atomicAdd per chunk), so a straggler never idles the other 31 lanes (v2 of this kernel waited for the
 //     whole batch of 32: ncu showed 10 of 32 lanes active, profiles/r1_v2_*).
 // Anything that does not fit the bounded state (> 16 levels, a level > 24 B, > INLINE_RANGES ranges, topic > 64 KB)
 // is handed, whole, to the warp-per-topic tier through defer_list.
 constexpr int L_WARPS = 4;
 constexpr int L_MAXLV = 12;
-constexpr int L_CHUNK = 64;
+constexpr int L_CHUNK = 32;
 
 struct LaneSmem {
     uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
@@ -727,7 +727,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    // persistent grid (SM count x resident CTAs); warps claim 64-topic chunks with one atomicAdd each
+    // persistent grid (SM count x resident CTAs); warps claim 32-topic chunks with one atomicAdd each
     int64_t ctas = (int64_t) sms * ctas_per_sm;
     const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;
