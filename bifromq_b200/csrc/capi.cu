@@ -564,9 +564,13 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     if (n < 0 || !stats) return fail(BFQ_E_INVALID, "bad argument");
     Staging st;
     std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
     if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
+    const KVBlob& snapshot = st.materialize();
+    const auto t1 = std::chrono::steady_clock::now();
     FlatIndex flat;
-    if (!build_flat_index(st.materialize(), &flat, &err)) return fail(BFQ_E_INVALID, err);
+    if (!build_flat_index(snapshot, &flat, &err)) return fail(BFQ_E_INVALID, err);
+    const auto t2 = std::chrono::steady_clock::now();
     // self-check: every placed node is found again from its parent's record the way the kernels look it up
     {
         EdgeTable t;
@@ -603,6 +607,8 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     for (int32_t i = 0; i < n_stats && i < 8; i++) stats[i] = v[i];
     if (n_stats > 8) stats[8] = flat.overflowed_blocks;
     for (int32_t i = 9; i < n_stats && i < 9 + 5; i++) stats[i] = flat.child_hist[i - 9];
+    if (n_stats > 14) stats[14] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();   // staging
+    if (n_stats > 15) stats[15] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();   // flatten
     return BFQ_OK;
 }
 

@@ -2,7 +2,12 @@
 #include "index_builder.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace bfq {
 
@@ -113,7 +118,7 @@ public:
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> multi_lists;
     int64_t n_cont = 0;
 
-    Builder() { table_.assign(1u << 16, NONE); }
+    Builder() { table_.assign(1u << 8, NONE); }
 
     uint32_t new_root(uint32_t ordinal) {
         nodes.emplace_back();
@@ -216,254 +221,213 @@ inline uint32_t sat16(uint32_t v) { return v > 0xFFFFu ? 0xFFFFu : v; }
 
 }  // namespace
 
-bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
-    *out = FlatIndex();
-    const int64_t n = kv.n();
-    if (n >= (int64_t) 0x7FFFFFFF) {
-        if (err) *err = "too many routes for 31-bit ranks";
-        return false;
-    }
-    out->n_routes = n;
-    out->rkind.resize((size_t) n);
-    out->pfx_persistent.resize((size_t) n + 1);
-    out->pfx_group.resize((size_t) n + 1);
-    Builder b;
-    b.nodes.reserve((size_t) std::min<int64_t>(n * 2 + 16, 1 << 28));
+namespace {
 
-    sv cur_tenant;
-    bool have_tenant = false;
-    uint32_t cur_root = NONE;
-    std::vector<sv> path_levels;          // levels of the previous key of this tenant
-    std::vector<uint32_t> path_nodes;     // node reached after consuming path_levels[i]
-    std::vector<uint32_t> depth_count;    // real nodes per depth of the current tenant
-    int64_t tenant_nodes = 0;
-    std::vector<sv> levels;
-    auto close_tenant = [&]() {
-        for (uint32_t c : depth_count) out->max_nodes_per_depth = std::max<int64_t>(out->max_nodes_per_depth, c);
-        out->max_tenant_nodes = std::max(out->max_tenant_nodes, tenant_nodes);
-        depth_count.clear();
-        tenant_nodes = 0;
-    };
+struct ChildPlan { uint8_t lg; uint8_t big; uint16_t seed; };
 
+// Everything about one tenant's trie; tenants are independent, so phases B and D run one tenant per task in parallel.
+struct TenantBuild {
+    sv tenant;
+    int64_t lo = 0, hi = 0;               // rank range of the tenant's routes
+    uint32_t ordinal = 0;
+    Builder b;                            // local node indices; node 0 is the tenant root
+    std::vector<uint32_t> child_off, child_list;
+    std::vector<ChildPlan> plan;
+    uint64_t csr_slots = 0, big_edges = 0, seg_words = 0;
+    uint32_t pp = 0, pg = 0;              // persistent / group routes of this tenant
+    int64_t max_depth_nodes = 0, tenant_nodes = 0;
+    int64_t child_hist[5] = {0, 0, 0, 0, 0};
+    std::string err;
+    // assigned between the phases
+    uint64_t region_base = 0, seg_base = 0;
+    uint32_t pp_base = 0, pg_base = 0;
+    int64_t n_multi = 0;
+};
+
+// phase B: decode the tenant's keys, build its trie, plan the child arrays
+void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
+    Builder& b = tb.b;
+    const uint32_t root = b.new_root(0);
+    std::vector<sv> path_levels, levels;
+    std::vector<uint32_t> path_nodes, depth_count;
     uint32_t pp = 0, pg = 0;
-    for (int64_t r = 0; r < n; r++) {
+    for (int64_t r = tb.lo; r < tb.hi; r++) {
         DecodedKey d;
         if (!decode_route_key(kv.key(r), &d)) {
-            if (err) *err = "undecodable route key at rank " + std::to_string(r);
-            return false;
+            tb.err = "undecodable route key at rank " + std::to_string(r);
+            return;
         }
         out->rkind[(size_t) r] = (uint8_t) d.kind;
-        out->pfx_persistent[(size_t) r] = pp;
+        out->pfx_persistent[(size_t) r] = pp;   // tenant-local for now, rebased in phase D
         out->pfx_group[(size_t) r] = pg;
         if (d.kind == KIND_PERSISTENT) pp++;
         else if (d.kind == KIND_GROUP) pg++;
-
-        if (!have_tenant || d.tenant != cur_tenant) {
-            if (have_tenant) close_tenant();
-            cur_tenant = d.tenant;
-            have_tenant = true;
-            auto it = out->tenant_ordinal.find(std::string(d.tenant));
-            if (it == out->tenant_ordinal.end()) {
-                uint32_t ord = (uint32_t) out->tenant_ordinal.size();
-                out->tenant_ordinal.emplace(std::string(d.tenant), ord);
-                cur_root = b.new_root(ord);
-            } else {
-                // cannot happen for sorted keys (the tenant id is the key prefix)
-                if (err) *err = "tenant keys are not contiguous";
-                return false;
-            }
-            path_levels.clear();
-            path_nodes.clear();
-        }
         levels.clear();
         for_each_level(d.escaped_filter, '\0', [&](sv l) { levels.push_back(l); });
         const bool multi_wild = levels.back().size() == 1 && levels.back()[0] == '#';
         const size_t walk = multi_wild ? levels.size() - 1 : levels.size();
-        // reuse the longest common prefix with the previous key's path
-        size_t k = 0;
+        size_t k = 0;   // reuse the longest common prefix with the previous key's path
         while (k < walk && k < path_levels.size() && path_levels[k] == levels[k]) k++;
         path_levels.resize(k);
         path_nodes.resize(k);
-        uint32_t node = k ? path_nodes[k - 1] : cur_root;
+        uint32_t node = k ? path_nodes[k - 1] : root;
         for (; k < walk; k++) {
             bool created = false;
             node = b.descend(node, levels[k], &created);
             if (created) {
                 if (depth_count.size() <= k) depth_count.resize(k + 1, 0);
                 depth_count[k]++;
-                tenant_nodes++;
+                tb.tenant_nodes++;
             }
             path_levels.push_back(levels[k]);
             path_nodes.push_back(node);
         }
         b.add_route(multi_wild ? b.nodes[node].hash : b.nodes[node].own, (uint32_t) r, d.kind);
     }
-    if (have_tenant) close_tenant();
-    out->pfx_persistent[(size_t) n] = pp;
-    out->pfx_group[(size_t) n] = pg;
-    out->n_cont_chunks = b.n_cont;
-
-    // ---- flatten. Exact children of a node go either into a private perfect-hashed array (small fan-out) or into the
-    // global tag table (big fan-out); '+' children get a slot of their own. Nodes are laid out in BFS order so a parent's
-    // id is known before its children are keyed, and siblings are adjacent in memory.
-    const size_t total_nodes = b.nodes.size();
-    const size_t n_roots = out->tenant_ordinal.size();
-    out->n_nodes = (int64_t) total_nodes;
+    tb.pp = pp;
+    tb.pg = pg;
+    for (uint32_t c : depth_count) tb.max_depth_nodes = std::max<int64_t>(tb.max_depth_nodes, c);
     // group the exact children by parent (counting sort)
-    std::vector<uint32_t> child_off(total_nodes + 1, 0);
-    for (size_t i = 0; i < total_nodes; i++) {
+    const size_t N = b.nodes.size();
+    tb.child_off.assign(N + 1, 0);
+    for (size_t i = 0; i < N; i++) {
         const BNode& nd = b.nodes[i];
-        if (nd.parent != NONE && nd.lenw != LEN_PLUS) child_off[nd.parent + 1]++;
+        if (nd.parent != NONE && nd.lenw != LEN_PLUS) tb.child_off[nd.parent + 1]++;
     }
-    for (size_t i = 0; i < total_nodes; i++) child_off[i + 1] += child_off[i];
-    std::vector<uint32_t> child_list(child_off[total_nodes]);
+    for (size_t i = 0; i < N; i++) tb.child_off[i + 1] += tb.child_off[i];
+    tb.child_list.resize(tb.child_off[N]);
     {
-        std::vector<uint32_t> fill(child_off.begin(), child_off.end() - 1);
-        for (size_t i = 0; i < total_nodes; i++) {
+        std::vector<uint32_t> fill(tb.child_off.begin(), tb.child_off.end() - 1);
+        for (size_t i = 0; i < N; i++) {
             const BNode& nd = b.nodes[i];
-            if (nd.parent != NONE && nd.lenw != LEN_PLUS) child_list[fill[nd.parent]++] = (uint32_t) i;
+            if (nd.parent != NONE && nd.lenw != LEN_PLUS) tb.child_list[fill[nd.parent]++] = (uint32_t) i;
         }
     }
-    // sizing pass: per parent choose {single, perfect hash of 2^lg slots with a seed, big}
-    struct ChildPlan { uint8_t lg; uint8_t big; uint16_t seed; };
-    std::vector<ChildPlan> plan(total_nodes, ChildPlan{0, 0, 0});
-    uint64_t n_big_edges = 0, csr_slots = 0;
-    {
-        std::vector<uint32_t> t32, seen;
-        for (size_t i = 0; i < total_nodes; i++) {
-            const uint32_t c = child_off[i + 1] - child_off[i];
-            if (b.nodes[i].plus != NONE) csr_slots++;
-            if (c == 0) continue;
-            ChildPlan& pl = plan[i];
-            t32.clear();
-            for (uint32_t j = child_off[i]; j < child_off[i + 1]; j++) {
-                const BNode& ch = b.nodes[child_list[j]];
-                t32.push_back(fold32(token_hash(ch.lenw, ch.tok)));
-            }
-            bool big = c > SMALL_FANOUT_MAX;
-            if (!big && c == 1) {
-                pl.lg = 0;
-                pl.seed = (uint16_t) (t32[0] & 0xFFFFu);
-            } else if (!big) {
-                std::vector<uint32_t> sorted(t32);
-                std::sort(sorted.begin(), sorted.end());
-                if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) big = true;   // 32-bit fold collision
-                uint32_t lg = 1;
-                while ((1u << lg) < c) lg++;
-                if (c > 4) lg++;
-                bool found = false;
-                for (; !big && !found && lg <= 8; lg++) {
-                    for (uint32_t seed = 0; seed < 65536 && !found; seed++) {
-                        uint64_t mask_lo = 0, mask_hi = 0, mask_2 = 0, mask_3 = 0;   // up to 256 positions
-                        bool ok = true;
-                        for (uint32_t v : t32) {
-                            const uint32_t idx = child_index(v, seed, lg);
-                            uint64_t& m = idx < 64 ? mask_lo : (idx < 128 ? mask_hi : (idx < 192 ? mask_2 : mask_3));
-                            const uint64_t bit = 1ull << (idx & 63);
-                            if (m & bit) { ok = false; break; }
-                            m |= bit;
-                        }
-                        if (ok) {
-                            found = true;
-                            pl.lg = (uint8_t) lg;
-                            pl.seed = (uint16_t) seed;
-                        }
+    // per parent choose {single child + fingerprint, perfect hash of 2^lg slots with a seed, big (global tag table)}
+    tb.plan.assign(N, ChildPlan{0, 0, 0});
+    std::vector<uint32_t> t32, sorted;
+    for (size_t i = 0; i < N; i++) {
+        const BNode& nd = b.nodes[i];
+        const uint32_t c = tb.child_off[i + 1] - tb.child_off[i];
+        tb.child_hist[std::min<uint32_t>(c, 4)]++;
+        if (nd.plus != NONE) tb.csr_slots++;
+        for (const Target* t : {&nd.own, &nd.hash})
+            if (t->multi >= 0) tb.seg_words += 2 + 2 * (b.multi_lists[t->multi].size() + 1);
+        if (c == 0) continue;
+        ChildPlan& pl = tb.plan[i];
+        t32.clear();
+        for (uint32_t j = tb.child_off[i]; j < tb.child_off[i + 1]; j++) {
+            const BNode& ch = b.nodes[tb.child_list[j]];
+            t32.push_back(fold32(token_hash(ch.lenw, ch.tok)));
+        }
+        bool big = c > SMALL_FANOUT_MAX;
+        if (!big && c == 1) {
+            pl.lg = 0;
+            pl.seed = (uint16_t) (t32[0] & 0xFFFFu);
+        } else if (!big) {
+            sorted = t32;
+            std::sort(sorted.begin(), sorted.end());
+            if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) big = true;   // 32-bit fold collision
+            uint32_t lg = 1;
+            while ((1u << lg) < c) lg++;
+            if (c > 4) lg++;
+            bool found = false;
+            for (; !big && !found && lg <= 8; lg++) {
+                for (uint32_t seed = 0; seed < 65536 && !found; seed++) {
+                    uint64_t mask[4] = {0, 0, 0, 0};   // up to 256 positions
+                    bool ok = true;
+                    for (uint32_t v : t32) {
+                        const uint32_t idx = child_index(v, seed, lg);
+                        const uint64_t bit = 1ull << (idx & 63);
+                        if (mask[idx >> 6] & bit) { ok = false; break; }
+                        mask[idx >> 6] |= bit;
                     }
-                    if (found) break;
+                    if (ok) {
+                        found = true;
+                        pl.lg = (uint8_t) lg;
+                        pl.seed = (uint16_t) seed;
+                    }
                 }
-                if (!found) big = true;
+                if (found) break;
             }
-            if (big) {
-                pl.big = 1;
-                n_big_edges += c;
-            } else {
-                csr_slots += 1ull << pl.lg;
-            }
+            if (!found) big = true;
+        }
+        if (big) {
+            pl.big = 1;
+            tb.big_edges += c;
+        } else {
+            tb.csr_slots += 1ull << pl.lg;
         }
     }
-    EdgeTable table;
-    table.init(n_big_edges);
-    const uint64_t csr_base = (uint64_t) table.n_blocks * BLOCK_SLOTS;
-    if (csr_base + csr_slots >= 0x7FFFFFF0ull) {
-        if (err) *err = "index too large for 31-bit slot ids";
-        return false;
-    }
-    {
-        Slot empty;
-        memset(empty.w, 0, sizeof(empty.w));
-        empty.w[W_PARENT] = EMPTY_PARENT;
-        table.slots.resize((size_t) (csr_base + csr_slots), empty);
-    }
-    out->roots.assign(n_roots, Slot());
-    std::vector<uint32_t> id_of(total_nodes, NONE), child_base(total_nodes, 0);
-    // BFS placement
-    {
-        std::vector<uint32_t> order;
-        order.reserve(total_nodes);
-        for (size_t i = 0; i < total_nodes; i++)
-            if (b.nodes[i].parent == NONE) {
-                id_of[i] = ROOT_BASE + b.nodes[i].root_ordinal;
-                order.push_back((uint32_t) i);
-            }
-        uint64_t cursor = csr_base;
-        for (size_t qi = 0; qi < order.size(); qi++) {
-            const uint32_t pi = order[qi];
-            const BNode& P = b.nodes[pi];
-            if (P.plus != NONE) {
-                id_of[P.plus] = (uint32_t) cursor++;
-                order.push_back(P.plus);
-            }
-            const ChildPlan& pl = plan[pi];
-            const uint32_t c0 = child_off[pi], c1 = child_off[pi + 1];
-            if (c1 == c0) continue;
-            if (pl.big) {
-                for (uint32_t j = c0; j < c1; j++) {
-                    const BNode& ch = b.nodes[child_list[j]];
-                    id_of[child_list[j]] = table.place(id_of[pi], ch.lenw, ch.tok);
-                    order.push_back(child_list[j]);
-                }
-            } else {
-                child_base[pi] = (uint32_t) cursor;
-                for (uint32_t j = c0; j < c1; j++) {
-                    const BNode& ch = b.nodes[child_list[j]];
-                    const uint32_t idx = pl.lg ? child_index(fold32(token_hash(ch.lenw, ch.tok)), pl.seed, pl.lg) : 0u;
-                    id_of[child_list[j]] = (uint32_t) (cursor + idx);
-                    order.push_back(child_list[j]);
-                }
-                cursor += 1ull << pl.lg;
-            }
+}
+
+inline uint32_t sat8(uint32_t v) { return v > 255u ? 255u : v; }
+
+// phase D: place the tenant's nodes (BFS inside its private region; big fan-outs into the shared tag table) and emit records
+void place_tenant(TenantBuild& tb, EdgeTable& table, FlatIndex* out) {
+    Builder& b = tb.b;
+    const size_t N = b.nodes.size();
+    std::vector<uint32_t> id_of(N, NONE), child_base(N, 0), order;
+    order.reserve(N);
+    id_of[0] = ROOT_BASE + tb.ordinal;
+    order.push_back(0);
+    uint64_t cursor = tb.region_base;
+    for (size_t qi = 0; qi < order.size(); qi++) {
+        const uint32_t pi = order[qi];
+        const BNode& P = b.nodes[pi];
+        if (P.plus != NONE) {
+            id_of[P.plus] = (uint32_t) cursor++;
+            order.push_back(P.plus);
         }
-        if (order.size() != total_nodes || cursor != csr_base + csr_slots) {
-            if (err) *err = "internal error: BFS placement did not cover the trie";
-            return false;
+        const ChildPlan& pl = tb.plan[pi];
+        const uint32_t c0 = tb.child_off[pi], c1 = tb.child_off[pi + 1];
+        if (c1 == c0) continue;
+        if (pl.big) {
+            for (uint32_t j = c0; j < c1; j++) {
+                const BNode& ch = b.nodes[tb.child_list[j]];
+                id_of[tb.child_list[j]] = table.place(id_of[pi], ch.lenw, ch.tok);
+                order.push_back(tb.child_list[j]);
+            }
+        } else {
+            child_base[pi] = (uint32_t) cursor;
+            for (uint32_t j = c0; j < c1; j++) {
+                const BNode& ch = b.nodes[tb.child_list[j]];
+                const uint32_t idx = pl.lg ? child_index(fold32(token_hash(ch.lenw, ch.tok)), pl.seed, pl.lg) : 0u;
+                id_of[tb.child_list[j]] = (uint32_t) (cursor + idx);
+                order.push_back(tb.child_list[j]);
+            }
+            cursor += 1ull << pl.lg;
         }
     }
-    out->segs.clear();
+    if (order.size() != N || cursor != tb.region_base + tb.csr_slots) {
+        tb.err = "internal error: BFS placement did not cover the trie";
+        return;
+    }
+    uint64_t seg_cursor = tb.seg_base;   // in uint32 words
     auto emit_target = [&](Target& t, uint32_t* first, uint32_t* count, uint32_t multi_flag, uint32_t* flags) {
         if (t.multi >= 0) {
             auto& lst = b.multi_lists[t.multi];
             lst.push_back({t.first, t.count});
-            *first = (uint32_t) (out->segs.size() / 2);
+            *first = (uint32_t) (seg_cursor / 2);
             *count = t.total;
             *flags |= multi_flag;
-            out->segs.push_back((uint32_t) lst.size());
-            out->segs.push_back(t.total);
+            out->segs[seg_cursor++] = (uint32_t) lst.size();
+            out->segs[seg_cursor++] = t.total;
             for (auto& p : lst) {
-                out->segs.push_back(p.first);
-                out->segs.push_back(p.second);
+                out->segs[seg_cursor++] = p.first;
+                out->segs[seg_cursor++] = p.second;
             }
-            out->n_multi++;
+            tb.n_multi++;
         } else {
             *first = t.first;
             *count = t.total;
         }
     };
-    auto sat8 = [](uint32_t v) { return v > 255u ? 255u : v; };
-    for (size_t i = 0; i < total_nodes; i++) {
+    for (size_t i = 0; i < N; i++) {
         BNode& nd = b.nodes[i];
         Slot* rec;
         if (nd.parent == NONE) {
-            rec = &out->roots[nd.root_ordinal];
+            rec = &out->roots[tb.ordinal];
             memset(rec->w, 0, sizeof(rec->w));
             rec->w[W_PARENT] = NONE;
         } else {
@@ -476,18 +440,167 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
         emit_target(nd.own, &rec->w[W_OWN_FIRST], &rec->w[W_OWN_COUNT], FLAG_OWN_MULTI, &flags);
         emit_target(nd.hash, &rec->w[W_HASH_FIRST], &rec->w[W_HASH_COUNT], FLAG_HASH_MULTI, &flags);
         rec->w[W_CAPS] = sat8(nd.own.pc) | (sat8(nd.own.gc) << 8) | (sat8(nd.hash.pc) << 16) | (sat8(nd.hash.gc) << 24);
-        if (plan[i].big) flags |= FLAG_BIG;
-        rec->w[W_META] = meta_pack(flags, plan[i].lg, plan[i].seed);
+        if (tb.plan[i].big) flags |= FLAG_BIG;
+        rec->w[W_META] = meta_pack(flags, tb.plan[i].lg, tb.plan[i].seed);
         rec->w[W_CHILD_BASE] = child_base[i];
         rec->w[W_PLUS] = nd.plus == NONE ? NONE : id_of[nd.plus];
     }
-    if (out->segs.empty()) out->segs.assign(2, 0);
-    {
-        std::vector<uint32_t> nchild(total_nodes, 0);
-        for (size_t i = 0; i < total_nodes; i++)
-            if (b.nodes[i].parent != NONE && b.nodes[i].lenw != LEN_PLUS) nchild[b.nodes[i].parent]++;
-        for (size_t i = 0; i < total_nodes; i++) out->child_hist[std::min<uint32_t>(nchild[i], 4)]++;
+    // rebase the tenant-local prefix counts
+    for (int64_t r = tb.lo; r < tb.hi; r++) {
+        out->pfx_persistent[(size_t) r] += tb.pp_base;
+        out->pfx_group[(size_t) r] += tb.pg_base;
     }
+}
+
+template <typename F>
+void parallel_for_tenants(std::vector<TenantBuild>& tenants, const std::vector<uint32_t>& by_size, F&& f) {
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    nthreads = std::min<unsigned>(nthreads, 64);
+    nthreads = (unsigned) std::min<size_t>(nthreads, std::max<size_t>(tenants.size(), 1));
+    std::atomic<size_t> cursor{0};
+    auto worker = [&]() {
+        while (true) {
+            const size_t i = cursor.fetch_add(1);
+            if (i >= by_size.size()) break;
+            f(tenants[by_size[i]]);
+        }
+    };
+    if (nthreads <= 1) {
+        worker();
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
+    *out = FlatIndex();
+    const bool trace = getenv("BFQ_BUILD_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bfq build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
+    const int64_t n = kv.n();
+    if (n >= (int64_t) 0x7FFFFFFF) {
+        if (err) *err = "too many routes for 31-bit ranks";
+        return false;
+    }
+    out->n_routes = n;
+    out->rkind.resize((size_t) n);
+    out->pfx_persistent.resize((size_t) n + 1);
+    out->pfx_group.resize((size_t) n + 1);
+    // ---- phase A (serial, cheap): tenant boundaries. The tenant id is the key prefix <0x00><u16 BE len><id>.
+    std::vector<TenantBuild> tenants;
+    {
+        sv cur;
+        for (int64_t r = 0; r < n; r++) {
+            const sv k = kv.key(r);
+            if (k.size() < 3 || k[0] != 0) {
+                if (err) *err = "undecodable route key at rank " + std::to_string(r);
+                return false;
+            }
+            const size_t tl = ((size_t) (uint8_t) k[1] << 8) | (uint8_t) k[2];
+            if (k.size() < 3 + tl) {
+                if (err) *err = "undecodable route key at rank " + std::to_string(r);
+                return false;
+            }
+            const sv t = k.substr(3, tl);
+            if (tenants.empty() || t != cur) {
+                if (!tenants.empty()) tenants.back().hi = r;
+                if (out->tenant_ordinal.count(std::string(t))) {
+                    if (err) *err = "tenant keys are not contiguous";
+                    return false;
+                }
+                tenants.emplace_back();
+                tenants.back().tenant = t;
+                tenants.back().lo = r;
+                tenants.back().ordinal = (uint32_t) tenants.size() - 1;
+                out->tenant_ordinal.emplace(std::string(t), tenants.back().ordinal);
+                cur = t;
+            }
+        }
+        if (!tenants.empty()) tenants.back().hi = n;
+    }
+    lap("A tenant boundaries");
+    std::vector<uint32_t> by_size(tenants.size());
+    for (size_t i = 0; i < tenants.size(); i++) by_size[i] = (uint32_t) i;
+    std::sort(by_size.begin(), by_size.end(), [&](uint32_t a, uint32_t b) { return tenants[a].hi - tenants[a].lo > tenants[b].hi - tenants[b].lo; });
+    // ---- phase B (parallel): per-tenant trie + child-array plans
+    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { build_tenant(kv, tb, out); });
+    lap("B tries + plans (parallel)");
+    // ---- phase C (serial): regions, prefix bases, the shared tag table
+    uint64_t n_big_edges = 0, csr_total = 0, seg_total = 0;
+    uint32_t pp = 0, pg = 0;
+    int64_t total_nodes = 0;
+    for (auto& tb : tenants) {
+        if (!tb.err.empty()) {
+            if (err) *err = tb.err;
+            return false;
+        }
+        n_big_edges += tb.big_edges;
+        tb.pp_base = pp;
+        tb.pg_base = pg;
+        pp += tb.pp;
+        pg += tb.pg;
+        tb.seg_base = seg_total;
+        seg_total += tb.seg_words;
+        total_nodes += (int64_t) tb.b.nodes.size();
+        out->max_nodes_per_depth = std::max(out->max_nodes_per_depth, tb.max_depth_nodes);
+        out->max_tenant_nodes = std::max(out->max_tenant_nodes, tb.tenant_nodes);
+        out->n_cont_chunks += tb.b.n_cont;
+        for (int i = 0; i < 5; i++) out->child_hist[i] += tb.child_hist[i];
+    }
+    out->pfx_persistent[(size_t) n] = pp;
+    out->pfx_group[(size_t) n] = pg;
+    out->n_nodes = total_nodes;
+    EdgeTable table;
+    table.init(n_big_edges, /*fill=*/false);
+    const uint64_t csr_base = (uint64_t) table.n_blocks * BLOCK_SLOTS;
+    for (auto& tb : tenants) {
+        tb.region_base = csr_base + csr_total;
+        csr_total += tb.csr_slots;
+    }
+    if (csr_base + csr_total >= 0x7FFFFFF0ull) {
+        if (err) *err = "index too large for 31-bit slot ids";
+        return false;
+    }
+    table.slots.resize((size_t) (csr_base + csr_total));   // uninitialised; filled (first-touched) in parallel below
+    {
+        const size_t total = table.slots.size(), piece = 1u << 16;
+        std::atomic<size_t> next{0};
+        unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+        auto worker = [&]() {
+            while (true) {
+                const size_t at = next.fetch_add(piece);
+                if (at >= total) break;
+                fill_empty_slots(table.slots.data() + at, std::min(piece, total - at));
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    out->roots.assign(tenants.size(), Slot());
+    out->segs.assign((size_t) std::max<uint64_t>(seg_total, 2), 0);
+    lap("C regions + allocation");
+    // ---- phase D (parallel): placement + record emission (tag-table claims are atomic)
+    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { place_tenant(tb, table, out); });
+    for (auto& tb : tenants) {
+        if (!tb.err.empty()) {
+            if (err) *err = tb.err;
+            return false;
+        }
+        out->n_multi += tb.n_multi;
+    }
+    lap("D placement (parallel)");
     out->n_blocks = table.n_blocks;
     out->n_slots = (uint32_t) table.slots.size();
     out->overflowed_blocks = table.overflowed_blocks;

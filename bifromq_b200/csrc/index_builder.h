@@ -31,7 +31,7 @@ struct KVBlob {
 
 // Everything the device needs, in host memory, plus build statistics.
 struct FlatIndex {
-    std::vector<Slot> slots;                  // blocked hash table (n_blocks * BLOCK_SLOTS)
+    SlotVec slots;                            // blocked hash table (n_blocks * BLOCK_SLOTS)
     std::vector<uint8_t> tags;                // 16 tag bytes per block
     std::vector<Slot> roots;                  // one record per tenant (key words unused)
     std::vector<uint32_t> segs;               // segment table (pairs), see trie_layout.h

@@ -640,7 +640,7 @@ int32_t rebuild(bfq_rindex* h) {
         const uint32_t s = table.place(e.parent, e.lenw, e.tok);
         table.slots[s].w[W_PLUS] = e.child;
     }
-    std::vector<Slot>& slots = table.slots;
+    SlotVec& slots = table.slots;
     // ---- upload
     RCUDA_TRY(cudaSetDevice(h->device));
     RCUDA_TRY(cudaStreamSynchronize(h->stream));

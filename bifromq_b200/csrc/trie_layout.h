@@ -112,25 +112,45 @@ BFQ_HD uint32_t fingerprint(uint64_t h) {
 }  // namespace bfq
 
 // ---- host-side placement shared by the forward and the inverse index builders
+#include <memory>
+#include <utility>
 #include <vector>
 namespace bfq {
+// std::vector allocator that leaves trivially-constructible elements uninitialised on resize(): the 64-byte slot array is
+// gigabytes at full size and is filled (and its pages first touched) by the builder's worker threads instead.
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <typename U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <typename U> void construct(U* p) noexcept { ::new ((void*) p) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new ((void*) p) U(std::forward<A>(a)...); }
+};
+using SlotVec = std::vector<Slot, NoInitAlloc<Slot>>;
+
+inline void fill_empty_slots(Slot* s, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        for (auto& w : s[i].w) w = 0;
+        s[i].w[W_PARENT] = EMPTY_PARENT;
+    }
+}
+
 struct EdgeTable {
-    std::vector<Slot> slots;        // n_blocks * BLOCK_SLOTS
+    SlotVec slots;                  // n_blocks * BLOCK_SLOTS
     std::vector<uint8_t> tags;      // n_blocks * 16
     uint32_t n_blocks = 0;
     int64_t overflowed_blocks = 0;
 
-    void init(uint64_t n_edges) {
+    // sizes the table; with fill == false the caller resizes `slots` further and fills all of it itself
+    void init(uint64_t n_edges, bool fill = true) {
         // target load 0.5 of the usable slots
         uint64_t nb = (n_edges * 2 + BLOCK_USABLE - 1) / BLOCK_USABLE;
         if (nb < 64) nb = 64;
         n_blocks = (uint32_t) nb;
-        slots.assign((size_t) n_blocks * BLOCK_SLOTS, Slot());
-        for (auto& sl : slots) {
-            for (auto& w : sl.w) w = 0;
-            sl.w[W_PARENT] = EMPTY_PARENT;
-        }
         tags.assign((size_t) n_blocks * 16, 0);
+        if (!fill) return;
+        slots.resize((size_t) n_blocks * BLOCK_SLOTS);
+        fill_empty_slots(slots.data(), slots.size());
     }
     // claims a slot for the edge key and returns its index (the caller fills the payload)
     uint32_t place(uint32_t parent, uint32_t lenw, const uint32_t* tok) {
@@ -140,8 +160,9 @@ struct EdgeTable {
         while (true) {
             uint8_t* tg = &tags[(size_t) b * 16];
             for (uint32_t j = 0; j < BLOCK_USABLE; j++) {
-                if (tg[j] == 0) {
-                    tg[j] = fp;
+                uint8_t expected = 0;   // claim a free tag atomically: tenants are placed by concurrent threads
+                if (__atomic_load_n(&tg[j], __ATOMIC_RELAXED) == 0 &&
+                    __atomic_compare_exchange_n(&tg[j], &expected, fp, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) {
                     const uint32_t s = b * BLOCK_SLOTS + j;
                     slots[s].w[W_PARENT] = parent;
                     slots[s].w[W_LEN] = lenw;
@@ -149,10 +170,8 @@ struct EdgeTable {
                     return s;
                 }
             }
-            if (tg[TAG_CTRL] == 0) {
-                tg[TAG_CTRL] = 1;
-                overflowed_blocks++;
-            }
+            if (__atomic_exchange_n(&tg[TAG_CTRL], (uint8_t) 1, __ATOMIC_ACQ_REL) == 0)
+                __atomic_fetch_add(&overflowed_blocks, (int64_t) 1, __ATOMIC_RELAXED);
             b = b + 1 == n_blocks ? 0 : b + 1;
         }
     }
