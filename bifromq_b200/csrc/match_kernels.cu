@@ -312,17 +312,21 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     // per-lane topic state; level < 0: the tenant root has not been expanded yet (`node` holds the root ordinal)
     bool have = false, bad = false;
     uint32_t t = 0, node = 0 /* child ref a (root ordinal while level < 0) */, plusf = NONE31, meta = 0, pending = 0, n_rg = 0, acc_r = 0;
-    uint64_t acc_p = 0, acc_g = 0;
+    // matched persistent / group routes so far; bit 31 = "a node's saturated count byte was seen" (then the true sum is
+    // unknown but large: the topic is flagged unless the cap is INT_MAX). <= INLINE_RANGES * 254 otherwise.
+    uint32_t acc_p = 0, acc_g = 0;
+    uint2* rg_out = nullptr;   // next inline range slot of the lane's topic
     int64_t my_off = 0;
     int len = 0, level = 0, tenant = 0;
 
     auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
-        if (n_rg < INLINE_RANGES) p.ranges[(uint64_t) t * INLINE_RANGES + n_rg] = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
+        if (n_rg < INLINE_RANGES) *rg_out++ = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
         else bad = true;
         n_rg++;
         acc_r += count;
-        acc_p += caps_value(caps & 0xFFu);
-        acc_g += caps_value((caps >> 8) & 0xFFu);
+        const uint32_t cp = caps & 0xFFu, cg = (caps >> 8) & 0xFFu;
+        acc_p = (acc_p + cp) | (cp == 0xFFu ? 0x80000000u : 0u);   // <= INLINE_RANGES additions of <= 255: no carry into bit 31
+        acc_g = (acc_g + cg) | (cg == 0xFFu ? 0x80000000u : 0u);
     };
     auto finish = [&]() {
         if (bad) {
@@ -333,8 +337,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             p.route_count[t] = 0;
         } else {
             const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
-            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint64_t) (maxP < 0 ? 0 : maxP);
-            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint64_t) (maxG < 0 ? 0 : maxG);
+            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint32_t) (maxP < 0 ? 0 : maxP);
+            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint32_t) (maxG < 0 ? 0 : maxG);
             const bool flagged = flag_p || flag_g;
             p.span_begin[t] = t * INLINE_RANGES;
             p.span_count[t] = n_rg | (flagged ? SPAN_FLAGGED : 0u);
@@ -376,9 +380,11 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     if (kPrefetch) {
                         // pull the chunk's topic bytes towards L2 now: the first key read of each topic would
                         // otherwise be a compulsory HBM miss in the middle of a lock-step warp step
-                        const int64_t cend = p.topic_off[end];
-                        for (int64_t o = cbase + (int64_t) lane * 128; o < cend; o += 32 * 128)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.topics + o));
+                        // (one or two lines per lane cover a 32-topic chunk of up to 8 KB; longer chunks go unprefetched)
+                        const uint32_t cbytes = (uint32_t) min((int64_t) 8192, p.topic_off[end] - cbase);
+                        const uint8_t* pf = p.topics + cbase + lane * 128;
+                        if ((uint32_t) lane * 128u < cbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                        if ((uint32_t) lane * 128u + 4096u < cbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 4096));
                     }
                 }
             }
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     tenant = ws.m_tenant[i];
                     const int root_ord = ws.m_root[i];
                     n_rg = 0; acc_r = 0; acc_p = 0; acc_g = 0; pending = 0;
+                    rg_out = p.ranges + (uint64_t) t * INLINE_RANGES;
                     bad = len > 65535;
                     have = true;
                     ws.lv[0][lane] = 0;
@@ -430,14 +437,17 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             const int lvl = rootstep ? 0 : level;
             const int s = ws.lv[lvl][lane];
             const int rem = len - s;
-            // 28 bytes at the level start: aligned words + funnel shift (words at/after the topic end are not read)
+            // 28 bytes at the level start from up to three ALIGNED 16-byte granules (each one holds at least one byte of the
+            // topic, so the reads never leave the granules the blob occupies), then a word-select + funnel shift. Eight
+            // 4-byte loads here were 25 % of the kernel's L1 tag lookups.
             const uint64_t a = (uint64_t) (uintptr_t) p.topics + (uint64_t) my_off + (uint64_t) s;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~3ull);
-            const uint32_t* wend = reinterpret_cast<const uint32_t*>((uint64_t) (uintptr_t) p.topics + (uint64_t) my_off + (uint64_t) len);
-            const int sh = (int) (a & 3) * 8;
-            uint32_t x[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) x[j] = (wp + j) < wend ? __ldg(wp + j) : 0u;
+            const uint4* qp = reinterpret_cast<const uint4*>(a & ~15ull);
+            const int o = (int) (a & 15);
+            const int need = o + min(rem, 28);
+            uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0, q2 = q0;
+            if (need > 0) q0 = __ldg(qp);
+            if (need > 16) q1 = __ldg(qp + 1);
+            if (need > 32) q2 = __ldg(qp + 2);
             // the '+' child (or the tenant root) record: independent of the token, issue its load right away
             const uint32_t plus = plusf;
             const bool has_plus = rootstep || plus != NONE31;
@@ -447,8 +457,18 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 else load_payload<kNA>(p.slots + plus, pw);
             }
             uint32_t k[7];
+            {
+                const uint32_t X[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                const bool by2 = o & 8, by1 = o & 4;
+                uint32_t Y[10], Z[8];
 #pragma unroll
-            for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(x[j], x[j + 1], sh);
+                for (int j = 0; j < 10; j++) Y[j] = by2 ? X[j + 2] : X[j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) Z[j] = by1 ? Y[j + 1] : Y[j];
+                const int sh = (o & 3) * 8;
+#pragma unroll
+                for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(Z[j], Z[j + 1], sh);
+            }
             const uint32_t first_byte = k[0] & 0xFFu;
             // first '/' within the 28 bytes (SWAR zero-byte test on w ^ "////")
             int q = 28;
@@ -478,17 +498,14 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 finish();
             } else {
                 if (!last) ws.lv[level + 1][lane] = (uint16_t) (s + tlen + 1);
+                const int tbits = 8 * tlen;
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const int vb = tlen - 4 * j;
-                    k[j] = vb >= 4 ? k[j] : (vb <= 0 ? 0u : (k[j] & ((1u << (8 * vb)) - 1u)));
-                }
-                bool alive = meta & FLAG_HAS_EXACT;
+                for (int j = 0; j < 6; j++)   // clear the bytes at and after the token end: 0xFFFFFFFF >> clamp(32(j+1) - 8 tlen, 0, 32)
+                    k[j] &= __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (j + 1) - tbits, 0));
                 uint32_t cw[16], cid = 0;
-                if (alive) {
-                    uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
-                    alive = find_child<kNA>(p.slots, p.tags, p.n_blocks, node, meta, (uint32_t) tlen, kk, token_hash((uint32_t) tlen, kk), cw, cid);
-                }
+                const uint32_t kk[6] = {k[0], k[1], k[2], k[3], k[4], k[5]};
+                const bool alive = find_child_lanes<kNA>(p.slots, p.tags, p.n_blocks, meta & FLAG_HAS_EXACT, node, meta, (uint32_t) tlen, kk,
+                                                         token_hash((uint32_t) tlen, kk), cw, cid);
                 bool push_c = false, push_p = false;
                 if (alive) {
                     if (cw[W_HASH_COUNT] > 0) emit(cw[W_HASH_FIRST], cw[W_HASH_COUNT], cw[W_META] & FLAG_HASH_MULTI, (cw[W_CAPS] >> 16));

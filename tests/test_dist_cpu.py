@@ -40,6 +40,13 @@ def _worker(rank, world, port, q):
     # a fake per-rank time: rank r "took" (r + 1) * 10 ms -> whole-job time is the max
     ms, units = D.aggregate((rank + 1) * 10.0, w.n_topics)
     _, total_routes = D.aggregate(0.0, routes)
+    # the exchange step: per-topic fan-out counts of every rank's topics, reassembled in rank order on every rank
+    import torch
+    fan = torch.from_numpy(np.diff(out.offsets).astype(np.int32))
+    gathered = D.gather_fanout(fan)
+    assert gathered.numel() == int(units) and int(gathered.sum()) == int(total_routes)
+    parts = D.all_gather_varlen(fan)
+    assert torch.equal(parts[rank], fan) and len(parts) == world
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, w.n_topics, routes, ms, units, total_routes, sorted(w.tenants)))
@@ -86,3 +93,50 @@ def test_fnv1a64_known_answers():
     assert D.fnv1a64(b"") == 0xCBF29CE484222325
     assert D.fnv1a64(b"a") == 0xAF63DC4C8601EC8C
     assert D.fnv1a64("foobar") == 0x85944171F73967E8
+
+
+def _reassemble_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from bifromq_b200 import dist as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tenants = ["tenant-%d" % i for i in range(40)]
+    rng = np.random.default_rng(7)
+    topic_tenant = rng.integers(0, len(tenants), 1000)
+    truth = (np.arange(1000) * 7 + 3).astype(np.int32)          # the "fan-out" of topic i, known to its owner only
+    parts = D.split_batch_by_owner(tenants, topic_tenant, world)
+    mine = torch.from_numpy(truth[parts[rank]])
+    whole = D.gather_fanout(mine, parts, 1000)
+    ok = bool(np.array_equal(whole.numpy(), truth))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, ok))
+
+
+def test_fanout_exchange_reassembles_batch_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reassemble_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == [(0, True), (1, True)]
+
+
+def test_replica_split_covers_the_batch():
+    sys.path.insert(0, ROOT)
+    from bifromq_b200 import dist as D
+    for n, wsz in ((10, 3), (0, 2), (7, 8), (1000000, 8)):
+        cuts = D.split_batch_replicas(n, wsz)
+        assert len(cuts) == wsz and cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert max(e - b for b, e in cuts) - min(e - b for b, e in cuts) <= 1
