@@ -115,6 +115,10 @@ struct bfq_index {
     DevBuf<uint2> d_ranges, d_scratch, d_ranges_c;
     DevBuf<uint8_t> d_scan_tmp;
     DevBuf<uint32_t> d_cnt, d_new_begin;
+    DevBuf<uint32_t> d_ord_keys, d_ord_vals;   // locality ordering of tier 0 (launch_order): 2n each
+    DevBuf<uint8_t> d_ord_tmp;
+    size_t ord_tmp_stride = 0;                 // bytes of sort scratch per sub-batch
+    int64_t order_min = 32768;                 // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
     DevBuf<uint3> d_throttled;
     DevBuf<unsigned long long> d_counters;
     PinBuf<unsigned long long> h_counters;
@@ -222,6 +226,17 @@ int32_t prepare_workspace(bfq_index* h, int64_t n, int n_chunks) {
     if (dyn_base >= 0xF0000000ull) return fail(BFQ_E_RANGE, "batch too large for 32-bit range indices; split the batch");
     const size_t min_dyn = std::max<size_t>((size_t) n_chunks << 18, nn);
     if (h->d_ranges.cap < dyn_base + min_dyn) CUDA_TRY(h->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, min_dyn))));
+    if (n >= h->order_min) {
+        CUDA_TRY(h->d_ord_keys.reserve(2 * nn));
+        CUDA_TRY(h->d_ord_vals.reserve(2 * nn));
+        OrderParams q{};
+        q.n_topics = n;
+        size_t tb = 0;
+        CUDA_TRY(launch_order(q, nullptr, &tb, nullptr));
+        tb = (tb + 255) / 256 * 256;
+        h->ord_tmp_stride = std::max(h->ord_tmp_stride, tb);
+        CUDA_TRY(h->d_ord_tmp.reserve(h->ord_tmp_stride * MAX_CHUNKS));
+    }
     if (h->d_throttled.cap < ((size_t) n_chunks << 14)) CUDA_TRY(h->d_throttled.reserve(std::max<size_t>(1 << 16, (size_t) n_chunks << 14)));
     return BFQ_OK;
 }
@@ -280,6 +295,22 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
     CUDA_TRY(cudaMemsetAsync(d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), stream));
     p.work_list = nullptr;
     p.n_work = 0;
+    p.order = nullptr;
+    if (n >= h->order_min && h->d_ord_keys.cap >= 2 * (size_t) (b + n) && h->ord_tmp_stride > 0) {
+        // group the topics by tenant and leading levels so that neighbouring lanes walk the same part of the trie
+        OrderParams q{};
+        q.n_topics = n;
+        q.topics = d_topics;
+        q.topic_off = p.topic_off;
+        q.topic_tenant = p.topic_tenant;
+        q.n_tenants = n_tenants;
+        q.keys = h->d_ord_keys.p + 2 * b;
+        q.vals = h->d_ord_vals.p + 2 * b;
+        size_t tb = h->ord_tmp_stride;
+        CUDA_TRY(launch_order(q, h->d_ord_tmp.p + (size_t) sb.chunk * h->ord_tmp_stride, &tb, stream));
+        p.order = q.vals + n;
+        out->n_launches += 2;
+    }
     if (n > 0) {
         // tier 0 (one lane per topic) over the whole sub-batch, then tier 1 (one warp per topic) over whatever tier 0
         // deferred — its count is read on the device, so both launches go out back to back
@@ -426,6 +457,10 @@ int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
     if (e != cudaSuccess) {
         delete h;
         return fail(BFQ_E_CUDA, cudaGetErrorString(e));
+    }
+    if (const char* eo = getenv("BFQ_ORDER")) {   // experiment switch: 0 = never order, N > 0 = order batches of >= N topics
+        const long long v = atoll(eo);
+        h->order_min = v <= 0 ? (int64_t) 1 << 62 : (int64_t) v;
     }
     *out = h;
     return BFQ_OK;
@@ -594,7 +629,7 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
             if (meta & FLAG_BIG) {
                 found = t.find(pid, sl.w[W_LEN], &sl.w[W_TOK]);
             } else {
-                const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(token_hash(sl.w[W_LEN], &sl.w[W_TOK]));
+                const uint32_t lg = meta_log2size(meta), sd = meta >> 16, t32 = fold32(token_hash(sl.w[W_LEN], &sl.w[W_TOK]));
                 if (lg == 0 && (t32 & 0xFFFFu) != sd) return fail(BFQ_E_STATE, "single-child fingerprint mismatch");
                 found = pr.w[W_CHILD_BASE] + (lg ? child_index(t32, sd, lg) : 0u);
             }

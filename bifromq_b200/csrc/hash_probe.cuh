@@ -94,7 +94,7 @@ template <bool kNA = false>
 __device__ __forceinline__ bool find_child(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t a, uint32_t meta,
                                            uint32_t lenw, const uint32_t (&k)[6], uint64_t tokh, uint32_t (&w)[16], uint32_t& slot) {
     if (meta & FLAG_BIG) return probe<kNA>(slots, tags, n_blocks, a, lenw, k, tokh, w, slot);
-    const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(tokh);
+    const uint32_t lg = meta_log2size(meta), sd = meta >> 16, t32 = fold32(tokh);
     uint32_t idx = 0;
     if (lg == 0) {
         if ((t32 & 0xFFFFu) != sd) return false;
@@ -138,7 +138,7 @@ __device__ __forceinline__ bool find_child_lanes(const Slot* slots, const uint4*
             want = true;
         }
     } else if (alive) {
-        const uint32_t lg = (meta >> 8) & 15u, sd = meta >> 16, t32 = fold32(tokh);
+        const uint32_t lg = meta_log2size(meta), sd = meta >> 16, t32 = fold32(tokh);
         want = lg != 0 || (t32 & 0xFFFFu) == sd;
         slot = a + (lg ? child_index(t32, sd, lg) : 0u);
     }

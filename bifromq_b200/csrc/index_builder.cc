@@ -305,7 +305,13 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
     }
     // per parent choose {single child + fingerprint, perfect hash of 2^lg slots with a seed, big (global tag table)}
     tb.plan.assign(N, ChildPlan{0, 0, 0});
-    std::vector<uint32_t> t32, sorted;
+    std::vector<uint32_t> t32, sorted, stamp;
+    uint32_t epoch = 0;
+    static const uint32_t perfect_max = [] {   // experiment switch BFQ_PERFECT_LOG2_MAX (default PERFECT_LOG2_MAX)
+        const char* e = getenv("BFQ_PERFECT_LOG2_MAX");
+        const int v = e ? atoi(e) : (int) PERFECT_LOG2_MAX;
+        return (uint32_t) std::min(std::max(v, 1), (int) PERFECT_LOG2_MAX);
+    }();
     for (size_t i = 0; i < N; i++) {
         const BNode& nd = b.nodes[i];
         const uint32_t c = tb.child_off[i + 1] - tb.child_off[i];
@@ -320,27 +326,37 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
             const BNode& ch = b.nodes[tb.child_list[j]];
             t32.push_back(fold32(token_hash(ch.lenw, ch.tok)));
         }
-        bool big = c > SMALL_FANOUT_MAX;
-        if (!big && c == 1) {
+        // Private child array of 2^lg slots addressed by child_index(fold32(token hash), seed, lg) with a seed that makes it
+        // collision-free: ONE memory access per lookup, hit or miss. A random seed works with probability
+        // ~exp(-c^2 / 2^(lg+1)), so the array needs ~c^2/16 slots for the 16-bit seed space to contain one: cheap for the
+        // common small fan-outs, 4096 slots for 256 children, and beyond 2^PERFECT_LOG2_MAX the global tag table takes over
+        // (two dependent accesses — ncu: the tag wait alone was 20 % of the lane kernel's stall samples when fan-outs
+        // of 17..1000 still went there).
+        bool big = false;
+        if (c == 1) {
             pl.lg = 0;
             pl.seed = (uint16_t) (t32[0] & 0xFFFFu);
-        } else if (!big) {
+        } else {
             sorted = t32;
             std::sort(sorted.begin(), sorted.end());
             if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) big = true;   // 32-bit fold collision
             uint32_t lg = 1;
             while ((1u << lg) < c) lg++;
             if (c > 4) lg++;
+            while (lg <= perfect_max && ((uint64_t) c * c) / 16 > (1ull << lg)) lg++;
             bool found = false;
-            for (; !big && !found && lg <= 8; lg++) {
+            for (; !big && !found && lg <= perfect_max; lg++) {
+                if (stamp.size() < (1u << lg)) stamp.assign(1u << lg, 0), epoch = 0;
                 for (uint32_t seed = 0; seed < 65536 && !found; seed++) {
-                    uint64_t mask[4] = {0, 0, 0, 0};   // up to 256 positions
+                    if (++epoch == 0) {   // stamp wrap-around
+                        std::fill(stamp.begin(), stamp.end(), 0u);
+                        epoch = 1;
+                    }
                     bool ok = true;
                     for (uint32_t v : t32) {
-                        const uint32_t idx = child_index(v, seed, lg);
-                        const uint64_t bit = 1ull << (idx & 63);
-                        if (mask[idx >> 6] & bit) { ok = false; break; }
-                        mask[idx >> 6] |= bit;
+                        uint32_t& st = stamp[child_index(v, seed, lg)];
+                        if (st == epoch) { ok = false; break; }
+                        st = epoch;
                     }
                     if (ok) {
                         found = true;
@@ -535,6 +551,20 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     // ---- phase B (parallel): per-tenant trie + child-array plans
     parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { build_tenant(kv, tb, out); });
     lap("B tries + plans (parallel)");
+    if (trace) {
+        uint64_t big_nodes = 0, big_edges = 0, hist[6] = {0, 0, 0, 0, 0, 0};
+        for (auto& tb : tenants)
+            for (size_t i = 0; i < tb.plan.size(); i++)
+                if (tb.plan[i].big) {
+                    const uint32_t c = tb.child_off[i + 1] - tb.child_off[i];
+                    big_nodes++;
+                    big_edges += c;
+                    hist[c <= 16 ? 0 : c <= 32 ? 1 : c <= 64 ? 2 : c <= 256 ? 3 : c <= 4096 ? 4 : 5]++;
+                }
+        fprintf(stderr, "[bfq build] big nodes %llu (edges %llu): fan-out <=16: %llu, <=32: %llu, <=64: %llu, <=256: %llu, <=4096: %llu, more: %llu\n",
+                (unsigned long long) big_nodes, (unsigned long long) big_edges, (unsigned long long) hist[0], (unsigned long long) hist[1],
+                (unsigned long long) hist[2], (unsigned long long) hist[3], (unsigned long long) hist[4], (unsigned long long) hist[5]);
+    }
     // ---- phase C (serial): regions, prefix bases, the shared tag table
     uint64_t n_big_edges = 0, csr_total = 0, seg_total = 0;
     uint32_t pp = 0, pg = 0;

@@ -17,8 +17,10 @@
 #include "match_kernels.cuh"
 #include "hash_probe.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace bfq {
@@ -286,13 +288,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 constexpr int L_WARPS = 4;
 constexpr int L_MAXLV = 12;
 constexpr int L_CHUNK = 32;
+constexpr int TENANT_CAPPED = 1 << 30;   // flag in the lane's tenant word: the tenant has a finite fan-out cap
 
 struct LaneSmem {
     uint16_t lv[L_MAXLV + 1][32];   // start offset of each level of the lane's topic (lane-minor: conflict free)
     uint2 stk[L_MAXLV + 1][32];     // parked '+' branch per level: {child ref a, '+' child slot or NONE31}
     uint32_t stkm[L_MAXLV + 1][32]; //   ... and its meta word
     // metadata of the warp's current chunk of topics, loaded cooperatively (coalesced) when the chunk is claimed
-    uint32_t m_off[L_CHUNK];        // byte offset relative to the chunk's first topic
+    int64_t m_off[L_CHUNK];         // byte offset of the topic in the blob
+    uint32_t m_t[L_CHUNK];          // topic index (the chunk is a run of positions of p.order, or of topic indices)
     uint32_t m_len[L_CHUNK];
     int32_t m_tenant[L_CHUNK];
     int32_t m_root[L_CHUNK];        // root ordinal of the topic's tenant, or -1
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     const int64_t n = p.n_topics;
 
     // warp-uniform work cursor over the current chunk [cstart, end)
-    int64_t next = 0, end = 0, cstart = 0, cbase = 0;
+    int64_t next = 0, end = 0, cstart = 0;
     bool exhausted = false;
     // per-lane topic state; level < 0: the tenant root has not been expanded yet (`node` holds the root ordinal)
     bool have = false, bad = false;
@@ -336,10 +340,16 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             p.span_count[t] = SPAN_OVERFLOW;
             p.route_count[t] = 0;
         } else {
-            const int maxP = p.max_pfanout[tenant], maxG = p.max_gfanout[tenant];
-            const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint32_t) (maxP < 0 ? 0 : maxP);
-            const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint32_t) (maxG < 0 ? 0 : maxG);
-            const bool flagged = flag_p || flag_g;
+            // the caps are only read for a topic that matched capped-kind routes in a tenant with a finite cap (bit 30 of
+            // `tenant`, set when the chunk was claimed): the loads would otherwise stall the whole warp at every finish
+            bool flagged = false;
+            if ((tenant & TENANT_CAPPED) && (acc_p | acc_g)) {
+                const int tn = tenant & ~TENANT_CAPPED;
+                const int maxP = p.max_pfanout[tn], maxG = p.max_gfanout[tn];
+                const bool flag_p = maxP != 0x7FFFFFFF && acc_p > (uint32_t) (maxP < 0 ? 0 : maxP);
+                const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint32_t) (maxG < 0 ? 0 : maxG);
+                flagged = flag_p || flag_g;
+            }
             p.span_begin[t] = t * INLINE_RANGES;
             p.span_count[t] = n_rg | (flagged ? SPAN_FLAGGED : 0u);
             p.route_count[t] = acc_r;
@@ -364,28 +374,30 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 } else {
                     cstart = next = (int64_t) c;
                     end = min(n, next + L_CHUNK);
-                    cbase = p.topic_off[cstart];
                     __syncwarp();
                     for (int i = lane; i < (int) (end - cstart); i += 32) {
-                        const int64_t o = p.topic_off[cstart + i], o2 = p.topic_off[cstart + i + 1];
-                        int tn = p.topic_tenant[cstart + i];
+                        const uint32_t ti = p.order ? p.order[cstart + i] : (uint32_t) (cstart + i);
+                        const int64_t o = p.topic_off[ti], o2 = p.topic_off[ti + 1];
+                        int tn = p.topic_tenant[ti];
                         const bool tn_ok = tn >= 0 && tn < p.n_tenants;
                         if (!tn_ok) tn = 0;
-                        ws.m_off[i] = (uint32_t) (o - cbase);
-                        ws.m_len[i] = (uint32_t) min((int64_t) 0x7FFFFFFF, o2 - o);
-                        ws.m_tenant[i] = tn;
+                        if (kPrefetch) {
+                            // pull the topic's bytes towards L2 now: the first key read of each topic would otherwise be a
+                            // compulsory HBM miss in the middle of a lock-step warp step
+                            // (the '$' test below reads the first line; a topic's first 28 bytes may straddle into a second)
+                            if (((o + 28) >> 7) != (o >> 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.topics + o + 28));
+                        }
+                        // bit 31 of m_len: the topic starts with '$' (first-level wildcards skip it) — read here, with the rest
+                        // of the chunk's metadata, instead of as a dependent load in the middle of a refill
+                        const bool sys = o2 > o && p.topics[o] == '$';
+                        const bool capped = p.max_pfanout[tn] != 0x7FFFFFFF || p.max_gfanout[tn] != 0x7FFFFFFF;
+                        ws.m_t[i] = ti;
+                        ws.m_off[i] = o;
+                        ws.m_len[i] = (uint32_t) min((int64_t) 0x7FFFFFFF, o2 - o) | (sys ? 0x80000000u : 0u);
+                        ws.m_tenant[i] = tn | (capped ? TENANT_CAPPED : 0);
                         ws.m_root[i] = tn_ok ? p.tenant_root[tn] : -1;
                     }
                     __syncwarp();
-                    if (kPrefetch) {
-                        // pull the chunk's topic bytes towards L2 now: the first key read of each topic would
-                        // otherwise be a compulsory HBM miss in the middle of a lock-step warp step
-                        // (one or two lines per lane cover a 32-topic chunk of up to 8 KB; longer chunks go unprefetched)
-                        const uint32_t cbytes = (uint32_t) min((int64_t) 8192, p.topic_off[end] - cbase);
-                        const uint8_t* pf = p.topics + cbase + lane * 128;
-                        if ((uint32_t) lane * 128u < cbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-                        if ((uint32_t) lane * 128u + 4096u < cbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 4096));
-                    }
                 }
             }
             if (next < end) {
@@ -394,9 +406,10 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 next = min(end, next + (int64_t) __popc(idle));
                 if (take) {
                     const int i = (int) (idx - cstart);
-                    t = (uint32_t) idx;
-                    my_off = cbase + (int64_t) ws.m_off[i];
-                    len = (int) ws.m_len[i];
+                    t = ws.m_t[i];
+                    my_off = ws.m_off[i];
+                    const uint32_t lenw = ws.m_len[i];
+                    len = (int) (lenw & 0x7FFFFFFFu);
                     tenant = ws.m_tenant[i];
                     const int root_ord = ws.m_root[i];
                     n_rg = 0; acc_r = 0; acc_p = 0; acc_g = 0; pending = 0;
@@ -413,7 +426,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                         // expand the tenant root right here instead of spending a lock-step DFS step on it
                         uint32_t rw[16];
                         load_payload(p.roots + root_ord, rw);
-                        const bool sys = len > 0 && p.topics[my_off] == '$';
+                        const bool sys = lenw >> 31;
                         if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI, (rw[W_CAPS] >> 16));
                         const uint32_t rplus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
                         const uint32_t has_exact = rw[W_META] & FLAG_HAS_EXACT;
@@ -554,6 +567,53 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ locality order
+// key = tenant index (T bits) | hash(level 0) | hash(level 1) | hash(level 2): equal leading levels => equal digits =>
+// adjacent after the sort. Hash collisions only merge groups. Topics with fewer levels use digit 0.
+__global__ void order_keys_kernel(const OrderParams q, int tenant_bits, int key_bits) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n_topics) return;
+    const int64_t o = q.topic_off[i];
+    const int len = (int) min((int64_t) 40, q.topic_off[i + 1] - o);   // three levels of ordinary topics end well before this
+    const int rest = key_bits - tenant_bits;
+    const int b0 = rest / 3 + (rest % 3 > 0), b1 = rest / 3 + (rest % 3 > 1), b2 = rest / 3;
+    int tn = q.topic_tenant[i];
+    if (tn < 0 || tn >= q.n_tenants) tn = 0;
+    // the first 40 bytes from four aligned 16-byte granules (as in the lane kernel: a granule is read only if it holds a
+    // byte of the topic), scanned in registers
+    const uint64_t a = (uint64_t) (uintptr_t) q.topics + (uint64_t) o;
+    const uint4* qp = reinterpret_cast<const uint4*>(a & ~15ull);
+    const int off = (int) (a & 15), need = off + len;
+    uint4 g[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) g[j] = need > 16 * j ? __ldg(qp + j) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t W[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
+                            g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
+    uint32_t d[3] = {0u, 0u, 0u};
+    uint32_t h = 0x811C9DC5u;
+    int lvl = 0;
+#pragma unroll
+    for (int j = 0; j < 56; j++) {   // off <= 15, len <= 40
+        const uint32_t c = (W[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        const bool in = j >= off && j < need;
+        const bool close = in && c == '/';
+        if (close) {
+            if (lvl == 0) d[0] = h; else if (lvl == 1) d[1] = h; else if (lvl == 2) d[2] = h;
+            lvl++;
+            h = 0x811C9DC5u;
+        } else if (in) {
+            h = (h ^ c) * 0x01000193u;
+        }
+    }
+    if (lvl == 0) d[0] = h; else if (lvl == 1) d[1] = h; else if (lvl == 2) d[2] = h;   // the level the window ends in
+    uint32_t key = tenant_bits ? ((uint32_t) tn & ((1u << tenant_bits) - 1u)) : 0u;
+    key = (key << b0) | (b0 ? (d[0] * 0x9E3779B1u) >> (32 - b0) : 0u);
+    key = (key << b1) | (b1 ? (lvl >= 1 ? (d[1] * 0x9E3779B1u) >> (32 - b1) : 0u) : 0u);
+    key = (key << b2) | (b2 ? (lvl >= 2 ? (d[2] * 0x9E3779B1u) >> (32 - b2) : 0u) : 0u);
+    q.keys[i] = key;
+    q.vals[i] = (uint32_t) i;
 }
 
 // ------------------------------------------------------------------------------------------------ compaction
@@ -724,6 +784,25 @@ void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStrea
     match_topics_kernel<false><<<(unsigned) ctas, WARPS_PER_CTA * 32, 0, stream>>>(p);
 }
 
+cudaError_t launch_order(const OrderParams& q, void* d_tmp, size_t* tmp_bytes, cudaStream_t stream) {
+    const int n = (int) q.n_topics;
+    if (!d_tmp)
+        return cub::DeviceRadixSort::SortPairs(nullptr, *tmp_bytes, q.keys, q.keys + n, q.vals, q.vals + n, n, 0, 32, stream);
+    if (n <= 0) return cudaSuccess;
+    int tenant_bits = 0;
+    while (tenant_bits < 20 && (1ll << tenant_bits) < (long long) q.n_tenants) tenant_bits++;
+    // width of the sort key: tenant bits + ~14 bits of level hashes, in whole 8-bit radix passes (1000 tenants: 24 bits, three
+    // passes; measured: a fourth pass costs 12 us and buys 1.5 % of kernel time). BFQ_ORDER_BITS overrides (experiments).
+    static const int forced_bits = [] {
+        const char* e = getenv("BFQ_ORDER_BITS");
+        return e ? std::min(std::max(atoi(e), 8), 32) : 0;
+    }();
+    int kb = forced_bits ? forced_bits : std::min(32, (tenant_bits + 12 + 7) / 8 * 8);
+    kb = std::max(kb, std::min(32, tenant_bits + 3));
+    order_keys_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(q, tenant_bits, kb);
+    return cub::DeviceRadixSort::SortPairs(d_tmp, *tmp_bytes, q.keys, q.keys + n, q.vals, q.vals + n, n, 0, kb, stream);
+}
+
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -741,7 +820,17 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
         const char* na = getenv("BFQ_NOALLOC");
         const int rootstep = rs ? atoi(rs) : 0, prefetch = pf ? atoi(pf) : 1, noalloc = na ? atoi(na) : 0;
         variant = (noalloc ? 4 : 0) + (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
+        // Shared memory and L1 share 256 KB per SM, and the kernel lives on L1 (top trie levels, topic bytes): with the
+        // 228 KB carve-out (what 8 resident CTAs need) only 28 KB of L1 remain and the kernel runs 1.5x slower (measured).
+        // Ask for the 196 KB carve-out (60 KB L1) and size the persistent grid for what fits there.
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, kerns[variant]);
+        const char* cv = getenv("BFQ_CARVEOUT");   // experiment switch: percent of the 228 KB, 0 = leave it to the driver
+        const int carve = cv ? atoi(cv) : 85;
+        if (carve > 0) cudaFuncSetAttribute(kerns[variant], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
+        const int fit = (int) ((196 * 1024) / (fa.sharedSizeBytes + 1024));
+        if (ctas_per_sm > fit) ctas_per_sm = fit;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     // persistent grid (SM count x resident CTAs); warps claim 32-topic chunks with one atomicAdd each

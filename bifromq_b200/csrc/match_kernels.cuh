@@ -39,6 +39,9 @@ struct MatchParams {
     const int32_t* max_gfanout;     // [n_tenants]
     int32_t n_tenants;
     int64_t n_topics;
+    // tier 0: optional processing order (topic indices grouped by tenant and leading levels, see launch_order); nullptr =>
+    // 0..n_topics. Only the order in which lanes pick topics changes; every output stays indexed by topic.
+    const uint32_t* order;
     // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
     int64_t n_work;
@@ -105,6 +108,21 @@ struct ExpandParams {
 // device CSR of the surviving routes: phase 1 = per-topic counts + exclusive scan into offsets (offsets[n] = total),
 // phase 2 = write the ranks (unordered within a topic). tmp as for launch_compact.
 cudaError_t launch_expand(const ExpandParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase);
+
+// Locality ordering for tier 0: 32-bit key = tenant index | hashes of the first three levels, radix-sorted (cub) with the
+// topic index as payload -> order_out[n]. Topics that walk the same top of the trie are then matched by neighbouring
+// lanes at the same time: their node reads hit L1/L2 instead of being ~18 random DRAM accesses per topic.
+// keys/vals: scratch of 2 * n uint32 each; d_tmp / tmp_bytes as for launch_compact (query with d_tmp == nullptr).
+struct OrderParams {
+    int64_t n_topics;
+    const uint8_t* topics;
+    const int64_t* topic_off;
+    const int32_t* topic_tenant;
+    int32_t n_tenants;
+    uint32_t* keys;                 // [2n]
+    uint32_t* vals;                 // [2n]; the sorted order ends up in vals + n
+};
+cudaError_t launch_order(const OrderParams& q, void* d_tmp, size_t* tmp_bytes, cudaStream_t stream);
 
 // tier 0: one LANE per topic (DFS, bounded smem); tier 1: one WARP per topic; tier 2: warp per topic, global scratch
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream);

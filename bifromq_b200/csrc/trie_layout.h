@@ -62,7 +62,8 @@ constexpr uint32_t LEN_PLUS = 0xFFFFFFFFu;
 constexpr uint32_t LEN_CONT = 0x80000000u;       // | chunk index
 constexpr uint32_t ROOT_BASE = 0x80000000u;      // node id of tenant root = ROOT_BASE + tenant ordinal
 constexpr uint32_t FLAG_HAS_EXACT = 1u, FLAG_OWN_MULTI = 2u, FLAG_HASH_MULTI = 4u, FLAG_BIG = 8u;
-constexpr uint32_t SMALL_FANOUT_MAX = 16;        // more exact children than this => global tag table
+constexpr uint32_t PERFECT_LOG2_MAX = 16;       // largest private (perfect-hashed) child array: 2^16 slots; a fan-out whose
+                                                //   array would be larger (> ~1000 children) goes to the global tag table
 constexpr uint32_t TOKEN_WORDS = 6;              // 24 inline token bytes per edge
 constexpr uint32_t TOKEN_BYTES = 24;
 constexpr uint32_t RANGE_MULTI = 0x80000000u;    // marker in an emitted range's count word
@@ -100,7 +101,8 @@ BFQ_HD uint32_t fold32(uint64_t tokh) { return (uint32_t) (tokh ^ (tokh >> 32));
 BFQ_HD uint32_t child_index(uint32_t t32, uint32_t seed, uint32_t log2size) {   // log2size >= 1
     return ((t32 ^ (seed * 0x9E3779B9u)) * 0x85EBCA6Bu) >> (32u - log2size);
 }
-BFQ_HD uint32_t meta_pack(uint32_t flags, uint32_t log2size, uint32_t seed) { return (flags & 0xFFu) | ((log2size & 15u) << 8) | (seed << 16); }
+BFQ_HD uint32_t meta_pack(uint32_t flags, uint32_t log2size, uint32_t seed) { return (flags & 0xFFu) | ((log2size & 31u) << 8) | (seed << 16); }
+BFQ_HD uint32_t meta_log2size(uint32_t meta) { return (meta >> 8) & 31u; }
 
 BFQ_HD uint64_t edge_hash(uint64_t tokh, uint32_t parent) { return fmix64(tokh + (uint64_t) parent * 0xC2B2AE3D27D4EB4Full); }
 BFQ_HD uint32_t home_block(uint64_t h, uint32_t n_blocks) { return (uint32_t) (((h >> 32) * (uint64_t) n_blocks) >> 32); }

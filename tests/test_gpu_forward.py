@@ -309,6 +309,37 @@ def test_multi_segment_filter_interleaving(B):
         compare_with_oracle(B, idx, kv, ["t"], topics, np.zeros(4, np.int32), caps[0], caps[1], O.MODE_BRUTE)
 
 
+def test_wide_fanouts_perfect_hash_and_tag_table(B):
+    # child arrays of every kind under one tenant: 1 child (fingerprint), 2..16, 17..1000 (perfect hash, arrays up to 2^16
+    # slots) and > ~1000 children (global tag table, two accesses) — at the first level and below a '+' / exact parent
+    pairs = []
+    widths = {"w1": 1, "w3": 3, "w16": 16, "w17": 17, "w40": 40, "w300": 300, "w1500": 1500}
+    for name, n in widths.items():
+        for i in range(n):
+            normal(B, pairs, "t", "%s/c%04d" % (name, i), i % 2, "r%s%d" % (name, i), "d", 1)
+        normal(B, pairs, "t", "%s/+" % name, 0, "plus" + name, "d", 1)
+        normal(B, pairs, "t", "%s/#" % name, 1, "hash" + name, "d", 1)
+    for i in range(2500):   # wide at the tenant root too
+        normal(B, pairs, "t2", "dev%05d/state" % i, 0, "s%d" % i, "d", 1)
+    normal(B, pairs, "t2", "+/state", 1, "all", "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    topics, tt = [], []
+    for name, n in widths.items():
+        for i in sorted({0, 1, n // 2, n - 1, n, n + 7}):
+            topics.append("%s/c%04d" % (name, i))
+            tt.append(0)
+        topics += [name, name + "/c0000/x"]
+        tt += [0, 0]
+    for i in (0, 1, 1234, 2499, 2500, 99999):
+        topics += ["dev%05d/state" % i, "dev%05d" % i]
+        tt += [1, 1]
+    for caps in [(2 ** 31 - 1, 2 ** 31 - 1), (1, 1)]:
+        want = compare_with_oracle(B, idx, kv, ["t", "t2"], topics, np.array(tt, np.int32), caps[0], caps[1], O.MODE_BRUTE)
+    assert sum(len(r) for r in want.route_sets()) > 0
+
+
 def test_long_levels_and_long_topics(B):
     # levels longer than the 24 inline token bytes (continuation chunks) and topics longer than the 256 B stage
     l25, l24, l48, l49, l100 = "x" * 25, "y" * 24, "z" * 48, "w" * 49, "v" * 100
