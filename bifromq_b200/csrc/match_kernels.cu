@@ -591,27 +591,45 @@ __global__ void order_keys_kernel(const OrderParams q, int tenant_bits, int key_
     for (int j = 0; j < 4; j++) g[j] = need > 16 * j ? __ldg(qp + j) : make_uint4(0u, 0u, 0u, 0u);
     const uint32_t W[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
                             g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
-    uint32_t d[3] = {0u, 0u, 0u};
-    uint32_t h = 0x811C9DC5u;
-    int lvl = 0;
+    // topic-aligned words k[0..9] (word select + funnel shift), then a bitmap of the '/' positions (SWAR)
+    uint32_t k[10];
+    {
+        const bool by2 = off & 8, by1 = off & 4;
+        const int sh = (off & 3) * 8;
+        uint32_t Y[13], Z[11];
 #pragma unroll
-    for (int j = 0; j < 56; j++) {   // off <= 15, len <= 40
-        const uint32_t c = (W[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        const bool in = j >= off && j < need;
-        const bool close = in && c == '/';
-        if (close) {
-            if (lvl == 0) d[0] = h; else if (lvl == 1) d[1] = h; else if (lvl == 2) d[2] = h;
-            lvl++;
-            h = 0x811C9DC5u;
-        } else if (in) {
-            h = (h ^ c) * 0x01000193u;
-        }
+        for (int j = 0; j < 13; j++) Y[j] = by2 ? W[j + 2] : W[j];
+#pragma unroll
+        for (int j = 0; j < 11; j++) Z[j] = by1 ? Y[j + 1] : Y[j];
+#pragma unroll
+        for (int j = 0; j < 10; j++) k[j] = __funnelshift_r(Z[j], Z[j + 1], sh);
     }
-    if (lvl == 0) d[0] = h; else if (lvl == 1) d[1] = h; else if (lvl == 2) d[2] = h;   // the level the window ends in
+    uint64_t slashes = 0;
+#pragma unroll
+    for (int j = 0; j < 10; j++) slashes |= (uint64_t) nibble(match_bytes(k[j], 0x2F2F2F2Fu)) << (4 * j);
+    slashes &= (1ull << len) - 1ull;   // len <= 40
+    // ends of the first three levels (a level that runs to the end of the window ends at len); a digit is the hash of the
+    // PREFIX up to that end, so equal leading levels give equal digits
+    int end[3], lvl = 0;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        end[l] = slashes ? __ffsll((long long) slashes) - 1 : len;
+        if (slashes) lvl = l + 1;
+        slashes &= slashes - 1ull;
+    }
+    auto prefix_hash = [&](int nbytes) {
+        const uint32_t C[10] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u,
+                                0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u};
+        uint32_t h = (uint32_t) nbytes;
+#pragma unroll
+        for (int j = 0; j < 10; j++)   // bytes at and after nbytes are cleared: 0xFFFFFFFF >> clamp(32(j+1) - 8 nbytes, 0, 32)
+            h += (k[j] & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (j + 1) - 8 * nbytes, 0))) * C[j];
+        return (h ^ (h >> 15)) * 0x9E3779B1u;
+    };
     uint32_t key = tenant_bits ? ((uint32_t) tn & ((1u << tenant_bits) - 1u)) : 0u;
-    key = (key << b0) | (b0 ? (d[0] * 0x9E3779B1u) >> (32 - b0) : 0u);
-    key = (key << b1) | (b1 ? (lvl >= 1 ? (d[1] * 0x9E3779B1u) >> (32 - b1) : 0u) : 0u);
-    key = (key << b2) | (b2 ? (lvl >= 2 ? (d[2] * 0x9E3779B1u) >> (32 - b2) : 0u) : 0u);
+    key = (key << b0) | (b0 ? prefix_hash(end[0]) >> (32 - b0) : 0u);
+    key = (key << b1) | (b1 && lvl >= 1 ? prefix_hash(end[1]) >> (32 - b1) : 0u);
+    key = (key << b2) | (b2 && lvl >= 2 ? prefix_hash(end[2]) >> (32 - b2) : 0u);
     q.keys[i] = key;
     q.vals[i] = (uint32_t) i;
 }
