@@ -372,10 +372,12 @@ def main():
                 "config": {"workload": workload_name(args, w), "routes_per_gpu": w.n_routes, "filters_per_gpu": w.n_filters,
                            "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "parallelism": "tenant-sharded x%d" % world,
                            "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
-                           "caps": "MaxPersistentFanout=INT_MAX, MaxGroupFanout=INT_MAX", "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
+                           "caps": "MaxPersistentFanout=INT_MAX, MaxGroupFanout=INT_MAX",
+                           "order": "tier 0 picks the topics in locality order (order_keys_kernel + cub radix sort, inside the timed region)",
+                           "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},
-                "gpu_launches": launches, "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
+                "gpu_launches": launches, "gpu_launches_note": "own kernels only: order_keys + tier 0 + tier 1 per step (cub's sort passes not counted)", "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
                 "ranges_per_step": n_ranges, "tier2_topics_per_step": n_overflow, "index": stats, "clocks": clocks}
         if exchange_ms is not None:
             line["exchange"] = {"what": "all-gather of per-topic fan-out counts (int32) over NCCL, all ranks end with the whole job's",

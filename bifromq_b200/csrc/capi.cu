@@ -309,7 +309,7 @@ int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic
         size_t tb = h->ord_tmp_stride;
         CUDA_TRY(launch_order(q, h->d_ord_tmp.p + (size_t) sb.chunk * h->ord_tmp_stride, &tb, stream));
         p.order = q.vals + n;
-        out->n_launches += 2;
+        out->n_launches += 1;   // order_keys_kernel (the radix-sort passes are cub's)
     }
     if (n > 0) {
         // tier 0 (one lane per topic) over the whole sub-batch, then tier 1 (one warp per topic) over whatever tier 0

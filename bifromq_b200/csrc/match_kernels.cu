@@ -300,6 +300,10 @@ struct LaneSmem {
     uint32_t m_len[L_CHUNK];
     int32_t m_tenant[L_CHUNK];
     int32_t m_root[L_CHUNK];        // root ordinal of the topic's tenant, or -1
+    // payload of the tenant root of the chunk's first topic: in locality order a chunk is almost always one tenant, and the
+    // root read at every refill was a dependent L2 access in the middle of a lock-step step (ncu: 4 % of the stall samples)
+    uint32_t c_root[8];
+    int32_t c_ord;
 };
 
 template <bool kRootStep, bool kPrefetch, bool kNA>
@@ -395,7 +399,17 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                         ws.m_off[i] = o;
                         ws.m_len[i] = (uint32_t) min((int64_t) 0x7FFFFFFF, o2 - o) | (sys ? 0x80000000u : 0u);
                         ws.m_tenant[i] = tn | (capped ? TENANT_CAPPED : 0);
-                        ws.m_root[i] = tn_ok ? p.tenant_root[tn] : -1;
+                        const int ro = tn_ok ? p.tenant_root[tn] : -1;
+                        ws.m_root[i] = ro;
+                        if (i == 0) {
+                            ws.c_ord = ro;
+                            if (ro >= 0) {
+                                uint32_t rw[16];
+                                load_payload(p.roots + ro, rw);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) ws.c_root[j] = rw[8 + j];
+                            }
+                        }
                     }
                     __syncwarp();
                 }
@@ -425,7 +439,12 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                     } else if (!kRootStep) {
                         // expand the tenant root right here instead of spending a lock-step DFS step on it
                         uint32_t rw[16];
-                        load_payload(p.roots + root_ord, rw);
+                        if (root_ord == ws.c_ord) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) rw[8 + j] = ws.c_root[j];
+                        } else {
+                            load_payload(p.roots + root_ord, rw);
+                        }
                         const bool sys = lenw >> 31;
                         if (!sys && rw[W_HASH_COUNT] > 0) emit(rw[W_HASH_FIRST], rw[W_HASH_COUNT], rw[W_META] & FLAG_HASH_MULTI, (rw[W_CAPS] >> 16));
                         const uint32_t rplus = (sys || rw[W_PLUS] == NONE) ? NONE31 : rw[W_PLUS];
@@ -849,6 +868,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
         const int fit = (int) ((196 * 1024) / (fa.sharedSizeBytes + 1024));
         if (ctas_per_sm > fit) ctas_per_sm = fit;
+        if (const char* ce = getenv("BFQ_CTAS")) ctas_per_sm = std::min(ctas_per_sm, std::max(1, atoi(ce)));   // experiment switch
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     // persistent grid (SM count x resident CTAs); warps claim 32-topic chunks with one atomicAdd each
