@@ -57,6 +57,8 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
+        """gpu_index: one index or a comma-separated list (rank 0 samples every GPU of the job from ONE nvidia-smi process:
+        eight pollers at 20 ms contend for the driver and slow the ranks' launches)"""
         self.rows, self.proc, self.gpu = [], None, gpu_index
         self.t_begin = self.t_end = None
 
@@ -264,8 +266,9 @@ def main():
         r.close()
         return d2h, tm
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize(dev)
@@ -325,7 +328,7 @@ def main():
         d2h_bytes, e2e_tm = step_e2e()
         e2e_t.append(time.perf_counter() - t0)
     sampler.end()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     e2e_total = float(sum(e2e_t))
     h2d_bytes = blob_bytes + 8 * (n + 1) + 4 * n
 

@@ -21,6 +21,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 
 namespace bfq {
@@ -844,32 +845,42 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // experiment switches (defaults are the measured best): BFQ_ROOTSTEP=0/1, BFQ_PREFETCH=0/1, BFQ_NOALLOC=0/1
-    static int variant = -1, ctas_per_sm = 0;
+    // experiment switches (defaults are the measured best): BFQ_ROOTSTEP=0/1, BFQ_PREFETCH=0/1, BFQ_NOALLOC=0/1.
+    // Node records bypass L1 allocation when the batch is matched in locality order (neighbouring lanes share the top of the
+    // trie inside one request, so L1 is left to the topic bytes: 6 % faster) and allocate in L1 in arrival order (small
+    // batches; there the top trie levels live in L1 and bypassing it is 1.8x slower).
     typedef void (*kern_t)(const MatchParams);
     static const kern_t kerns[8] = {match_topics_lane_kernel<false, false, false>, match_topics_lane_kernel<false, true, false>,
                                     match_topics_lane_kernel<true, false, false>,  match_topics_lane_kernel<true, true, false>,
                                     match_topics_lane_kernel<false, false, true>,  match_topics_lane_kernel<false, true, true>,
                                     match_topics_lane_kernel<true, false, true>,   match_topics_lane_kernel<true, true, true>};
-    if (variant < 0) {
-        const char* rs = getenv("BFQ_ROOTSTEP");
-        const char* pf = getenv("BFQ_PREFETCH");
-        const char* na = getenv("BFQ_NOALLOC");
-        const int rootstep = rs ? atoi(rs) : 0, prefetch = pf ? atoi(pf) : 1, noalloc = na ? atoi(na) : 0;
-        variant = (noalloc ? 4 : 0) + (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
-        // Shared memory and L1 share 256 KB per SM, and the kernel lives on L1 (top trie levels, topic bytes): with the
-        // 228 KB carve-out (what 8 resident CTAs need) only 28 KB of L1 remain and the kernel runs 1.5x slower (measured).
-        // Ask for the 196 KB carve-out (60 KB L1) and size the persistent grid for what fits there.
-        cudaFuncAttributes fa{};
-        cudaFuncGetAttributes(&fa, kerns[variant]);
-        const char* cv = getenv("BFQ_CARVEOUT");   // experiment switch: percent of the 228 KB, 0 = leave it to the driver
-        const int carve = cv ? atoi(cv) : 85;
-        if (carve > 0) cudaFuncSetAttribute(kerns[variant], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kerns[variant], L_WARPS * 32, 0);
-        const int fit = (int) ((196 * 1024) / (fa.sharedSizeBytes + 1024));
-        if (ctas_per_sm > fit) ctas_per_sm = fit;
-        if (const char* ce = getenv("BFQ_CTAS")) ctas_per_sm = std::min(ctas_per_sm, std::max(1, atoi(ce)));   // experiment switch
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    static std::mutex setup_mu;
+    static int ctas_of[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static const int rootstep = getenv("BFQ_ROOTSTEP") ? atoi(getenv("BFQ_ROOTSTEP")) : 0;
+    static const int prefetch = getenv("BFQ_PREFETCH") ? atoi(getenv("BFQ_PREFETCH")) : 1;
+    static const int noalloc_forced = getenv("BFQ_NOALLOC") ? atoi(getenv("BFQ_NOALLOC")) : -1;
+    const int noalloc = noalloc_forced >= 0 ? noalloc_forced : (p.order != nullptr);
+    const int variant = (noalloc ? 4 : 0) + (rootstep ? 2 : 0) + (prefetch ? 1 : 0);
+    int ctas_per_sm;
+    {
+        std::lock_guard<std::mutex> g(setup_mu);
+        if (ctas_of[variant] == 0) {
+            // Shared memory and L1 share 256 KB per SM, and the kernel lives on L1 (topic bytes, top trie levels): with the
+            // 228 KB carve-out (what 8 resident CTAs need) only 28 KB of L1 remain and the kernel runs 1.5x slower (measured).
+            // Ask for the 196 KB carve-out (60 KB L1) and size the persistent grid for what fits there.
+            cudaFuncAttributes fa{};
+            cudaFuncGetAttributes(&fa, kerns[variant]);
+            const char* cv = getenv("BFQ_CARVEOUT");   // experiment switch: percent of the 228 KB, 0 = leave it to the driver
+            const int carve = cv ? atoi(cv) : 85;
+            if (carve > 0) cudaFuncSetAttribute(kerns[variant], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kerns[variant], L_WARPS * 32, 0);
+            const int fit = (int) ((196 * 1024) / (fa.sharedSizeBytes + 1024));
+            if (occ > fit) occ = fit;
+            if (const char* ce = getenv("BFQ_CTAS")) occ = std::min(occ, std::max(1, atoi(ce)));   // experiment switch
+            ctas_of[variant] = occ < 1 ? 1 : occ;
+        }
+        ctas_per_sm = ctas_of[variant];
     }
     // persistent grid (SM count x resident CTAs); warps claim 32-topic chunks with one atomicAdd each
     int64_t ctas = (int64_t) sms * ctas_per_sm;

@@ -282,6 +282,25 @@ def test_random_small_vocab_vs_oracle(B, seed, caps):
     assert idx.stats()["multi_segment_filters"] >= 0
 
 
+@pytest.mark.parametrize("seed,caps", [(11, (2 ** 31 - 1, 100)), (12, (2, 1)), (13, (0, 0))])
+def test_locality_order_path_vs_oracle(B, seed, caps, monkeypatch):
+    # BFQ_ORDER=1: every batch (not only those of >= 32768 topics) is matched in locality order — the order keys, the radix
+    # sort and the order-indirected chunk claims of tier 0 against the oracle, incl. empty levels, '$' topics, unknown tenants
+    monkeypatch.setenv("BFQ_ORDER", "1")
+    rng = random.Random(seed)
+    pairs, tenants, topics, tt = random_pairs(B, rng, 600, ["a", "b", "c", "dd", "e1"], 5)
+    topics += ["", "/", "//", "$sys", "x" * 70 + "/a", "/".join("l%d" % i for i in range(14))]
+    tt = np.concatenate([tt, np.array([0, 1, 2, 0, 1, 2], np.int32)])
+    idx = make_index(B, pairs)
+    kv = oracle_kv_from_pairs(pairs)
+    want = compare_with_oracle(B, idx, kv, tenants, topics, tt, caps[0], caps[1], O.MODE_TRIE)
+    assert sum(len(r) for r in want.route_sets()) > 0
+    # a tenant the index has never seen, mixed into the same batch
+    compare_with_oracle(B, idx, kv, tenants + ["nobody"], topics, np.where(np.arange(len(topics)) % 7 == 0, 3, tt).astype(np.int32),
+                        caps[0], caps[1], O.MODE_TRIE)
+    idx.close()
+
+
 def test_reference_literal_algorithm_agrees_without_empty_levels(B):
     rng = random.Random(9)
     pairs, tenants, topics, tt = random_pairs(B, rng, 500, ["a", "b", "c", "dd"], 4, empties=False)
