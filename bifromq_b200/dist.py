@@ -48,7 +48,7 @@ class _DeviceArray:
     """zero-copy view of device memory owned by the native library (valid until the next match on the index)"""
 
     def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 def device_view(ptr, n, typestr="<i4", device=None):
