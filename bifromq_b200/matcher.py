@@ -52,7 +52,7 @@ class BatchResult:
         self.throttled = arr(pt, nt.value, np.dtype([("topic", np.uint32), ("rank", np.uint32), ("kind", np.uint32)]))
         ms = np.zeros(4, np.float64)
         lib.bfq_result_timings(handle, ms.ctypes.data, 4)
-        self.timings_ms = dict(zip(["h2d", "kernels", "d2h", "total"], ms.tolist()))
+        self.timings_ms = dict(zip(["h2d_stream_busy", "tier0_kernel_first_sub_batch", "sub_batches", "total"], ms.tolist()))
 
     def expand(self):
         """-> (offsets[n+1], ranks) surviving route ranks, ascending per topic"""

@@ -133,7 +133,9 @@ int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n);
 void bfq_result_free(bfq_result* r);
 
 /* Same match with the topic batch already resident in device memory and the result left there
- * (used by bench.py's kernel-only leg and by callers that pipeline batches). d_* are device pointers,
+ * (used by bench.py's kernel-only leg and by callers that pipeline batches). d_* are device pointers
+ * (the kernels read d_topics in whole 16-byte aligned granules that hold at least one topic byte, so the
+ * blob must lie in memory that is readable up to its enclosing 16-byte boundaries: any cudaMalloc'd buffer),
  * stream is a cudaStream_t (NULL = default stream). The call enqueues the kernels, then synchronises
  * the stream once to read the counters. The device result buffers belong to the index and stay valid
  * until the next match on it. */

@@ -497,7 +497,7 @@ def test_pipelined_host_path_large_batch(B, caps):
     tenants = w.tenants
     nt = len(tenants)
     res = idx.match_topics(tenants, topics, tt, [caps[0]] * nt, [caps[1]] * nt)
-    assert int(res.timings_ms["d2h"]) == 4   # number of pipelined sub-batches
+    assert int(res.timings_ms["sub_batches"]) == 4   # number of pipelined sub-batches
     offsets, ranks = res.expand()
     # dense, topic-ordered ranges
     sb, sc = res.span_begin.astype(np.int64), res.span_count.astype(np.int64)
