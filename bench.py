@@ -109,6 +109,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
+def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms):
+    """`roofline` object of the JSON line. SURVEY.md §8(d): algorithmic bytes per topic
+    B = len(topic) + 4 + 32 V + 8 P + 8 ranges (range-encoded output) + 4, with V / P / ranges counted by the oracle on the
+    cpu_baseline sample (`st`, over `ns` topics); achieved = B x topics per launch / the tier-0 kernel's duration."""
+    per_topic = (sample_topic_bytes + 4 * ns + 32 * st["V"] + 8 * st["P"] + 8 * st["ranges"] + 4 * ns) / ns
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = per_topic * n_topics_per_launch / (kernel_ms / 1000.0) / 1e9
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
+            "frac_of_nominal_8000": achieved / 8000.0,
+            "kernel": "match_topics_lane_kernel (tier 0, one lane per topic)", "kernel_ms": kernel_ms, "alg_bytes_per_topic": per_topic,
+            "alg_counters_per_topic": {"V": st["V"] / ns, "P": st["P"] / ns, "ranges": st["ranges"] / ns, "R": st["R"] / ns},
+            "note": "algorithmic bytes per topic measured by the oracle on the cpu_baseline sample"}
+    if traffic:
+        # SURVEY.md §8(d) item (3): DRAM bytes the kernel actually moved (ncu capture of the same command) over the live time
+        roof["dram_gbs_from_ncu_traffic"] = traffic / (kernel_ms / 1000.0) / 1e9
+        roof["traffic_over_algorithmic"] = traffic / (per_topic * n_topics_per_launch)
+    return roof
+
+
 def make_workload(args, rank, world):
     from bifromq_b200.workload import Workload
     if world > 1 and args.scaling == "strong":
@@ -349,26 +379,7 @@ def main():
         k_ms = float(np.mean(kernel_ms))
         if not args.no_cpu_baseline:
             cpu_base, st, ns, sample_topic_bytes = run_cpu_baseline(w, args, "trie")
-            # B = len(topic) + 4 + 32 V + 8 P + 8 ranges (range-encoded output) + 4, per topic
-            per_topic = (sample_topic_bytes + 4 * ns + 32 * st["V"] + 8 * st["P"] + 8 * st["ranges"] + 4 * ns) / ns
-            import json as _j
-            peaks = {}
-            try:
-                peaks = _j.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except Exception:
-                pass
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            achieved = per_topic * n / (k_ms / 1000.0) / 1e9
-            traffic = None
-            try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-                traffic = _j.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
-            except Exception:
-                pass
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                    "kernel": "match_topics_lane_kernel (tier 0, one lane per topic)", "kernel_ms": k_ms, "alg_bytes_per_topic": per_topic,
-                    "alg_counters_per_topic": {"V": st["V"] / ns, "P": st["P"] / ns, "ranges": st["ranges"] / ns, "R": st["R"] / ns},
-                    "note": "algorithmic bytes per topic measured by the oracle on the cpu_baseline sample"}
+            roof = make_roofline(sample_topic_bytes, st, ns, n, k_ms)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic",

@@ -173,3 +173,23 @@ def test_workload_c5_shapes(pkg):
     fs = w.query_filter_list()
     assert all((b"+" in f) or f.endswith(b"/#") for f in fs)
     assert all(O.is_valid_topic_filter(f, 40, 16, 255) for f in fs[:300])
+
+
+def test_bench_roofline_record_and_defaults():
+    """bench.py's pure-host pieces: the roofline record follows SURVEY.md §8(d) and the default run is the full-size C4 line"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ns, n = 1000, 1_000_000
+    st = {"V": 25.0 * ns, "P": 70.0 * ns, "ranges": 6.0 * ns, "R": 300.0 * ns}
+    r = bench.make_roofline(50 * ns, st, ns, n, 0.5)
+    per_topic = 50 + 4 + 32 * 25.0 + 8 * 70.0 + 8 * 6.0 + 4
+    assert abs(r["alg_bytes_per_topic"] - per_topic) < 1e-9
+    assert abs(r["achieved"] - per_topic * n / 0.5e-3 / 1e9) < 1e-6
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["frac_of_nominal_8000"] - r["achieved"] / 8000.0) < 1e-12
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
+    assert r["traffic"] == traffic and abs(r["dram_gbs_from_ncu_traffic"] - traffic / 0.5e-3 / 1e9) < 1e-6
+    assert bench.METRIC.startswith("publish-topics matched/sec")
