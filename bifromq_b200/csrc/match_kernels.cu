@@ -276,15 +276,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) match_topics_kernel(const 
 // is a handful of nodes (the common case: ~4 per level on BASELINE config C4; ncu: ~2100 warp instructions per
 // topic, profiles/r1_v1_*). Here every lane walks its own topic depth-first:
 //   * a node has at most two continuations per level (exact child, '+' child), so the DFS parks at most ONE
-//     pending '+' branch per level: a 16-entry per-lane array plus a bitmask, never a growing frontier;
-//   * per step a lane reads the 28 bytes at its current level start (aligned words + funnel shift), finds the
-//     '/' with a SWAR zero-byte test — the level table is filled lazily, there is no tokenising pre-pass —,
-//     issues the exact-child probe and the '+' child load together (eight independent LDG.128) and writes the
-//     discovered ranges straight to the topic's INLINE_RANGES inline slots: no staging, no output atomics;
+//     pending '+' branch per level: a (L_MAXLV+1)-entry per-lane array plus a bitmask, never a growing frontier;
+//   * per step a lane reads the 28 bytes at its current level start (up to three aligned 16-byte granules, word select +
+//     funnel shift), finds the '/' with a SWAR zero-byte test — the level table is filled lazily, there is no tokenising
+//     pre-pass —, issues the exact-child slot read (2 x LDG.256) and the '+' child payload read (1 x LDG.256) together and
+//     writes the discovered ranges straight to the topic's INLINE_RANGES inline slots: no staging, no output atomics;
 //   * a lane that finishes takes the next topic at once (warp-uniform refill from 32-topic chunks claimed with
 //     one atomicAdd per chunk), so a straggler never idles the other 31 lanes (v2 of this kernel waited for the
-//     whole batch of 32: ncu showed 10 of 32 lanes active, profiles/r1_v2_*).
-// Anything that does not fit the bounded state (> 16 levels, a level > 24 B, > INLINE_RANGES ranges, topic > 64 KB)
+//     whole batch of 32: ncu showed 10 of 32 lanes active, profiles/r1_v2_*);
+//   * chunks are runs of p.order — the batch sorted by (tenant, leading-level hashes), see launch_order — so the lanes of
+//     a warp walk the same part of the trie, take the same branches and finish together (profiles/r1_v8_*).
+// Anything that does not fit the bounded state (> L_MAXLV levels, a level > 24 B, > INLINE_RANGES ranges, topic > 64 KB)
 // is handed, whole, to the warp-per-topic tier through defer_list.
 constexpr int L_WARPS = 4;
 constexpr int L_MAXLV = 12;
