@@ -193,3 +193,39 @@ def test_bench_roofline_record_and_defaults():
     traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
     assert r["traffic"] == traffic and abs(r["dram_gbs_from_ncu_traffic"] - traffic / 0.5e-3 / 1e9) < 1e-6
     assert bench.METRIC.startswith("publish-topics matched/sec")
+
+
+def _route_blobs(pairs):
+    keys = b"".join(k for k, _ in pairs)
+    vals = b"".join(v for _, v in pairs)
+    koff = np.zeros(len(pairs) + 1, np.int64)
+    voff = np.zeros(len(pairs) + 1, np.int64)
+    koff[1:] = np.cumsum([len(k) for k, _ in pairs])
+    voff[1:] = np.cumsum([len(v) for _, v in pairs])
+    return (np.frombuffer(keys, np.uint8).copy(), koff, np.frombuffer(vals or b"\0", np.uint8).copy(), voff)
+
+
+def test_builder_places_every_child_array_kind():
+    """host builder + its self-check (every placed node is found again from its parent's record the way the kernels look it
+    up) over fan-outs of 1, 3, 16, 17, 40, 300 (perfect-hashed private arrays) and 1500 / 2500 (global tag table)"""
+    from bifromq_b200 import _native as N, schema
+    pairs = []
+    widths = {"w1": 1, "w3": 3, "w16": 16, "w17": 17, "w40": 40, "w300": 300, "w1500": 1500}
+    for name, n in widths.items():
+        for i in range(n):
+            url = schema.receiver_url(i % 2, "r%s%d" % (name, i), "d")
+            pairs.append((schema.route_key("t", "%s/c%04d" % (name, i), url), schema.incarnation_bytes(1)))
+        pairs.append((schema.route_key("t", "%s/+" % name, schema.receiver_url(0, "p" + name, "d")), schema.incarnation_bytes(1)))
+    for i in range(2500):
+        pairs.append((schema.route_key("t2", "dev%05d/state" % i, schema.receiver_url(0, "s%d" % i, "d")), schema.incarnation_bytes(1)))
+    pairs.sort()
+    k, ko, v, vo = _route_blobs(pairs)
+    st = np.zeros(16, np.int64)
+    rc = N.lib.bfq_host_build_stats(k.ctypes.data, ko.ctypes.data, v.ctypes.data, vo.ctypes.data, len(pairs), st.ctypes.data, 16)
+    assert rc == 0, N.lib.bfq_last_error()
+    assert st[0] == len(pairs) and st[1] == 2
+    n_nodes = int(st[2])
+    # 2 roots + per width: the width node, its children, its '+' child; t2: 2500 devices each with a "state" child
+    assert n_nodes == 2 + sum(1 + n + 1 for n in widths.values()) + 2 * 2500
+    assert st[3] >= n_nodes - 2            # slots: private arrays + tag-table blocks
+    assert st[9] + st[10] + st[11] + st[12] + st[13] == n_nodes   # child-count histogram covers every node
