@@ -109,6 +109,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa_node(dev_index):
+    """Run this rank on the CPU socket its GPU hangs off (and first-touch its pinned buffers there): on a two-socket box a
+    process that lands on the far socket sees a third less PCIe bandwidth, which is what the end-to-end number measures.
+    Returns {"node", "cpus", "previous"} or None when the topology is not exposed; never raises."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        previous = os.sched_getaffinity(0)
+        target = cpus & previous
+        if not target or target == previous:
+            return None
+        os.sched_setaffinity(0, target)
+        return {"node": node, "cpus": len(target), "previous": previous}
+    except Exception:
+        return None
+
+
 def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms):
     """`roofline` object of the JSON line. SURVEY.md §8(d): algorithmic bytes per topic
     B = len(topic) + 4 + 32 V + 8 P + 8 ranges (range-encoded output) + 4, with V / P / ranges counted by the oracle on the
@@ -264,6 +296,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
 
     t_gen = time.perf_counter()
     w = make_workload(args, rank, world)
@@ -359,6 +392,11 @@ def main():
         e2e_t.append(time.perf_counter() - t0)
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
+    if numa:   # the CPU baseline below uses every host core
+        try:
+            os.sched_setaffinity(0, numa["previous"])
+        except Exception:
+            pass
     e2e_total = float(sum(e2e_t))
     h2d_bytes = blob_bytes + 8 * (n + 1) + 4 * n
 
@@ -388,6 +426,8 @@ def main():
                            "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
                            "caps": "MaxPersistentFanout=INT_MAX, MaxGroupFanout=INT_MAX",
                            "order": "tier 0 picks the topics in locality order (order_keys_kernel + cub radix sort, inside the timed region)",
+                           "host": ("rank pinned to NUMA node %d of its GPU (%d cpus) for the GPU legs" % (numa["node"], numa["cpus"])) if numa
+                                   else "no NUMA pinning (topology not exposed or single node)",
                            "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},

@@ -193,6 +193,8 @@ def test_bench_roofline_record_and_defaults():
     traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
     assert r["traffic"] == traffic and abs(r["dram_gbs_from_ncu_traffic"] - traffic / 0.5e-3 / 1e9) < 1e-6
     assert bench.METRIC.startswith("publish-topics matched/sec")
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench.pin_to_gpu_numa_node(0) is None      # no GPU here: must decline quietly, never raise
 
 
 def _route_blobs(pairs):
