@@ -598,7 +598,7 @@ __global__ void order_keys_kernel(const OrderParams q, int tenant_bits, int key_
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n_topics) return;
     const int64_t o = q.topic_off[i];
-    const int len = (int) min((int64_t) 40, q.topic_off[i + 1] - o);   // three levels of ordinary topics end well before this
+    const int len = (int) max((int64_t) 0, min((int64_t) 40, q.topic_off[i + 1] - o));   // three levels of ordinary topics end well before this
     const int rest = key_bits - tenant_bits;
     const int b0 = rest / 3 + (rest % 3 > 0), b1 = rest / 3 + (rest % 3 > 1), b2 = rest / 3;
     int tn = q.topic_tenant[i];
