@@ -356,27 +356,30 @@ def main():
     total_ms = float(sum(step_ms))
     # ---- the one exchange step of the sharded path: all ranks gather the per-topic fan-out counts of the
     # whole job (what BatchDistReply carries); timed on its own, the matching itself needs no collective
-    exchange_ms, imbalance = None, None
+    exchange_ms, imbalance, exchange_error = None, None, None
     if world > 1:
         from bifromq_b200 import dist as D
-        fan = D.device_view(out.d_route_count, n, "<i4", dev)
-        for _ in range(3):
-            D.gather_fanout(fan)
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        xe[0].record(stream)
-        for _ in range(args.steps):
-            gathered = D.gather_fanout(fan)
-        xe[1].record(stream)
-        torch.cuda.synchronize(dev)
-        exchange_ms = xe[0].elapsed_time(xe[1]) / args.steps
-        assert gathered.numel() == n * world
-        ex_max, _ = D.aggregate(exchange_ms, 0, dev)
+        try:   # every rank runs the same code on the same shapes, so a failure here is the same failure on every rank
+            fan = D.device_view(out.d_route_count, n, "<i4", dev)
+            for _ in range(3):
+                D.gather_fanout(fan)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            xe[0].record(stream)
+            for _ in range(args.steps):
+                gathered = D.gather_fanout(fan)
+            xe[1].record(stream)
+            torch.cuda.synchronize(dev)
+            exchange_ms = xe[0].elapsed_time(xe[1]) / args.steps
+            assert gathered.numel() == n * world
+        except Exception as ex:   # the exchange is reported beside the metric, it must not take the metric down
+            exchange_ms, exchange_error = None, "%s: %s" % (type(ex).__name__, ex)
+        ex_max, _ = D.aggregate(exchange_ms if exchange_ms is not None else -1.0, 0, dev)
         t_max, _ = D.aggregate(total_ms, 0, dev)
         t_sum = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t_sum)
-        exchange_ms, imbalance = ex_max, t_max / (t_sum.item() / world)
+        exchange_ms, imbalance = (ex_max if exchange_ms is not None else None), t_max / (t_sum.item() / world)
     n_routes = int(torch.from_numpy(np.zeros(1)).sum()) if n == 0 else None
     # ---- e2e through the host-buffer call
     for _ in range(2):
@@ -433,6 +436,9 @@ def main():
                         "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},
                 "gpu_launches": launches, "gpu_launches_note": "own kernels only: order_keys + tier 0 + tier 1 per step (cub's sort passes not counted)", "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
                 "ranges_per_step": n_ranges, "tier2_topics_per_step": n_overflow, "index": stats, "clocks": clocks}
+        if exchange_error is not None:
+            line["exchange"] = {"error": exchange_error}
+            line["load_imbalance_max_over_mean"] = imbalance
         if exchange_ms is not None:
             line["exchange"] = {"what": "all-gather of per-topic fan-out counts (int32) over NCCL, all ranks end with the whole job's",
                                 "ms_per_step": exchange_ms, "bytes_per_rank": 4 * n,
