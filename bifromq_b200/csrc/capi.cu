@@ -164,6 +164,7 @@ struct CoreOut {
 int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                         const int32_t* max_p, const int32_t* max_g, cudaStream_t stream) {
     if (n_tenants < 0) return fail(BFQ_E_INVALID, "n_tenants < 0");
+    if (n_tenants >= (1 << 30)) return fail(BFQ_E_RANGE, "more than 2^30 tenants in one batch");   // bit 30 of the lane's tenant word is a flag
     const size_t nt = (size_t) std::max(n_tenants, 1);
     // the same tenant list + caps usually accompany every batch: fingerprint it and keep the device table
     uint64_t fp = 0xcbf29ce484222325ull ^ (uint64_t) n_tenants;
