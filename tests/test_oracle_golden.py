@@ -424,6 +424,74 @@ def test_trigger_group_fanout_throttling(mode):  # :303-342
 
 
 # ------------------------------------------------------------------------------------------------
+# bifromq-dist/bifromq-dist-worker/src/test/.../DistQoS0Test.java:82-340,450-561 — the integration tests' SUB sets and the
+# fan-out count BatchDistReply reports for the published topic (a shared-subscription group counts once, whatever its
+# member count; MqttBroker = 0, InboxService = 1, DistWorkerTest.java:130-131)
+# ------------------------------------------------------------------------------------------------
+INT_MAX = 2 ** 31 - 1
+
+
+def _qos0_case(name):
+    kv = O.KV()
+    A, B = TENANT_ID, OTHER_TENANT
+    if name == "case1":          # :83-92
+        normal(kv, A, "TopicA/#", 0, "inbox1", "batch1", 1)
+        return kv, "TopicB", 0
+    if name == "case2":          # :95-149 (BMP and supplementary-plane characters, '#' below an empty first level)
+        normal(kv, A, "/你好/hello/😄", 0, "inbox1", "batch1", 1)
+        normal(kv, A, "/#", 0, "inbox1", "batch1", 1)
+        normal(kv, A, "/#", 1, "inbox2", "batch2", 1)
+        return kv, "/你好/hello/😄", 3
+    if name == "case3":          # :152-193
+        normal(kv, A, "/a/b/c", 0, "inbox1", "batch1", 1)
+        normal(kv, A, "/a/b/c", 0, "inbox2", "batch1", 1)
+        return kv, "/a/b/c", 2
+    if name in ("case4", "case5"):   # :196-243 unordered share, :246-284 ordered share: two members, ONE group
+        group(kv, A, "/a/b/c", "group", {O.receiver_url(0, "inbox1", "batch1"): 1, O.receiver_url(0, "inbox2", "batch2"): 1},
+              ordered=name == "case5")
+        return kv, "/a/b/c", 1
+    if name == "case6":          # :287-306 normal + $share + $oshare of the same filter are three routes
+        normal(kv, A, "/a/b/c", 0, "inbox6", "batch1", 1)
+        group(kv, A, "/a/b/c", "group", {O.receiver_url(0, "inbox7", "batch2"): 1})
+        group(kv, A, "/a/b/c", "group", {O.receiver_url(0, "inbox8", "batch3"): 1}, ordered=True)
+        return kv, "/a/b/c", 3
+    if name == "case7":          # :309-338 another tenant's '#' does not leak
+        normal(kv, A, "/a/b/c", 0, "inbox1", "batch1", 1)
+        normal(kv, B, "#", 0, "inbox1", "batch1", 1)
+        return kv, "/a/b/c", 1
+    if name == "wildcard_refresh":   # :450-515 final state: exact + '/#' + '$share/group/#' + '$oshare/group/#'
+        normal(kv, A, "/a/b/c", 0, "inbox1", "batch1", 1)
+        normal(kv, A, "/#", 0, "inbox2", "batch2", 1)
+        group(kv, A, "#", "group", {O.receiver_url(0, "inbox3", "batch3"): 1})
+        group(kv, A, "#", "group", {O.receiver_url(0, "inbox3", "batch3"): 1}, ordered=True)
+        return kv, "/a/b/c", 4
+    if name == "probe_and_seek":     # :518-528 more than 20 routes of "test" sit between the cursor and "test/#"
+        normal(kv, A, "test/#", 0, "inbox", "batch1", 1)
+        for i in range(21):
+            normal(kv, A, "test", 0, "inbox%d" % i, "batch1", 1)
+        return kv, "test/r1", 1
+    if name == "ordered_share_groups":   # :531-562 two ordered groups on '#'
+        group(kv, A, "#", "group1", {O.receiver_url(0, "inbox1", "batch1"): 1}, ordered=True)
+        group(kv, A, "#", "group2", {O.receiver_url(0, "inbox1", "batch1"): 1}, ordered=True)
+        return kv, "/a/b/c", 2
+    raise KeyError(name)
+
+
+QOS0_CASES = ["case1", "case2", "case3", "case4", "case5", "case6", "case7", "wildcard_refresh", "probe_and_seek",
+              "ordered_share_groups"]
+
+
+@pytest.mark.parametrize("mode", ALL_MODES)
+@pytest.mark.parametrize("name", QOS0_CASES)
+def test_dist_qos0_fanout_counts(name, mode):
+    kv, topic, fanout = _qos0_case(name)
+    res, out = kv.match_all(TENANT_ID, [topic], INT_MAX, INT_MAX, mode)
+    assert set(res) == {topic}
+    assert len(res[topic]) == fanout
+    assert not out.events
+
+
+# ------------------------------------------------------------------------------------------------
 # bifromq-dist/bifromq-dist-worker/src/test/.../KeyLayoutTest.java:47-78 — key byte order == iterator order
 # ------------------------------------------------------------------------------------------------
 
