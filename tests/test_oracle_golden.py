@@ -424,6 +424,46 @@ def test_trigger_group_fanout_throttling(mode):  # :303-342
 
 
 # ------------------------------------------------------------------------------------------------
+# bifromq-dist/bifromq-dist-worker/src/test/.../cache/MatchedRoutesTest.java:59-190 — the cap rules of the accumulator,
+# expressed through matchAll (the mutable add/remove/adjust API of IMatchedRoutes stays in Java and is out of scope)
+# ------------------------------------------------------------------------------------------------
+MR_TOPIC = "sensors/temperature"
+
+
+@pytest.mark.parametrize("mode", ALL_MODES)
+def test_matched_routes_persistent_within_and_over_limit(mode):  # :59-96
+    kv = O.KV()
+    normal(kv, TENANT_ID, MR_TOPIC, 1, "receiverA", "delivererA", 1)
+    res, out = kv.match_all(TENANT_ID, [MR_TOPIC], 2, 2, mode)
+    assert len(res[MR_TOPIC]) == 1 and out.persistent_fanout.tolist() == [1] and not out.events
+    normal(kv, TENANT_ID, MR_TOPIC, 1, "receiverB", "delivererB", 1)
+    res, out = kv.match_all(TENANT_ID, [MR_TOPIC], 1, 2, mode)
+    assert len(res[MR_TOPIC]) == 1 and out.persistent_fanout.tolist() == [1]
+    assert [(e[0], e[1], e[3]) for e in out.events] == [(1, 0, 1)]       # PersistentFanoutThrottled, maxCount 1
+
+
+@pytest.mark.parametrize("mode", ALL_MODES)
+def test_matched_routes_non_persistent_is_not_capped(mode):  # :97-107
+    kv = O.KV()
+    for i in range(3):
+        normal(kv, TENANT_ID, MR_TOPIC, 0, "receiver%d" % i, "deliverer", 1)     # subBrokerId 0: not persistent
+    res, out = kv.match_all(TENANT_ID, [MR_TOPIC], 1, 2, mode)
+    assert len(res[MR_TOPIC]) == 3 and out.persistent_fanout.tolist() == [0] and not out.events
+
+
+@pytest.mark.parametrize("mode", ALL_MODES)
+def test_matched_routes_group_within_and_over_limit(mode):  # :152-190
+    kv = O.KV()
+    group(kv, TENANT_ID, MR_TOPIC, "groupA", {O.receiver_url(1, "receiverA", "delivererA"): 1})
+    res, out = kv.match_all(TENANT_ID, [MR_TOPIC], 2, 2, mode)
+    assert len(res[MR_TOPIC]) == 1 and out.group_fanout.tolist() == [1] and not out.events
+    group(kv, TENANT_ID, MR_TOPIC, "groupB", {O.receiver_url(1, "receiverB", "delivererB"): 1})
+    res, out = kv.match_all(TENANT_ID, [MR_TOPIC], 2, 1, mode)
+    assert len(res[MR_TOPIC]) == 1 and out.group_fanout.tolist() == [1]
+    assert [(e[0], e[1], e[3]) for e in out.events] == [(2, 0, 1)]       # GroupFanoutThrottled, maxCount 1
+
+
+# ------------------------------------------------------------------------------------------------
 # bifromq-dist/bifromq-dist-worker/src/test/.../DistQoS0Test.java:82-340,450-561 — the integration tests' SUB sets and the
 # fan-out count BatchDistReply reports for the published topic (a shared-subscription group counts once, whatever its
 # member count; MqttBroker = 0, InboxService = 1, DistWorkerTest.java:130-131)
@@ -475,6 +515,35 @@ def _qos0_case(name):
         group(kv, A, "#", "group2", {O.receiver_url(0, "inbox1", "batch1"): 1}, ordered=True)
         return kv, "/a/b/c", 2
     raise KeyError(name)
+
+
+# bifromq-dist/bifromq-dist-worker/src/test/.../FanoutThrottledTest.java:52-70,148-166,240-262 and BatchDistTest.java:78-109
+@pytest.mark.parametrize("mode", ALL_MODES)
+def test_fanout_throttled_and_batch_dist_counts(mode):
+    kv = O.KV()
+    for i in (1, 2, 3):          # persistent sessions (InboxService = 1): capped at MaxPersistentFanout = 2
+        normal(kv, TENANT_ID, "/fanout/topic", 1, "inbox%d" % i, "batch%d" % i, 1)
+    res, out = kv.match_all(TENANT_ID, ["/fanout/topic"], 2, INT_MAX, mode)
+    assert len(res["/fanout/topic"]) == 2 and len(out.events) == 1
+    kv = O.KV()
+    for i in (1, 2, 3):          # three shared groups: capped at MaxGroupFanout = 2
+        group(kv, TENANT_ID, "fanout/topic", "group%d" % i, {O.receiver_url(1, "inbox%d" % i, "batch%d" % i): 1})
+    res, out = kv.match_all(TENANT_ID, ["fanout/topic"], INT_MAX, 2, mode)
+    assert len(res["fanout/topic"]) == 2 and len(out.events) == 1
+    kv = O.KV()
+    for i in (1, 2, 3):          # transient sessions (MqttBroker = 0) are never capped
+        normal(kv, TENANT_ID, "/fanout/topic2", 0, "inbox%d" % i, "batch%d" % i, 1)
+    res, out = kv.match_all(TENANT_ID, ["/fanout/topic2"], 2, 2, mode)
+    assert len(res["/fanout/topic2"]) == 3 and not out.events
+    kv = O.KV()                  # BatchDistTest: one request, four topics
+    normal(kv, TENANT_ID, "/a/1", 0, "inbox1", "batch1", 1)
+    normal(kv, TENANT_ID, "/a/2", 0, "inbox1", "batch1", 1)
+    normal(kv, TENANT_ID, "/a/2", 0, "inbox3", "batch1", 1)
+    normal(kv, TENANT_ID, "/a/3", 1, "inbox2", "batch2", 1)
+    normal(kv, TENANT_ID, "/a/4", 1, "inbox2", "batch2", 1)
+    topics = ["/a/1", "/a/2", "/a/3", "/a/4"]
+    res, out = kv.match_all(TENANT_ID, topics, INT_MAX, INT_MAX, mode)
+    assert [len(res[t]) for t in topics] == [1, 2, 1, 1]
 
 
 QOS0_CASES = ["case1", "case2", "case3", "case4", "case5", "case6", "case7", "wildcard_refresh", "probe_and_seek",
