@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Record-keeping run of the inverse path on BASELINE.json config C5 (1M retained topics vs 100k wildcard SUBSCRIBE
 filters): filters/s through bfq_rmatch (host buffers in, ids out) with limit = 10 (RetainMessageMatchLimit default) and
-unlimited, next to the oracle's TopicLevelTrie restatement on the host cores. Not the driver's bench line (bench.py)."""
+unlimited, next to the oracle's TopicLevelTrie restatement on the host cores. Not the driver's bench line (bench.py); it lives
+under tests/ because it runs the oracle as the CPU yardstick, which only test infrastructure may do.
+
+    python tests/bench_inverse.py [scale]
+"""
 import json
 import os
 import sys
@@ -11,7 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # oracle_lib
 
 
 def main():
