@@ -55,6 +55,18 @@ def test_product_package_does_not_touch_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("oracle/", "oracle_lib", "liboracle", "import oracle", "from oracle", "oracle.h", "orc_"):
                     assert needle not in src, "%s must not use the oracle (%s)" % (f, needle)
+    # neither do the helper scripts; only tests/, __graft_entry__.smoke() and bench.py's CPU legs may
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        src = open(os.path.join(ROOT, "tools", f), errors="replace").read()
+        for needle in ("oracle_lib", "liboracle", "import oracle", "from oracle"):
+            assert needle not in src, "tools/%s must not use the oracle (%s)" % (f, needle)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [i for i in range(len(bench)) if bench.startswith("import oracle_lib", i)]
+    assert uses, "bench.py times the oracle for cpu_baseline / --impl reference"
+    for i in uses:   # the one place: oracle_for_sample(), called by run_cpu_baseline() only (cpu_baseline and --impl reference)
+        head = bench[:i]
+        fn = head[head.rindex("\ndef ") + 5:].split("(")[0]
+        assert fn in ("oracle_for_sample",), "bench.py imports the oracle in %s()" % fn
 
 
 # ------------------------------------------------------------------ codec parity (product C++ vs oracle C++)
