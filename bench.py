@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="topics in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-pfanout", type=int, default=2 ** 31 - 1, help="Setting.MaxPersistentFanout (reference default INT_MAX)")
+    ap.add_argument("--max-gfanout", type=int, default=100, help="Setting.MaxGroupFanout (reference default 100)")
     return ap.parse_args()
 
 
@@ -141,10 +143,12 @@ def pin_to_gpu_numa_node(dev_index):
         return None
 
 
-def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms):
+def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms, gpu_ranges=None, gpu_routes=None, kernel_name=None):
     """`roofline` object of the JSON line. SURVEY.md §8(d): algorithmic bytes per topic
-    B = len(topic) + 4 + 32 V + 8 P + 8 ranges (range-encoded output) + 4, with V / P / ranges counted by the oracle on the
-    cpu_baseline sample (`st`, over `ns` topics); achieved = B x topics per launch / the tier-0 kernel's duration."""
+    B = len(topic) + 4 + 32 V + 8 P + 8 ranges (range-encoded output) + 4, with V / P / ranges counted by the oracle over the
+    cpu_baseline sample (`st`, over `ns` topics: the WHOLE batch by default); achieved = B x topics per launch / the tier-0
+    kernel's duration. Duplicate topics count like any other topic (the figure is per topic of the batch, whatever the
+    kernel does about repeats)."""
     per_topic = (sample_topic_bytes + 4 * ns + 32 * st["V"] + 8 * st["P"] + 8 * st["ranges"] + 4 * ns) / ns
     peaks = {}
     try:
@@ -153,17 +157,26 @@ def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = per_topic * n_topics_per_launch / (kernel_ms / 1000.0) / 1e9
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))["dram_bytes_per_launch"]
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel cannot be measured inside a bench run (ncu replays every
+    # launch ~40 times); it comes from the committed `ncu --set full` capture of the same command, named here, or is null
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel_traffic.json")))
+        if tj.get("config", "C4") == (kernel_name or {}).get("config", "C4"):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
             "frac_of_nominal_8000": achieved / 8000.0,
-            "kernel": "match_topics_lane_kernel (tier 0, one lane per topic)", "kernel_ms": kernel_ms, "alg_bytes_per_topic": per_topic,
+            "kernel": "match_topics_lane_kernel (tier 0, one lane per distinct topic)", "kernel_ms": kernel_ms, "alg_bytes_per_topic": per_topic,
             "alg_counters_per_topic": {"V": st["V"] / ns, "P": st["P"] / ns, "ranges": st["ranges"] / ns, "R": st["R"] / ns},
-            "note": "algorithmic bytes per topic measured by the oracle on the cpu_baseline sample"}
+            "note": "algorithmic bytes per topic measured by the oracle over %d topics (%s)" % (ns, "the whole batch" if ns == n_topics_per_launch else "uniform random sample")}
+    if gpu_ranges is not None and ns == n_topics_per_launch:
+        # same population on both sides: the oracle's matched-filter and route counts must equal the GPU's own
+        roof["counts_check"] = {"oracle_ranges": int(st["ranges"]), "gpu_ranges": int(gpu_ranges), "oracle_routes": int(st["R"]),
+                                "gpu_routes": int(gpu_routes), "equal": int(st["ranges"]) == int(gpu_ranges) and int(st["R"]) == int(gpu_routes)}
     if traffic:
         # DRAM bytes the kernel actually moved (ncu capture of the same command) over the live time
         roof["dram_gbs_from_ncu_traffic"] = traffic / (kernel_ms / 1000.0) / 1e9
@@ -181,81 +194,103 @@ def make_workload(args, rank, world):
 
 
 def cpu_sample_indices(w, want):
-    """bounded sample of the batch: every topic of every 8th tenant (keeps the largest tenant), capped at `want`"""
-    tt = np.asarray(w.topic_tenant[:w.n_topics])
-    keep = np.nonzero(tt % 8 == 0)[0] if w.n_tenants >= 8 else np.arange(w.n_topics)
-    if len(keep) > want:
-        keep = keep[np.linspace(0, len(keep) - 1, want).astype(np.int64)]
-    return keep
+    """UNBIASED bounded sample of the batch: the whole batch when it fits `want`, else a uniform random subset without
+    replacement (seeded). Round 1 took "every topic of every 8th tenant", which over-weights the largest tenant (tenant index
+    == Zipf rank): 1494 B/topic instead of the whole batch's 1162."""
+    if w.n_topics <= want:
+        return np.arange(w.n_topics)
+    return np.sort(np.random.default_rng(0xB1F20).choice(w.n_topics, want, replace=False))
+
+
+_ORACLE_CACHE = {}
 
 
 def oracle_for_sample(w, idx):
-    """load only the sampled tenants' routes into the oracle (tenants are independent key ranges)"""
+    """the oracle over ALL tenants' routes (a uniform topic sample touches every tenant) and the sampled topics as blobs"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    tt = np.asarray(w.topic_tenant[:w.n_topics])[idx]
-    tenants = w.tenants
-    used = sorted(set(tt.tolist()))
-    kv = O.KV()
-    keys_all = w.keys
-    # tenant key ranges: binary search on the tenant begin keys
-    kb = keys_all.tobytes() if w.n_routes < 3_000_000 else None
-    for t in used:
-        begin = O.tenant_begin_key(tenants[t])
-        end = O.upper_bound(begin)
-        lo = _lower_bound(w, begin, kb)
-        hi = _lower_bound(w, end, kb)
-        if hi > lo:
-            ko = np.ascontiguousarray(w.key_off[lo:hi + 1])
-            vo = np.ascontiguousarray(w.val_off[lo:hi + 1])
-            O.lib.orc_kv_load(kv.h, w.keys.ctypes.data, ko, w.vals.ctypes.data, vo, hi - lo)
-    kv.freeze()
-    remap = {t: i for i, t in enumerate(used)}
-    sub_tenants = [tenants[t] for t in used]
-    sub_tt = np.array([remap[t] for t in tt.tolist()], np.int32)
-    topics = [w.topic(int(i)) for i in idx]
-    return O, kv, sub_tenants, topics, sub_tt
+    if _ORACLE_CACHE.get("w") is not w:
+        kv = O.KV()
+        kv.load(w.keys, w.key_off, w.vals, w.val_off)
+        kv.freeze()
+        _ORACLE_CACHE.update(w=w, kv=kv)
+    kv = _ORACLE_CACHE["kv"]
+    if len(idx) == w.n_topics:
+        pb, poff = w.topics, np.ascontiguousarray(w.topic_off)
+    else:
+        off = np.asarray(w.topic_off)
+        lens = (off[idx + 1] - off[idx]).astype(np.int64)
+        poff = np.zeros(len(idx) + 1, np.int64)
+        poff[1:] = np.cumsum(lens)
+        pb = np.zeros(max(int(poff[-1]), 1), np.uint8)
+        src = np.asarray(w.topics)
+        for k, i in enumerate(idx.tolist()):   # <= a few hundred thousand short copies
+            pb[poff[k]:poff[k + 1]] = src[off[i]:off[i + 1]]
+    tt = np.ascontiguousarray(np.asarray(w.topic_tenant[:w.n_topics])[idx]).astype(np.int32)
+    return O, kv, w.tenants, (pb, poff), tt
 
 
-def _lower_bound(w, key, kb):
-    lo, hi = 0, w.n_routes
-    mv = memoryview(w.keys)
-    while lo < hi:
-        mid = (lo + hi) // 2
-        k = bytes(mv[w.key_off[mid]:w.key_off[mid + 1]])
-        if k < key:
-            lo = mid + 1
-        else:
-            hi = mid
-    return lo
-
-
-def run_cpu_baseline(w, args, mode_name):
-    """times the oracle on the host cores over a bounded sample; returns the cpu_baseline dict and the per-topic
-    algorithmic-byte figures measured on the same sample"""
+def run_cpu_baseline(w, args, mode_name, cached=False):
+    """times the oracle on the host cores over a bounded, unbiased sample; returns the cpu_baseline dict and the per-topic
+    algorithmic-byte figures measured on the same sample.
+    mode_name: "trie" = the oracle's per-topic filter-trie walk over the WHOLE batch (also the exact V / P / ranges counters);
+    "reference" = the literal TenantRouteMatcher.matchAll restatement, one call per topic (the production shape,
+    DW/cache/TenantRouteCache.java:185-186) on a uniform random sample. cached=True puts a (tenant, topic) -> result map in
+    front, the way TenantRouteCache (DW/cache/TenantRouteCache.java:100-139) serves repeated topics: every distinct pair is
+    matched once, the repeats are lookups."""
     cores = os.cpu_count() or 1
-    want = args.cpu_sample or 200000
+    want = args.cpu_sample or (1 << 30 if mode_name == "trie" else 100000)
     idx = cpu_sample_indices(w, want)
-    O, kv, tenants, topics, tt = oracle_for_sample(w, idx)
+    O, kv, tenants, (pb, poff), tt = oracle_for_sample(w, idx)
     tb, toff = O.blob(tenants)
-    pb, poff = O.blob(topics)
+    n = len(idx)
     mode = O.MODE_TRIE if mode_name == "trie" else O.MODE_REFERENCE
     singleton = mode_name != "trie"
+    n_unique = n
+    if cached:
+        # the cache's effect on the matcher's work: only the first occurrence of every (tenant, topic) pair reaches it
+        seen, keep = set(), []
+        mv = memoryview(np.ascontiguousarray(pb))
+        for k in range(n):
+            key = (int(tt[k]), bytes(mv[poff[k]:poff[k + 1]]))
+            if key not in seen:
+                seen.add(key)
+                keep.append(k)
+        keep = np.asarray(keep, np.int64)
+        n_unique = len(keep)
+        lens = (poff[keep + 1] - poff[keep]).astype(np.int64)
+        poff2 = np.zeros(n_unique + 1, np.int64)
+        poff2[1:] = np.cumsum(lens)
+        pb2 = np.zeros(max(int(poff2[-1]), 1), np.uint8)
+        for j, k in enumerate(keep.tolist()):
+            pb2[poff2[j]:poff2[j + 1]] = pb[poff[k]:poff[k + 1]]
+        pb, poff, tt_run = pb2, poff2, np.ascontiguousarray(tt[keep])
+    else:
+        tt_run = tt
+    n_run = len(tt_run)
     # warm (also builds the oracle's trie outside the timed region)
-    kv.match_blobs(tb, toff, pb, poff, tt, min(len(topics), 256), 2 ** 31 - 1, 100, mode, singleton, cores)
-    passes, dt = (5 if mode_name == "trie" else 1), 0.0
-    for _ in range(passes):
-        out = kv.match_blobs(tb, toff, pb, poff, tt, len(topics), 2 ** 31 - 1, 100, mode, singleton, cores)
-        dt += kv.last_match_seconds   # the C++ matcher call alone (result marshalling to numpy excluded)
-    dt /= passes
-    n = len(topics)
+    kv.match_blobs(tb, toff, pb, poff, tt_run, min(n_run, 256), 2 ** 31 - 1, 100, mode, singleton, cores)
+    # >= 5 timed passes, each repeated until it lasts >= 1 s of wall time; the MEDIAN pass is reported
+    passes, per_pass = [], []
+    for _ in range(5):
+        dt, reps = 0.0, 0
+        while dt < 1.0 and reps < 64:
+            out = kv.match_blobs(tb, toff, pb, poff, tt_run, n_run, 2 ** 31 - 1, 100, mode, singleton, cores)
+            dt += kv.last_match_seconds   # the C++ matcher call alone (result marshalling to numpy excluded)
+            reps += 1
+        passes.append(dt / reps)
+        per_pass.append(reps)
+    dt = float(np.median(passes))
     stats = out.stats
+    what = ("oracle filter-trie walk" if mode_name == "trie" else
+            "literal TenantRouteMatcher.matchAll restatement, one call per topic (production shape)")
     res = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": "%d topics (all topics of every 8th tenant, evenly thinned) against those tenants' %d routes; %s; %.2f s wall per pass = %.0f core-seconds"
-                     % (n, len(kv), "oracle filter-trie walk, std::thread x %d, mean of 5 passes" % cores if mode_name == "trie" else
-                        "literal TenantRouteMatcher.matchAll restatement, one call per topic (production shape), std::thread x %d" % cores,
-                        dt, dt * cores)}
-    return res, stats, n, float(np.diff(poff).sum())
+           "sample": "%s: %d topics (%s) against all %d routes; %s, std::thread x %d; median of 5 passes of >= 1 s (%.3f s per "
+                     "batch, spread %.3f-%.3f) = %.0f core-seconds per batch%s"
+                     % (w.config, n, "the whole batch" if n == w.n_topics else "uniform random sample without replacement", len(kv), what, cores,
+                        dt, min(passes), max(passes), dt * cores,
+                        ("; a (tenant, topic) result cache in front: %d distinct pairs matched, %d repeats served as lookups" % (n_unique, n - n_unique)) if cached else "")}
+    return res, stats, n, float(poff[-1] - poff[0]) if not cached else None
 
 
 def main():
@@ -269,20 +304,15 @@ def main():
         if rank != 0:
             return
         w = make_workload(args, 0, 1)
-        samples, per = [], None
         base, _, n, _ = run_cpu_baseline(w, args, "reference")
-        # the contract's K steps: each step is the same bounded sample; W warm-ups are untimed
-        vals = [base["value"]]
-        for _ in range(max(0, min(args.steps, 3) - 1)):
-            b2, _, _, _ = run_cpu_baseline(w, args, "reference")
-            vals.append(b2["value"])
-        v = float(np.mean(vals))
-        base["value"] = v
-        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
+        cached, _, _, _ = run_cpu_baseline(w, args, "reference", cached=True)
+        v = base["value"]
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 5, "warmup": 1,
                 "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic", "impl": "reference",
                 "config": {"workload": workload_name(args, w), "note": "C++ restatement of the Java reference, not the JVM (no JDK in the image)"},
                 "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "with_tenant_route_cache": {"value": cached["value"], "unit": UNIT, "sample": cached["sample"]},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -319,39 +349,61 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
-    def step_device():
-        return idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, stream=stream.cuda_stream)
+    nt = len(w.tenants)
+    # the reference's defaults (Setting.MaxPersistentFanout = INT_MAX, MaxGroupFanout = 100), as in the CPU legs
+    max_p, max_g = [args.max_pfanout] * nt, [args.max_gfanout] * nt
+
+    def enqueue_device():
+        """one step, enqueued without a host synchronisation (bfq_match_device_async): every count the later kernels need is
+        read on the device; the result is waited for DEPTH steps later, so the host never idles the GPU between steps"""
+        return idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, max_p, max_g,
+                                stream=stream.cuda_stream, wait=False)
 
     def step_e2e():
-        r = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy())
+        r = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy(), max_p, max_g)
         d2h = 12 * n + 8 * len(r.ranges) + 12 * len(r.throttled)
         tm = r.timings_ms
         r.close()
         return d2h, tm
 
+    DEPTH = 3   # matches in flight (each on its own leased workspace)
     sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    inflight = []
+    for _ in range(max(args.warmup, 3) + DEPTH):   # warm-up (also creates the DEPTH workspaces the timed loop will reuse)
+        inflight.append(enqueue_device())
+        if len(inflight) >= DEPTH:
+            inflight.pop(0).wait().release()
+    while inflight:
+        inflight.pop(0).wait().release()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, launches, n_ranges, n_overflow = [], 0, 0, 0
+    kernel_ms, launches, n_ranges, n_overflow, n_distinct = [], 0, 0, 0, 0
+    done = []
     torch.cuda.synchronize(dev)
     for i in range(args.steps):
-        flush.zero_()                     # L2 flush between timed iterations (untimed)
+        flush.zero_()                     # L2 flush between timed iterations (untimed: outside the event pair)
         ev[i][0].record(stream)
-        out = step_device()
+        inflight.append(enqueue_device())
         ev[i][1].record(stream)
-        kernel_ms.append(idx.last_kernel_ms())
-        launches += out.n_launches
-        n_ranges, n_overflow = out.n_ranges, out.n_overflow_topics
+        if len(inflight) >= DEPTH:
+            done.append(inflight.pop(0).wait())
+    while inflight:
+        done.append(inflight.pop(0).wait())
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+    for out in done:
+        kernel_ms.append(out.tier0_ms)
+        launches += out.n_launches
+        n_ranges, n_overflow, n_distinct = out.n_ranges, out.n_overflow_topics, out.n_distinct_topics
+    out = done[-1]               # kept for the exchange leg below
+    for o in done[:-1]:
+        o.release()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     # ---- the one exchange step of the sharded path (SURVEY.md §8e): all ranks gather the per-topic fan-out counts of the
@@ -412,29 +464,33 @@ def main():
 
     if rank == 0:
         # matched routes of one batch (for the fan-out routes/s figure)
-        res = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy())
+        res = idx.match(tenants, h_topics.numpy(), h_off.numpy(), h_tt.numpy(), max_p, max_g)
         routes_per_batch = int(res.route_count.astype(np.int64).sum())
+        ranges_per_batch = int(res.span_count.astype(np.int64).sum())   # matched filters with >= 1 route, over every topic
         res.close()
         stats = idx.stats()
         cpu_base, roof = None, None
         k_ms = float(np.mean(kernel_ms))
         if not args.no_cpu_baseline:
             cpu_base, st, ns, sample_topic_bytes = run_cpu_baseline(w, args, "trie")
-            roof = make_roofline(sample_topic_bytes, st, ns, n, k_ms)
+            roof = make_roofline(sample_topic_bytes, st, ns, n, k_ms, ranges_per_batch, routes_per_batch, {"config": args.config})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic",
                 "config": {"workload": workload_name(args, w), "routes_per_gpu": w.n_routes, "filters_per_gpu": w.n_filters,
                            "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "parallelism": "tenant-sharded x%d" % world,
                            "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
-                           "caps": "MaxPersistentFanout=INT_MAX, MaxGroupFanout=INT_MAX",
-                           "order": "tier 0 picks the topics in locality order (order_keys_kernel + cub radix sort, inside the timed region)",
+                           "caps": "MaxPersistentFanout=%s, MaxGroupFanout=%s (reference defaults: INT_MAX, 100)" % (
+                               "INT_MAX" if args.max_pfanout == 2 ** 31 - 1 else args.max_pfanout, "INT_MAX" if args.max_gfanout == 2 ** 31 - 1 else args.max_gfanout),
+                           "order": "inside the timed region: duplicate (tenant, topic) pairs are found with a device hash table and answered from their "
+                                    "first occurrence (%d of %d topics distinct), the distinct ones are matched in locality order (own counting sort)" % (n_distinct, n),
+                           "pipelining": "steps are enqueued without host synchronisation (bfq_match_device_async), %d in flight; timed per step with CUDA events on the launching stream" % DEPTH,
                            "host": ("rank pinned to NUMA node %d of its GPU (%d cpus) for the GPU legs" % (numa["node"], numa["cpus"])) if numa
                                    else "no NUMA pinning (topology not exposed or single node)",
                            "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},
-                "gpu_launches": launches, "gpu_launches_note": "own kernels only: order_keys + tier 0 + tier 1 per step (cub's sort passes not counted)", "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
+                "gpu_launches": launches, "gpu_launches_note": "own kernels per step: order prep/scan/scatter + tier 0 + tier 1 + followers + caps (2)", "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
                 "ranges_per_step": n_ranges, "tier2_topics_per_step": n_overflow, "index": stats, "clocks": clocks}
         if exchange_error is not None:
             line["exchange"] = {"error": exchange_error}

@@ -28,7 +28,8 @@ class BfqDeviceResult(C.Structure):
     _fields_ = [("d_span_begin", C.c_void_p), ("d_span_count", C.c_void_p), ("d_route_count", C.c_void_p),
                 ("d_ranges", C.c_void_p), ("d_throttled", C.c_void_p), ("n_ranges", C.c_int64),
                 ("n_throttled", C.c_int64), ("n_routes", C.c_int64), ("n_overflow_topics", C.c_int64),
-                ("n_flagged_topics", C.c_int64), ("n_launches", C.c_int64)]
+                ("n_flagged_topics", C.c_int64), ("n_launches", C.c_int64), ("n_distinct_topics", C.c_int64),
+                ("tier0_ms", C.c_double), ("generation", C.c_uint64), ("lease", C.c_void_p)]
 
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -40,6 +41,7 @@ _SIGNATURES = {
     "bfq_index_load": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64]),
     "bfq_index_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]),
     "bfq_index_commit": (_i32, [_vp]),
+    "bfq_index_generation": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "bfq_index_stats": (_i32, [_vp, _vp, _i32]),
     "bfq_host_build_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32]),
     "bfq_index_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_double)]),
@@ -54,10 +56,16 @@ _SIGNATURES = {
     "bfq_result_ranges": (_vp, [_vp, C.POINTER(_i64)]),
     "bfq_result_throttled": (_vp, [_vp, C.POINTER(_i64)]),
     "bfq_result_expand": (_i64, [_vp, _vp, _vp, _i64]),
+    "bfq_result_route_lookup": (_i32, [_vp, _i64, _vp, _i64, C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]),
+    "bfq_result_route_kinds": (_i32, [_vp, _vp, _i64, _vp]),
+    "bfq_result_generation": (C.c_uint64, [_vp]),
     "bfq_result_timings": (_i32, [_vp, _vp, _i32]),
     "bfq_result_free": (None, [_vp]),
     "bfq_match_device": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(BfqDeviceResult)]),
-    "bfq_expand_device": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "bfq_match_device_async": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(BfqDeviceResult)]),
+    "bfq_device_result_wait": (_i32, [C.POINTER(BfqDeviceResult)]),
+    "bfq_device_result_release": (None, [C.POINTER(BfqDeviceResult)]),
+    "bfq_expand_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "bfq_receiver_url": (_i64, [_i32, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_route_key": (_i64, [C.c_char_p, _i64, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_tenant_begin_key": (_i64, [C.c_char_p, _i64, _vp, _i64]),

@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -77,71 +79,93 @@ struct PinBuf {
 
 }  // namespace
 
-struct bfq_result {
-    bfq_index* owner = nullptr;
-    int64_t n_topics = 0, n_ranges = 0, n_throttled = 0;
-    const uint32_t *span_begin = nullptr, *span_count = nullptr, *route_count = nullptr;
-    const bfq_range* ranges = nullptr;
-    const bfq_throttled* throttled = nullptr;
-    double ms[4] = {0, 0, 0, 0};
-};
-
-struct bfq_index {
+// ------------------------------------------------------------------------------------------------ snapshots
+// One committed state of the index: device arrays + the host-side tables results are resolved against (segment table,
+// route kinds, raw KV). Immutable once published and reference counted: every match pins the snapshot it ran on, so a
+// result's ranks always resolve against the KV order they were produced from, whatever is committed meanwhile.
+struct Snapshot {
     int device = 0;
-    std::mutex mu;         // device snapshot + workspace: matches, lookups, the snapshot swap of commit
-    std::mutex stage_mu;   // staging area: reset / load / apply and the (long) host-side rebuild of commit
-    Staging staging;
-    FlatIndex flat;          // host copy of the committed snapshot (segs / tenant map / stats are used on the host)
-    KVBlob committed;        // committed KV (for bfq_route_lookup)
-    bool have_snapshot = false;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, work_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_h2d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t evk[2] = {nullptr, nullptr};
-    double last_kernel_ms = 0;
-    size_t l2_window_bytes = 0;
-    bool tenant_tab_valid = false;     // resolved tenant table cached on the device (invalidated by commit)
-    uint64_t tenant_tab_fp = 0;
-    int32_t tenant_tab_n = 0;
-    // snapshot on device
+    uint64_t generation = 0;
     DevBuf<Slot> d_slots, d_roots;
     DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
     DevBuf<uint8_t> d_rkind, d_tags;
-    // per-call workspace
+    FlatIndex flat;          // host copy (segs / rkind / tenant map / statistics; the uploaded arrays are dropped)
+    KVBlob committed;        // committed KV (route lookups)
+    size_t l2_window_bytes = 0;
+    int64_t device_bytes() const {
+        return (int64_t) (d_slots.bytes() + d_tags.bytes() + d_roots.bytes() + d_segs.bytes() + d_rkind.bytes() + d_pfxP.bytes() + d_pfxG.bytes());
+    }
+    ~Snapshot() {
+        cudaSetDevice(device);
+        d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release(); d_tags.release();
+    }
+};
+
+constexpr int MAX_CHUNKS = 8;
+
+// Everything ONE match in flight needs: streams, device scratch, pinned result buffers. A workspace is leased from the
+// index's pool for the duration of a call AND of the result it produced (the result's arrays live in it), so concurrent
+// matches on one handle never share a buffer. Returned to the pool by bfq_result_free / bfq_device_result_release.
+struct Workspace {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, work_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[MAX_CHUNKS] = {};
+    cudaEvent_t evk[2] = {nullptr, nullptr};
+    // resolved tenant table of the previous call on this workspace (reused when the same list comes again)
+    uint64_t tab_generation = ~0ull;
+    std::vector<uint8_t> tab_blob;
+    std::vector<int64_t> tab_off;
+    std::vector<int32_t> tab_caps;
+    int32_t tab_n = -1;
+    bool any_cap = true;
+    DevBuf<int32_t> d_tenant_tab;   // root | maxP | maxG, 3 x n_tenants
+    PinBuf<int32_t> h_tenant_tab;
+    // per-call device buffers
     DevBuf<uint8_t> d_topics;
     DevBuf<int64_t> d_topic_off;
-    DevBuf<int32_t> d_topic_tenant, d_tenant_tab;   // tenant_tab = root | maxP | maxG, 3 x n_tenants
+    DevBuf<int32_t> d_topic_tenant;
     DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept, d_defer;
     DevBuf<uint2> d_ranges, d_scratch, d_ranges_c;
     DevBuf<uint8_t> d_scan_tmp;
     DevBuf<uint32_t> d_cnt, d_new_begin;
-    DevBuf<uint32_t> d_ord_keys, d_ord_vals;   // locality ordering of tier 0 (launch_order): 2n each
-    DevBuf<uint8_t> d_ord_tmp;
-    size_t ord_tmp_stride = 0;                 // bytes of sort scratch per sub-batch
-    int64_t order_min = 32768;                 // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
+    // locality order + dedup (launch_order): per compute-stream slot (two sub-batches can be in flight)
+    DevBuf<uint32_t> d_ord_keys, d_leader, d_order;
+    DevBuf<unsigned long long> d_hash_tab;   // 2 x hash_stride
+    DevBuf<uint32_t> d_hist;                 // 2 x hist_stride (histogram + block totals/prefixes + ticket)
+    size_t hash_stride = 0, hist_stride = 0;
     DevBuf<uint3> d_throttled;
     DevBuf<unsigned long long> d_counters;
     PinBuf<unsigned long long> h_counters;
-    PinBuf<int32_t> h_tenant_tab;
-    // pinned result buffers (leased to the bfq_result of the latest bfq_match)
+    DevBuf<unsigned long long> d_exp_counts;
+    // pinned result buffers
     PinBuf<uint32_t> h_span_begin, h_span_count, h_route_count;
     PinBuf<uint2> h_ranges;
     PinBuf<uint3> h_throttled;
-    // statistics
-    int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0;
-    // last device result (for bfq_expand_device)
-    int64_t last_n_topics = 0, last_n_flagged = 0;
-    int32_t last_n_tenants = 0;
-    const int32_t* last_topic_tenant = nullptr;   // device pointer of the latest bfq_match_device call
-    DevBuf<unsigned long long> d_exp_counts;
 
-    ~bfq_index() {
+    cudaError_t init(int dev) {
+        device = dev;
+        cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+        for (auto& w : work_stream)
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking);
+        for (auto& x : ev)
+            if (e == cudaSuccess) e = cudaEventCreate(&x);
+        for (auto& x : evk)
+            if (e == cudaSuccess) e = cudaEventCreate(&x);
+        for (auto& x : ev_h2d)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+        return e;
+    }
+    ~Workspace() {
         cudaSetDevice(device);
-        d_slots.release(); d_roots.release(); d_segs.release(); d_pfxP.release(); d_pfxG.release(); d_rkind.release(); d_tags.release();
-        d_topics.release(); d_topic_off.release(); d_topic_tenant.release(); d_tenant_tab.release();
+        d_tenant_tab.release(); h_tenant_tab.release();
+        d_topics.release(); d_topic_off.release(); d_topic_tenant.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
-        d_flagged.release(); d_kept.release(); d_defer.release(); d_exp_counts.release(); d_ranges_c.release(); d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release(); d_throttled.release();
-        d_counters.release(); h_counters.release(); h_tenant_tab.release();
+        d_flagged.release(); d_kept.release(); d_defer.release(); d_exp_counts.release(); d_ranges_c.release();
+        d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release();
+        d_throttled.release(); d_counters.release(); h_counters.release();
+        d_ord_keys.release(); d_leader.release(); d_order.release(); d_hash_tab.release(); d_hist.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : evk) if (e) cudaEventDestroy(e);
@@ -152,49 +176,123 @@ struct bfq_index {
     }
 };
 
-namespace {
-
-// Shared core of bfq_match / bfq_match_device: topics are on the device; runs tier 1, tier 2 and caps.
-struct CoreOut {
-    int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0, n_deferred = 0;
-    uint64_t want_dyn = 0, want_thr = 0;
-    int64_t chunk_throttled[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+struct bfq_result {
+    bfq_index* owner = nullptr;
+    std::shared_ptr<Snapshot> snap;      // the snapshot the match ran on (ranks resolve against it)
+    Workspace* ws = nullptr;             // leased: the arrays below live in its pinned buffers
+    int64_t n_topics = 0, n_ranges = 0, n_throttled = 0;
+    const uint32_t *span_begin = nullptr, *span_count = nullptr, *route_count = nullptr;
+    const bfq_range* ranges = nullptr;
+    const bfq_throttled* throttled = nullptr;
+    double ms[4] = {0, 0, 0, 0};
 };
 
-int32_t resolve_tenants(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+struct bfq_index {
+    int device = 0;
+    std::mutex mu;         // current snapshot pointer, workspace pool, statistics
+    std::mutex stage_mu;   // staging area: reset / load / apply and the (long) host-side rebuild of commit
+    Staging staging;
+    std::shared_ptr<Snapshot> snap;
+    uint64_t next_generation = 1;
+    std::vector<Workspace*> pool;        // idle workspaces
+    int64_t order_min = 32768;           // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
+    bool dedup = true;                   // BFQ_DEDUP=0: match duplicates of a (tenant, topic) pair separately
+    double last_kernel_ms = 0;
+    int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0, duplicate_topics = 0;
+
+    ~bfq_index() {
+        cudaSetDevice(device);
+        for (Workspace* w : pool) delete w;
+    }
+};
+
+namespace {
+
+constexpr size_t POOL_KEEP = 4;   // idle workspaces kept for reuse; more are freed when they come back
+
+int32_t acquire(bfq_index* h, std::shared_ptr<Snapshot>* snap, Workspace** ws, const char* who) {
+    Workspace* w = nullptr;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (!h->snap) return fail(BFQ_E_STATE, std::string(who) + " before the first bfq_index_commit");
+        *snap = h->snap;
+        if (!h->pool.empty()) {
+            w = h->pool.back();
+            h->pool.pop_back();
+        }
+    }
+    if (!w) {
+        w = new Workspace();
+        cudaError_t e = w->init(h->device);
+        if (e != cudaSuccess) {
+            delete w;
+            return fail(BFQ_E_CUDA, std::string("workspace: ") + cudaGetErrorString(e));
+        }
+    }
+    *ws = w;
+    return BFQ_OK;
+}
+
+void give_back(bfq_index* h, Workspace* w) {
+    if (!w) return;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (h->pool.size() < POOL_KEEP) {
+            h->pool.push_back(w);
+            return;
+        }
+    }
+    cudaSetDevice(h->device);
+    delete w;
+}
+
+struct CoreOut {
+    int64_t n_ranges = 0, n_throttled = 0, n_overflow = 0, n_flagged = 0, n_launches = 0, n_deferred = 0, n_leaders = 0;
+    uint64_t want_dyn = 0, want_thr = 0;
+    int64_t chunk_throttled[MAX_CHUNKS] = {};
+};
+
+// tenant ids -> root ordinals of this snapshot + caps, uploaded to the workspace (skipped when the previous call on this
+// workspace carried the same list against the same snapshot: compared byte for byte, not by fingerprint)
+int32_t resolve_tenants(Workspace* w, const Snapshot* s, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                         const int32_t* max_p, const int32_t* max_g, cudaStream_t stream) {
     if (n_tenants < 0) return fail(BFQ_E_INVALID, "n_tenants < 0");
     if (n_tenants >= (1 << 30)) return fail(BFQ_E_RANGE, "more than 2^30 tenants in one batch");   // bit 30 of the lane's tenant word is a flag
     const size_t nt = (size_t) std::max(n_tenants, 1);
-    // the same tenant list + caps usually accompany every batch: fingerprint it and keep the device table
-    uint64_t fp = 0xcbf29ce484222325ull ^ (uint64_t) n_tenants;
-    auto mixin = [&](const void* p, size_t n) {
-        const uint8_t* b = (const uint8_t*) p;
-        for (size_t i = 0; i < n; i++) fp = (fp ^ b[i]) * 0x100000001b3ull;
-    };
-    if (n_tenants > 0) {
-        mixin(tenant_off, (size_t) (n_tenants + 1) * sizeof(int64_t));
-        mixin(tenants + tenant_off[0], (size_t) (tenant_off[n_tenants] - tenant_off[0]));
-        if (max_p) mixin(max_p, (size_t) n_tenants * 4);
-        if (max_g) mixin(max_g, (size_t) n_tenants * 4);
-        fp ^= (max_p ? 1u : 0u) | (max_g ? 2u : 0u);
+    const size_t blob_n = n_tenants ? (size_t) (tenant_off[n_tenants] - tenant_off[0]) : 0;
+    bool same = w->tab_generation == s->generation && w->tab_n == n_tenants && w->tab_blob.size() == blob_n;
+    if (same && n_tenants > 0) {
+        same = memcmp(w->tab_blob.data(), tenants + tenant_off[0], blob_n) == 0;
+        for (int32_t i = 0; same && i <= n_tenants; i++) same = w->tab_off[i] == tenant_off[i] - tenant_off[0];
+        for (int32_t i = 0; same && i < n_tenants; i++)
+            same = w->tab_caps[i] == (max_p ? max_p[i] : 0x7FFFFFFF) && w->tab_caps[nt + i] == (max_g ? max_g[i] : 0x7FFFFFFF);
     }
-    if (h->tenant_tab_valid && h->tenant_tab_fp == fp && h->tenant_tab_n == n_tenants) return BFQ_OK;
-    CUDA_TRY(cudaStreamSynchronize(stream));   // the pinned staging table may still be in flight
-    CUDA_TRY(h->h_tenant_tab.reserve(3 * nt));
-    CUDA_TRY(h->d_tenant_tab.reserve(3 * nt));
+    if (same) return BFQ_OK;
+    CUDA_TRY(w->h_tenant_tab.reserve(3 * nt));
+    CUDA_TRY(w->d_tenant_tab.reserve(3 * nt));
+    w->tab_blob.assign(tenants ? tenants + (n_tenants ? tenant_off[0] : 0) : nullptr, tenants ? tenants + (n_tenants ? tenant_off[0] : 0) + blob_n : nullptr);
+    w->tab_off.resize(nt + 1);
+    w->tab_caps.assign(2 * nt, 0x7FFFFFFF);
+    bool any_cap = false;
     for (int32_t i = 0; i < n_tenants; i++) {
         std::string t((const char*) tenants + tenant_off[i], (size_t) (tenant_off[i + 1] - tenant_off[i]));
-        auto it = h->flat.tenant_ordinal.find(t);
-        h->h_tenant_tab.p[i] = it == h->flat.tenant_ordinal.end() ? -1 : (int32_t) it->second;
-        h->h_tenant_tab.p[nt + i] = max_p ? max_p[i] : 0x7FFFFFFF;
-        h->h_tenant_tab.p[2 * nt + i] = max_g ? max_g[i] : 0x7FFFFFFF;
+        auto it = s->flat.tenant_ordinal.find(t);
+        const int32_t mp = max_p ? max_p[i] : 0x7FFFFFFF, mg = max_g ? max_g[i] : 0x7FFFFFFF;
+        w->h_tenant_tab.p[i] = it == s->flat.tenant_ordinal.end() ? -1 : (int32_t) it->second;
+        w->h_tenant_tab.p[nt + i] = mp;
+        w->h_tenant_tab.p[2 * nt + i] = mg;
+        w->tab_off[i] = tenant_off[i] - tenant_off[0];
+        w->tab_caps[i] = mp;
+        w->tab_caps[nt + i] = mg;
+        any_cap = any_cap || mp != 0x7FFFFFFF || mg != 0x7FFFFFFF;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_tenant_tab.p, h->h_tenant_tab.p, 3 * nt * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));   // other streams of this handle read the table without an event
-    h->tenant_tab_valid = true;
-    h->tenant_tab_fp = fp;
-    h->tenant_tab_n = n_tenants;
+    if (n_tenants > 0) w->tab_off[n_tenants] = tenant_off[n_tenants] - tenant_off[0];
+    // the workspace is idle between calls, so nothing reads the pinned staging table while it is rewritten; the streams
+    // that read the device table are ordered behind this copy (same stream, or through the H2D events of the host path)
+    CUDA_TRY(cudaMemcpyAsync(w->d_tenant_tab.p, w->h_tenant_tab.p, 3 * nt * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    w->tab_generation = s->generation;
+    w->tab_n = n_tenants;
+    w->any_cap = any_cap;
     return BFQ_OK;
 }
 
@@ -207,221 +305,371 @@ struct SubBatch {
     uint64_t dyn_off = 0, dyn_cap = 0;     // slice of ranges[n_total * INLINE_RANGES ...) for tiers 1/2
     uint64_t thr_off = 0, thr_cap = 0;     // slice of the throttled list
 };
-constexpr int MAX_CHUNKS = 8;
-constexpr int32_t BFQ_RETRY_GROW = -100;   // internal: a slice was too small, redo the batch un-chunked with bigger buffers
+constexpr int32_t BFQ_RETRY_GROW = -100;
+// words of one ordering scratch slot: histogram | block totals | block prefixes | ticket (kept 256-byte aligned)
+size_t hist_words(size_t buckets) { return (buckets + 2 * (buckets / 4096) + 64 + 63) / 64 * 64; }   // internal: a slice was too small, redo the batch un-chunked with bigger buffers
 
-int32_t prepare_workspace(bfq_index* h, int64_t n, int n_chunks) {
+int32_t prepare_workspace(bfq_index* h, Workspace* w, int64_t n, int n_chunks, int32_t n_tenants) {
     const size_t nn = (size_t) std::max<int64_t>(n, 1);
     if (n >= (int64_t) 0x3FFFFFFF) return fail(BFQ_E_INVALID, "too many topics in one batch");
-    CUDA_TRY(h->d_span_begin.reserve(nn));
-    CUDA_TRY(h->d_span_count.reserve(nn));
-    CUDA_TRY(h->d_route_count.reserve(nn));
-    CUDA_TRY(h->d_overflow.reserve(nn));
-    CUDA_TRY(h->d_flagged.reserve(nn));
-    CUDA_TRY(h->d_kept.reserve(nn));
-    CUDA_TRY(h->d_defer.reserve(nn));
-    CUDA_TRY(h->d_counters.reserve(CTR_COUNT * MAX_CHUNKS));
-    CUDA_TRY(h->h_counters.reserve(CTR_COUNT * MAX_CHUNKS));
+    CUDA_TRY(w->d_span_begin.reserve(nn));
+    CUDA_TRY(w->d_span_count.reserve(nn));
+    CUDA_TRY(w->d_route_count.reserve(nn));
+    CUDA_TRY(w->d_overflow.reserve(nn));
+    CUDA_TRY(w->d_flagged.reserve(nn));
+    CUDA_TRY(w->d_kept.reserve(nn));
+    CUDA_TRY(w->d_defer.reserve(nn));
+    CUDA_TRY(w->d_counters.reserve(CTR_COUNT * MAX_CHUNKS));
+    CUDA_TRY(w->h_counters.reserve(CTR_COUNT * MAX_CHUNKS));
     // ranges[0, n * INLINE_RANGES): tier-0 inline slots; the rest: cursor-allocated region of tiers 1 and 2
     const uint64_t dyn_base = (uint64_t) n * INLINE_RANGES;
     if (dyn_base >= 0xF0000000ull) return fail(BFQ_E_RANGE, "batch too large for 32-bit range indices; split the batch");
     const size_t min_dyn = std::max<size_t>((size_t) n_chunks << 18, nn);
-    if (h->d_ranges.cap < dyn_base + min_dyn) CUDA_TRY(h->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, min_dyn))));
-    if (n >= h->order_min) {
-        CUDA_TRY(h->d_ord_keys.reserve(2 * nn));
-        CUDA_TRY(h->d_ord_vals.reserve(2 * nn));
-        OrderParams q{};
-        q.n_topics = n;
-        size_t tb = 0;
-        CUDA_TRY(launch_order(q, nullptr, &tb, nullptr));
-        tb = (tb + 255) / 256 * 256;
-        h->ord_tmp_stride = std::max(h->ord_tmp_stride, tb);
-        CUDA_TRY(h->d_ord_tmp.reserve(h->ord_tmp_stride * MAX_CHUNKS));
+    if (w->d_ranges.cap < dyn_base + min_dyn) CUDA_TRY(w->d_ranges.reserve((size_t) (dyn_base + std::max<size_t>(1 << 20, min_dyn))));
+    const int64_t per_chunk = (n + n_chunks - 1) / n_chunks + 1;
+    if (per_chunk >= h->order_min) {
+        CUDA_TRY(w->d_ord_keys.reserve(nn));
+        CUDA_TRY(w->d_leader.reserve(nn));
+        CUDA_TRY(w->d_order.reserve(nn));
+        const size_t buckets = order_hist_buckets(per_chunk, n_tenants);
+        const size_t hist_stride = hist_words(buckets);
+        const size_t hash_stride = order_hash_entries(per_chunk);
+        if (hist_stride > w->hist_stride) {
+            CUDA_TRY(w->d_hist.reserve(2 * hist_stride));
+            w->hist_stride = hist_stride;
+        }
+        if (hash_stride > w->hash_stride) {
+            CUDA_TRY(w->d_hash_tab.reserve(2 * hash_stride));
+            w->hash_stride = hash_stride;
+        }
     }
-    if (h->d_throttled.cap < ((size_t) n_chunks << 14)) CUDA_TRY(h->d_throttled.reserve(std::max<size_t>(1 << 16, (size_t) n_chunks << 14)));
+    if (w->d_throttled.cap < ((size_t) n_chunks << 14)) CUDA_TRY(w->d_throttled.reserve(std::max<size_t>(1 << 16, (size_t) n_chunks << 14)));
     return BFQ_OK;
 }
 
-SubBatch whole_batch(bfq_index* h, int64_t n) {
+SubBatch whole_batch(Workspace* w, int64_t n) {
     SubBatch sb;
     sb.begin = 0;
     sb.n = sb.n_total = n;
-    sb.dyn_cap = h->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
-    sb.thr_cap = h->d_throttled.cap;
+    sb.dyn_cap = w->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
+    sb.thr_cap = w->d_throttled.cap;
     return sb;
 }
 
-// Runs tier 0 + tier 1 (+ tier 2, + caps) for one sub-batch on `stream`; blocks until its kernels have finished.
-int32_t match_core(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
-                   int32_t n_tenants, cudaStream_t stream, const SubBatch& sb, CoreOut* out) {
-    const size_t nt = (size_t) std::max(n_tenants, 1);
-    const int64_t n = sb.n, b = sb.begin;
+struct CoreCtx {
+    bfq_index* h;
+    Workspace* w;
+    const Snapshot* s;
+    const uint8_t* d_topics;
+    const int64_t* d_topic_off;
+    const int32_t* d_topic_tenant;
+    int32_t n_tenants;
+    cudaStream_t stream;
+};
+
+MatchParams core_params(const CoreCtx& c, const SubBatch& sb) {
+    Workspace* w = c.w;
+    const size_t nt = (size_t) std::max(c.n_tenants, 1);
+    const int64_t b = sb.begin;
     MatchParams p{};
-    p.slots = h->d_slots.p;
-    p.roots = h->d_roots.p;
-    p.tags = reinterpret_cast<const uint4*>(h->d_tags.p);
-    p.n_blocks = h->flat.n_blocks;
-    p.topics = d_topics;
-    p.topic_off = d_topic_off + b;
-    p.topic_tenant = d_topic_tenant + b;
-    p.tenant_root = h->d_tenant_tab.p;
-    p.max_pfanout = h->d_tenant_tab.p + nt;
-    p.max_gfanout = h->d_tenant_tab.p + 2 * nt;
-    p.n_tenants = n_tenants;
-    p.n_topics = n;
-    p.span_begin = h->d_span_begin.p + b;
-    p.span_count = h->d_span_count.p + b;
-    p.route_count = h->d_route_count.p + b;
-    p.overflow_list = h->d_overflow.p + b;
-    p.defer_list = h->d_defer.p + b;
-    p.flagged_list = h->d_flagged.p + b;
-    unsigned long long* d_ctr = h->d_counters.p + (size_t) sb.chunk * CTR_COUNT;
-    unsigned long long* hc = h->h_counters.p + (size_t) sb.chunk * CTR_COUNT;
-    p.counters = d_ctr;
+    p.slots = c.s->d_slots.p;
+    p.roots = c.s->d_roots.p;
+    p.tags = reinterpret_cast<const uint4*>(c.s->d_tags.p);
+    p.n_blocks = c.s->flat.n_blocks;
+    p.topics = c.d_topics;
+    p.topic_off = c.d_topic_off + b;
+    p.topic_tenant = c.d_topic_tenant + b;
+    p.tenant_root = w->d_tenant_tab.p;
+    p.max_pfanout = w->d_tenant_tab.p + nt;
+    p.max_gfanout = w->d_tenant_tab.p + 2 * nt;
+    p.n_tenants = c.n_tenants;
+    p.n_topics = sb.n;
+    p.span_begin = w->d_span_begin.p + b;
+    p.span_count = w->d_span_count.p + b;
+    p.route_count = w->d_route_count.p + b;
+    p.overflow_list = w->d_overflow.p + b;
+    p.defer_list = w->d_defer.p + b;
+    p.flagged_list = w->d_flagged.p + b;
+    p.counters = w->d_counters.p + (size_t) sb.chunk * CTR_COUNT;
     // range indices are relative to the sub-batch's first inline slot
-    p.ranges = h->d_ranges.p + (uint64_t) b * INLINE_RANGES;
+    p.ranges = w->d_ranges.p + (uint64_t) b * INLINE_RANGES;
     p.dyn_base = (uint64_t) (sb.n_total - b) * INLINE_RANGES + sb.dyn_off;
     p.ranges_cap = p.dyn_base + sb.dyn_cap;
+    return p;
+}
 
-    if (h->l2_window_bytes > 0) {
+CapsParams caps_params(const CoreCtx& c, const SubBatch& sb, const MatchParams& p) {
+    CapsParams q{};
+    q.flagged_list = p.flagged_list;
+    q.topic_tenant = p.topic_tenant;
+    q.max_pfanout = p.max_pfanout;
+    q.max_gfanout = p.max_gfanout;
+    q.span_begin = p.span_begin;
+    q.span_count = p.span_count;
+    q.ranges = p.ranges;
+    q.segs = c.s->d_segs.p;
+    q.rkind = c.s->d_rkind.p;
+    q.pfx_persistent = c.s->d_pfxP.p;
+    q.pfx_group = c.s->d_pfxG.p;
+    q.kept_count = c.w->d_kept.p + sb.begin;
+    q.counters = p.counters;
+    q.throttled = c.w->d_throttled.p + sb.thr_off;
+    q.throttled_cap = sb.thr_cap;
+    q.topic_base = (uint32_t) sb.begin;
+    return q;
+}
+
+bool wants_order(const CoreCtx& c, const SubBatch& sb) {
+    return sb.n >= c.h->order_min && c.w->d_order.cap >= (size_t) (sb.begin + sb.n) && c.w->hist_stride > 0 &&
+           c.w->hist_stride >= hist_words(order_hist_buckets(sb.n, c.n_tenants)) && c.w->hash_stride >= order_hash_entries(sb.n);
+}
+
+// Enqueues one sub-batch on c.stream WITHOUT synchronising: [dedup + locality order] -> tier 0 -> tier 1 -> [followers] ->
+// [caps], every count read on the device. The host looks at the counters only in finish_core.
+int32_t enqueue_core(const CoreCtx& c, const SubBatch& sb, CoreOut* out) {
+    Workspace* w = c.w;
+    cudaStream_t stream = c.stream;
+    const int64_t n = sb.n, b = sb.begin;
+    MatchParams p = core_params(c, sb);
+    if (c.s->l2_window_bytes > 0) {
         cudaStreamAttrValue attr{};
-        attr.accessPolicyWindow.base_ptr = h->d_tags.p;
-        attr.accessPolicyWindow.num_bytes = h->l2_window_bytes;
+        attr.accessPolicyWindow.base_ptr = c.s->d_tags.p;
+        attr.accessPolicyWindow.num_bytes = c.s->l2_window_bytes;
         attr.accessPolicyWindow.hitRatio = 1.0f;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
         cudaGetLastError();
     }
-    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), stream));
-    p.work_list = nullptr;
-    p.n_work = 0;
-    p.order = nullptr;
-    if (n >= h->order_min && h->d_ord_keys.cap >= 2 * (size_t) (b + n) && h->ord_tmp_stride > 0) {
-        // group the topics by tenant and leading levels so that neighbouring lanes walk the same part of the trie
+    CUDA_TRY(cudaMemsetAsync(p.counters, 0, CTR_COUNT * sizeof(unsigned long long), stream));
+    bool ordered = false, dedup = false;
+    if (wants_order(c, sb)) {
+        // group the topics by tenant and leading levels so that neighbouring lanes walk the same part of the trie, and
+        // match every distinct (tenant, topic) pair once
+        const int slot = sb.chunk & 1;
+        const size_t buckets = order_hist_buckets(n, c.n_tenants);
         OrderParams q{};
         q.n_topics = n;
-        q.topics = d_topics;
+        q.topics = c.d_topics;
         q.topic_off = p.topic_off;
         q.topic_tenant = p.topic_tenant;
-        q.n_tenants = n_tenants;
-        q.keys = h->d_ord_keys.p + 2 * b;
-        q.vals = h->d_ord_vals.p + 2 * b;
-        size_t tb = h->ord_tmp_stride;
-        CUDA_TRY(launch_order(q, h->d_ord_tmp.p + (size_t) sb.chunk * h->ord_tmp_stride, &tb, stream));
-        p.order = q.vals + n;
-        out->n_launches += 1;   // order_keys_kernel (the radix-sort passes are cub's)
+        q.n_tenants = c.n_tenants;
+        q.keys = w->d_ord_keys.p + b;
+        q.leader = w->d_leader.p + b;
+        q.order = w->d_order.p + b;
+        q.hash_tab = w->d_hash_tab.p + (size_t) slot * w->hash_stride;
+        q.hash_mask = order_hash_entries(n) - 1;
+        q.hist = w->d_hist.p + (size_t) slot * w->hist_stride;
+        q.blk_tot = q.hist + buckets;
+        q.blk_pfx = q.blk_tot + buckets / 4096;
+        q.ticket = q.blk_pfx + buckets / 4096;
+        q.hist_bits = 0;
+        while (((size_t) 1 << q.hist_bits) < buckets) q.hist_bits++;
+        q.dedup = c.h->dedup ? 1 : 0;
+        q.counters = p.counters;
+        CUDA_TRY(cudaMemsetAsync(q.hist, 0, hist_words(buckets) * sizeof(uint32_t), stream));
+        if (q.dedup) CUDA_TRY(cudaMemsetAsync(q.hash_tab, 0xFF, ((size_t) q.hash_mask + 1) * sizeof(unsigned long long), stream));
+        CUDA_TRY(launch_order(q, stream));
+        p.order = q.order;
+        p.order_count = p.counters + CTR_NLEAD;
+        out->n_launches += 3;
+        ordered = true;
+        dedup = q.dedup != 0;
     }
     if (n > 0) {
-        // tier 0 (one lane per topic) over the whole sub-batch, then tier 1 (one warp per topic) over whatever tier 0
-        // deferred — its count is read on the device, so both launches go out back to back
-        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(h->evk[0], stream));
+        // tier 0 (one lane per topic), then tier 1 (one warp per topic) over whatever tier 0 deferred — its count is read
+        // on the device, so both launches go out back to back
+        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(w->evk[0], stream));
         launch_match_lanes(p, stream);
-        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(h->evk[1], stream));
+        if (sb.chunk == 0) CUDA_TRY(cudaEventRecord(w->evk[1], stream));
         p.work_list = p.defer_list;
         p.n_work = -1;
         launch_match(p, false, 0, stream);
         out->n_launches += 2;
+        if (ordered && dedup) {
+            FinalizeParams f{};
+            f.n_topics = n;
+            f.leader = w->d_leader.p + b;
+            f.span_begin = p.span_begin;
+            f.span_count = p.span_count;
+            f.route_count = p.route_count;
+            f.flagged_list = p.flagged_list;
+            f.counters = p.counters;
+            f.second_pass = 0;
+            launch_finalize(f, stream);
+            out->n_launches += 1;
+        }
+        if (w->any_cap) {
+            CapsParams q = caps_params(c, sb, p);
+            q.n_flagged = -1;
+            launch_caps(q, stream);
+            out->n_launches += 2;
+        }
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    return BFQ_OK;
+}
+
+int32_t copy_counters(const CoreCtx& c, const SubBatch& sb) {
+    CUDA_TRY(cudaMemcpyAsync(c.w->h_counters.p + (size_t) sb.chunk * CTR_COUNT, c.w->d_counters.p + (size_t) sb.chunk * CTR_COUNT,
+                             CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    return BFQ_OK;
+}
+
+// Waits for the sub-batch and handles what the optimistic enqueue could not: topics that need tier 2 (frontier / range
+// overflow of tier 1: scratch sized from the index statistics, then the followers and caps passes once more for what
+// tier 2 added) and slices that turned out too small (BFQ_RETRY_GROW). *reran = tier 2 changed the spans.
+int32_t finish_core(const CoreCtx& c, const SubBatch& sb, CoreOut* out, bool* reran) {
+    Workspace* w = c.w;
+    cudaStream_t stream = c.stream;
+    unsigned long long* hc = w->h_counters.p + (size_t) sb.chunk * CTR_COUNT;
+    if (reran) *reran = false;
     CUDA_TRY(cudaStreamSynchronize(stream));
     out->n_overflow += (int64_t) hc[CTR_OVERFLOW];
     out->n_deferred += (int64_t) hc[CTR_DEFER];
-    if (n > 0 && sb.chunk == 0) {
-        float kms = 0;
-        cudaEventElapsedTime(&kms, h->evk[0], h->evk[1]);
-        h->last_kernel_ms = kms;
-    }
     if (hc[CTR_OVERFLOW] > 0) {
-        // ---- tier 2: per-warp global scratch sized from the index statistics (exact upper bounds)
-        const uint64_t capF = (uint64_t) h->flat.max_nodes_per_depth + 2;
-        const uint64_t capR = 2 * ((uint64_t) h->flat.max_tenant_nodes + 2) + 2;
+        MatchParams p = core_params(c, sb);
+        const uint64_t capF = (uint64_t) c.s->flat.max_nodes_per_depth + 2;
+        const uint64_t capR = 2 * ((uint64_t) c.s->flat.max_tenant_nodes + 2) + 2;
         const uint64_t per_warp = 4 * capF + capR;   // uint2 units: two frontier buffers of uint4 entries + ranges
         uint64_t warps = std::min<uint64_t>(hc[CTR_OVERFLOW], std::max<uint64_t>(8, (1ull << 31) / (per_warp * sizeof(uint2))));
         warps = std::min<uint64_t>(warps, 148 * 8);
         warps = (warps + 7) / 8 * 8;
-        CUDA_TRY(cudaDeviceSynchronize());   // the scratch is shared: no other sub-batch may be in tier 2 (or running at all)
-        CUDA_TRY(h->d_scratch.reserve((size_t) (warps * per_warp)));
-        p.scratch = h->d_scratch.p;
+        if (w->d_scratch.cap < (size_t) (warps * per_warp)) {
+            CUDA_TRY(cudaDeviceSynchronize());   // the other compute stream of this workspace may be in tier 2 on the old scratch
+            CUDA_TRY(w->d_scratch.reserve((size_t) (warps * per_warp)));
+        }
+        p.scratch = w->d_scratch.p;
         p.scratch_frontier_cap = capF;
         p.scratch_ranges_cap = capR;
         p.work_list = p.overflow_list;
         p.n_work = (int64_t) hc[CTR_OVERFLOW];
         launch_match(p, true, (int) warps, stream);
         out->n_launches++;
+        if (w->hist_stride > 0 && c.h->dedup && wants_order(c, sb)) {
+            FinalizeParams f{};
+            f.n_topics = sb.n;
+            f.leader = w->d_leader.p + sb.begin;
+            f.span_begin = p.span_begin;
+            f.span_count = p.span_count;
+            f.route_count = p.route_count;
+            f.flagged_list = p.flagged_list;
+            f.counters = p.counters;
+            f.second_pass = 1;
+            launch_finalize(f, stream);
+            out->n_launches++;
+        }
+        if (w->any_cap) {
+            CapsParams q = caps_params(c, sb, p);
+            q.n_flagged = -1;
+            launch_caps(q, stream);
+            out->n_launches += 2;
+        }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        int32_t rc = copy_counters(c, sb);
+        if (rc != BFQ_OK) return rc;
         CUDA_TRY(cudaStreamSynchronize(stream));
         if (hc[CTR_ERROR] != 0) return fail(BFQ_E_STATE, "tier-2 scratch exhausted (index statistics inconsistent)");
+        if (reran) *reran = true;
     }
     if (hc[CTR_RANGES] > sb.dyn_cap) {
         out->want_dyn = std::max<uint64_t>(out->want_dyn, hc[CTR_RANGES]);
         return BFQ_RETRY_GROW;
     }
+    if (hc[CTR_THROTTLED] > sb.thr_cap) {
+        out->want_thr = std::max<uint64_t>(out->want_thr, hc[CTR_THROTTLED]);
+        return BFQ_RETRY_GROW;
+    }
     out->n_ranges += (int64_t) hc[CTR_RANGES];
     out->n_flagged += (int64_t) hc[CTR_FLAGGED];
-    if (hc[CTR_FLAGGED] > 0) {
-        CapsParams c{};
-        c.flagged_list = p.flagged_list;
-        c.n_flagged = (int64_t) hc[CTR_FLAGGED];
-        c.topic_tenant = p.topic_tenant;
-        c.max_pfanout = p.max_pfanout;
-        c.max_gfanout = p.max_gfanout;
-        c.span_begin = p.span_begin;
-        c.span_count = p.span_count;
-        c.ranges = p.ranges;
-        c.segs = h->d_segs.p;
-        c.rkind = h->d_rkind.p;
-        c.pfx_persistent = h->d_pfxP.p;
-        c.pfx_group = h->d_pfxG.p;
-        c.kept_count = h->d_kept.p + b;
-        c.counters = d_ctr;
-        c.throttled = h->d_throttled.p + sb.thr_off;
-        c.throttled_cap = sb.thr_cap;
-        c.topic_base = (uint32_t) b;
-        launch_caps(c, stream);
-        out->n_launches++;
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if (hc[CTR_THROTTLED] > sb.thr_cap) {
-            out->want_thr = std::max<uint64_t>(out->want_thr, hc[CTR_THROTTLED]);
-            return BFQ_RETRY_GROW;
-        }
-        out->chunk_throttled[sb.chunk] = (int64_t) hc[CTR_THROTTLED];
-        out->n_throttled += (int64_t) hc[CTR_THROTTLED];
-    }
+    out->n_leaders += wants_order(c, sb) ? (int64_t) hc[CTR_NLEAD] : sb.n;
+    out->chunk_throttled[sb.chunk] = (int64_t) hc[CTR_THROTTLED];
+    out->n_throttled += (int64_t) hc[CTR_THROTTLED];
     return BFQ_OK;
 }
 
-// un-chunked match with automatic buffer growth (device path, and the host path's fallback)
-int32_t match_whole(bfq_index* h, const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant, int64_t n,
-                    int32_t n_tenants, cudaStream_t stream, CoreOut* out) {
-    for (int attempt = 0; attempt < 8; attempt++) {
-        int32_t rc = prepare_workspace(h, n, 1);
-        if (rc != BFQ_OK) return rc;
-        *out = CoreOut();
-        rc = match_core(h, d_topics, d_topic_off, d_topic_tenant, n_tenants, stream, whole_batch(h, n), out);
-        if (rc != BFQ_RETRY_GROW) {
-            if (rc == BFQ_OK) {
-                h->launches += out->n_launches;
-                h->overflow_topics += out->n_overflow;
-                h->deferred_topics += out->n_deferred;
-                h->flagged_topics += out->n_flagged;
-                h->last_n_topics = n;
-            }
-            return rc;
-        }
-        CUDA_TRY(cudaDeviceSynchronize());
-        if (out->want_dyn) {
-            const size_t want = (size_t) ((uint64_t) n * INLINE_RANGES + out->want_dyn + out->want_dyn / 4 + 1024);
-            if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
-            CUDA_TRY(h->d_ranges.reserve(want));
-        }
-        if (out->want_thr) CUDA_TRY(h->d_throttled.reserve((size_t) (out->want_thr + out->want_thr / 4 + 1024)));
+void add_stats(bfq_index* h, const CoreOut& co, int64_t n, double kernel_ms) {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->launches += co.n_launches;
+    h->overflow_topics += co.n_overflow;
+    h->deferred_topics += co.n_deferred;
+    h->flagged_topics += co.n_flagged;
+    h->duplicate_topics += n - co.n_leaders;
+    if (kernel_ms >= 0) h->last_kernel_ms = kernel_ms;
+}
+
+// grows the buffers a retry asked for (the caller has synchronised the device)
+int32_t grow_for_retry(Workspace* w, const CoreOut& co, int64_t n, int C) {
+    if (co.want_dyn) {
+        const size_t want = (size_t) ((uint64_t) n * INLINE_RANGES + (co.want_dyn + co.want_dyn / 4 + 1024) * (uint64_t) C);
+        if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
+        CUDA_TRY(w->d_ranges.reserve(want));
     }
-    return fail(BFQ_E_STATE, "buffer sizing did not converge");
+    if (co.want_thr) CUDA_TRY(w->d_throttled.reserve((size_t) ((co.want_thr + co.want_thr / 4 + 1024) * (uint64_t) C)));
+    return BFQ_OK;
+}
+
+// A device-side match in flight (bfq_match_device_async .. bfq_device_result_wait .. bfq_device_result_release)
+struct DeviceLease {
+    bfq_index* h = nullptr;
+    std::shared_ptr<Snapshot> snap;
+    Workspace* ws = nullptr;
+    CoreCtx ctx{};
+    int64_t n = 0;
+    bool done = false;
+    int32_t rc = BFQ_OK;
+    CoreOut co;
+    double tier0_ms = 0;
+};
+
+void fill_device_result(const DeviceLease* L, bfq_device_result* out) {
+    Workspace* w = L->ws;
+    out->d_span_begin = w->d_span_begin.p;
+    out->d_span_count = w->d_span_count.p;
+    out->d_route_count = w->d_route_count.p;
+    out->d_ranges = reinterpret_cast<const bfq_range*>(w->d_ranges.p);
+    out->d_throttled = reinterpret_cast<const bfq_throttled*>(w->d_throttled.p);
+    out->n_ranges = (int64_t) ((uint64_t) L->n * INLINE_RANGES) + L->co.n_ranges;   // extent of the sparse range array
+    out->n_throttled = L->co.n_throttled;
+    out->n_routes = -1;
+    out->n_overflow_topics = L->co.n_overflow;
+    out->n_flagged_topics = L->co.n_flagged;
+    out->n_launches = L->co.n_launches;
+    out->n_distinct_topics = L->co.n_leaders;
+    out->tier0_ms = L->tier0_ms;
+    out->generation = L->snap->generation;
+}
+
+int32_t device_enqueue(DeviceLease* L) {
+    int32_t rc = prepare_workspace(L->h, L->ws, L->n, 1, L->ctx.n_tenants);
+    if (rc != BFQ_OK) return rc;
+    L->co = CoreOut();
+    const SubBatch sb = whole_batch(L->ws, L->n);
+    rc = enqueue_core(L->ctx, sb, &L->co);
+    if (rc != BFQ_OK) return rc;
+    return copy_counters(L->ctx, sb);
+}
+
+int32_t device_wait(DeviceLease* L) {
+    if (L->done) return L->rc;
+    L->done = true;
+    for (int attempt = 0;; attempt++) {
+        if (attempt == 8) return L->rc = fail(BFQ_E_STATE, "buffer sizing did not converge");
+        int32_t rc = finish_core(L->ctx, whole_batch(L->ws, L->n), &L->co, nullptr);
+        if (rc == BFQ_OK) break;
+        if (rc != BFQ_RETRY_GROW) return L->rc = rc;
+        if (cudaDeviceSynchronize() != cudaSuccess) return L->rc = fail(BFQ_E_CUDA, "cudaDeviceSynchronize");
+        rc = grow_for_retry(L->ws, L->co, L->n, 1);
+        if (rc == BFQ_OK) rc = device_enqueue(L);
+        if (rc != BFQ_OK) return L->rc = rc;
+    }
+    if (L->n > 0) {
+        float kms = 0;
+        cudaEventElapsedTime(&kms, L->ws->evk[0], L->ws->evk[1]);
+        L->tier0_ms = kms;
+    }
+    add_stats(L->h, L->co, L->n, L->n > 0 ? L->tier0_ms : -1.0);
+    return L->rc = BFQ_OK;
 }
 
 int64_t emit_bytes(const std::string& s, uint8_t* out, int64_t cap) {
@@ -445,24 +693,11 @@ int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
     CUDA_TRY(cudaSetDevice(device_ordinal));
     auto* h = new bfq_index();
     h->device = device_ordinal;
-    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    for (auto& ev : h->ev)
-        if (e == cudaSuccess) e = cudaEventCreate(&ev);
-    for (auto& ev : h->evk)
-        if (e == cudaSuccess) e = cudaEventCreate(&ev);
-    for (auto& ev : h->ev_h2d)
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for (auto& w : h->work_stream)
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking);
-    if (e != cudaSuccess) {
-        delete h;
-        return fail(BFQ_E_CUDA, cudaGetErrorString(e));
-    }
     if (const char* eo = getenv("BFQ_ORDER")) {   // experiment switch: 0 = never order, N > 0 = order batches of >= N topics
         const long long v = atoll(eo);
         h->order_min = v <= 0 ? (int64_t) 1 << 62 : (int64_t) v;
     }
+    if (const char* ed = getenv("BFQ_DEDUP")) h->dedup = atoi(ed) != 0;   // experiment switch
     *out = h;
     return BFQ_OK;
 }
@@ -480,6 +715,8 @@ int32_t bfq_index_load(bfq_index* h, const uint8_t* keys, const int64_t* key_off
                        const int64_t* val_off, int64_t n) {
     if (!h || n < 0 || (n > 0 && (!keys || !key_off || !vals || !val_off))) return fail(BFQ_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> g(h->stage_mu);
+    if (n > 0 && h->staging.has_delta())
+        return fail(BFQ_E_STATE, "bfq_index_load after bfq_index_apply: commit (or reset) the staged delta first");
     std::string err;
     if (!h->staging.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
     return BFQ_OK;
@@ -489,13 +726,21 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
                         const int64_t* add_val_off, int64_t n_add, const uint8_t* del_keys, const int64_t* del_key_off,
                         int64_t n_del) {
     if (!h || n_add < 0 || n_del < 0) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->stage_mu);
+    if (n_add > 0 && (!add_keys || !add_key_off || !add_vals || !add_val_off)) return fail(BFQ_E_INVALID, "NULL add set");
+    if (n_del > 0 && (!del_keys || !del_key_off)) return fail(BFQ_E_INVALID, "NULL delete set");
+    // all or nothing: every add key is decoded before the staging area is touched
     for (int64_t i = 0; i < n_add; i++) {
-        sv k((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i]));
+        if (add_key_off[i + 1] < add_key_off[i] || add_val_off[i + 1] < add_val_off[i]) return fail(BFQ_E_INVALID, "offsets not ascending");
         DecodedKey d;
-        if (!decode_route_key(k, &d)) return fail(BFQ_E_INVALID, "undecodable route key in add set");
-        h->staging.upsert(k, sv((const char*) add_vals + add_val_off[i], (size_t) (add_val_off[i + 1] - add_val_off[i])));
+        if (!decode_route_key(sv((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i])), &d))
+            return fail(BFQ_E_INVALID, "undecodable route key in add set (nothing was staged)");
     }
+    for (int64_t i = 0; i < n_del; i++)
+        if (del_key_off[i + 1] < del_key_off[i]) return fail(BFQ_E_INVALID, "offsets not ascending");
+    std::lock_guard<std::mutex> g(h->stage_mu);
+    for (int64_t i = 0; i < n_add; i++)
+        h->staging.upsert(sv((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i])),
+                          sv((const char*) add_vals + add_val_off[i], (size_t) (add_val_off[i + 1] - add_val_off[i])));
     for (int64_t i = 0; i < n_del; i++)
         h->staging.erase(sv((const char*) del_keys + del_key_off[i], (size_t) (del_key_off[i + 1] - del_key_off[i])));
     return BFQ_OK;
@@ -503,43 +748,32 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
 
 int32_t bfq_index_commit(bfq_index* h) {
     if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
-    // The rebuild runs under the staging lock only: matches keep running on the previous snapshot meanwhile and the
-    // new one is swapped in under the snapshot lock at the very end (two snapshots are resident for a moment).
+    // The rebuild runs under the staging lock only: matches keep running on the previous snapshot meanwhile; the new one
+    // is published by swapping one shared pointer. Matches and results in flight keep the old snapshot alive.
     std::lock_guard<std::mutex> gs(h->stage_mu);
     CUDA_TRY(cudaSetDevice(h->device));
     const KVBlob& kv = h->staging.materialize();
-    FlatIndex flat;
+    auto sn = std::make_shared<Snapshot>();
+    sn->device = h->device;
+    FlatIndex& flat = sn->flat;
     std::string err;
     if (!build_flat_index(kv, &flat, &err)) return fail(BFQ_E_INVALID, err);
-    DevBuf<Slot> n_slots, n_roots;
-    DevBuf<uint32_t> n_segs, n_pfxP, n_pfxG;
-    DevBuf<uint8_t> n_rkind, n_tags;
-    auto drop_new = [&]() { n_slots.release(); n_roots.release(); n_segs.release(); n_pfxP.release(); n_pfxG.release(); n_rkind.release(); n_tags.release(); };
-#define COMMIT_TRY(expr)                                                                            \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess) {                                                                    \
-            drop_new();                                                                             \
-            return fail(BFQ_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
-        }                                                                                           \
-    } while (0)
-    COMMIT_TRY(n_slots.reserve(flat.slots.size()));
-    COMMIT_TRY(n_tags.reserve(flat.tags.size()));
-    COMMIT_TRY(n_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
-    COMMIT_TRY(n_segs.reserve(flat.segs.size()));
-    COMMIT_TRY(n_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
-    COMMIT_TRY(n_pfxP.reserve(flat.pfx_persistent.size()));
-    COMMIT_TRY(n_pfxG.reserve(flat.pfx_group.size()));
-    COMMIT_TRY(cudaMemcpy(n_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
-    COMMIT_TRY(cudaMemcpy(n_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(sn->d_slots.reserve(flat.slots.size()));
+    CUDA_TRY(sn->d_tags.reserve(flat.tags.size()));
+    CUDA_TRY(sn->d_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
+    CUDA_TRY(sn->d_segs.reserve(flat.segs.size()));
+    CUDA_TRY(sn->d_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
+    CUDA_TRY(sn->d_pfxP.reserve(flat.pfx_persistent.size()));
+    CUDA_TRY(sn->d_pfxG.reserve(flat.pfx_group.size()));
+    CUDA_TRY(cudaMemcpy(sn->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sn->d_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
     if (!flat.roots.empty())
-        COMMIT_TRY(cudaMemcpy(n_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
-    COMMIT_TRY(cudaMemcpy(n_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(sn->d_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sn->d_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!flat.rkind.empty())
-        COMMIT_TRY(cudaMemcpy(n_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
-    COMMIT_TRY(cudaMemcpy(n_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    COMMIT_TRY(cudaMemcpy(n_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-#undef COMMIT_TRY
+        CUDA_TRY(cudaMemcpy(sn->d_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sn->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sn->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     // the host keeps only what it needs after the upload
     flat.slots.clear();
     flat.slots.shrink_to_fit();
@@ -550,48 +784,46 @@ int32_t bfq_index_commit(bfq_index* h) {
     flat.pfx_persistent.shrink_to_fit();
     flat.pfx_group.clear();
     flat.pfx_group.shrink_to_fit();
-    KVBlob committed = kv;   // snapshot of the raw KV for bfq_route_lookup
-    // ---- swap under the snapshot lock (no match is in flight while we hold it)
-    std::unique_lock<std::mutex> g(h->mu);
-    std::swap(h->d_slots, n_slots);
-    std::swap(h->d_tags, n_tags);
-    std::swap(h->d_roots, n_roots);
-    std::swap(h->d_segs, n_segs);
-    std::swap(h->d_rkind, n_rkind);
-    std::swap(h->d_pfxP, n_pfxP);
-    std::swap(h->d_pfxG, n_pfxG);
-    h->flat = std::move(flat);
-    h->committed = std::move(committed);
-    h->have_snapshot = true;
-    h->tenant_tab_valid = false;
-    // Keep the tag array resident in L2 (persisting access window): every lookup starts with a tag read and the
-    // array (~1/64 of the table) competes for L2 with the streaming slot traffic. BFQ_L2PERSIST=0 disables.
+    sn->committed = kv;   // snapshot of the raw KV for route lookups
+    // Keep the tag array of the (rare) global tag table resident in L2 (persisting access window). BFQ_L2PERSIST=0 disables.
     {
         const char* e = getenv("BFQ_L2PERSIST");
-        h->l2_window_bytes = 0;
         if (!e || atoi(e) != 0) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
-            size_t want = std::min<size_t>(h->d_tags.bytes(), std::min<size_t>((size_t) max_persist, (size_t) max_window));
-            if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_window_bytes = want;
+            size_t want = std::min<size_t>(sn->d_tags.bytes(), std::min<size_t>((size_t) max_persist, (size_t) max_window));
+            if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) sn->l2_window_bytes = want;
             cudaGetLastError();
         }
     }
-    g.unlock();
-    drop_new();   // the previous snapshot's buffers
+    std::shared_ptr<Snapshot> old;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        sn->generation = h->next_generation++;
+        old = std::move(h->snap);
+        h->snap = std::move(sn);
+    }
+    old.reset();   // freed here unless a match or a result still pins it
+    return BFQ_OK;
+}
+
+int32_t bfq_index_generation(bfq_index* h, uint64_t* generation) {
+    if (!h || !generation) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *generation = h->snap ? h->snap->generation : 0;
     return BFQ_OK;
 }
 
 int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
     if (!h || !stats) return fail(BFQ_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> g(h->mu);
-    const int64_t dev_bytes = (int64_t) (h->d_slots.bytes() + h->d_tags.bytes() + h->d_roots.bytes() + h->d_segs.bytes() + h->d_rkind.bytes() +
-                                         h->d_pfxP.bytes() + h->d_pfxG.bytes());
-    const int64_t v[12] = {h->flat.n_routes, (int64_t) h->flat.tenant_ordinal.size(), h->flat.n_nodes, (int64_t) h->flat.n_slots,
-                           dev_bytes, h->flat.max_nodes_per_depth, h->launches, h->overflow_topics, h->flagged_topics,
-                           h->flat.n_multi, h->flat.n_cont_chunks, h->deferred_topics};
-    for (int32_t i = 0; i < n && i < 12; i++) stats[i] = v[i];
+    static const FlatIndex empty;
+    const FlatIndex& f = h->snap ? h->snap->flat : empty;
+    const int64_t v[13] = {f.n_routes, (int64_t) f.tenant_ordinal.size(), f.n_nodes, (int64_t) f.n_slots,
+                           h->snap ? h->snap->device_bytes() : 0, f.max_nodes_per_depth, h->launches, h->overflow_topics,
+                           h->flagged_topics, f.n_multi, f.n_cont_chunks, h->deferred_topics, h->duplicate_topics};
+    for (int32_t i = 0; i < n && i < 13; i++) stats[i] = v[i];
     return BFQ_OK;
 }
 
@@ -655,60 +887,95 @@ int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms) {
     return BFQ_OK;
 }
 
-int32_t bfq_route_lookup(bfq_index* h, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
-                         uint8_t* val_out, int64_t val_cap, int64_t* val_len) {
-    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
-    if (rank < 0 || rank >= h->committed.n()) return fail(BFQ_E_RANGE, "rank out of range");
-    sv k = h->committed.key(rank), v = h->committed.val(rank);
+namespace {
+int32_t lookup_in(const Snapshot* s, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len, uint8_t* val_out,
+                  int64_t val_cap, int64_t* val_len) {
+    if (rank < 0 || rank >= s->committed.n()) return fail(BFQ_E_RANGE, "rank out of range");
+    sv k = s->committed.key(rank), v = s->committed.val(rank);
     if (key_len) *key_len = (int64_t) k.size();
     if (val_len) *val_len = (int64_t) v.size();
     if (key_out && (int64_t) k.size() <= key_cap) memcpy(key_out, k.data(), k.size());
     if (val_out && (int64_t) v.size() <= val_cap) memcpy(val_out, v.data(), v.size());
     return BFQ_OK;
 }
+int32_t kinds_in(const Snapshot* s, const int64_t* ranks, int64_t n, uint8_t* kinds_out) {
+    for (int64_t i = 0; i < n; i++) {
+        if (ranks[i] < 0 || ranks[i] >= (int64_t) s->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
+        kinds_out[i] = s->flat.rkind[(size_t) ranks[i]];
+    }
+    return BFQ_OK;
+}
+std::shared_ptr<Snapshot> current(bfq_index* h) {
+    std::lock_guard<std::mutex> g(h->mu);
+    return h->snap;
+}
+}  // namespace
+
+int32_t bfq_route_lookup(bfq_index* h, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
+                         uint8_t* val_out, int64_t val_cap, int64_t* val_len) {
+    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
+    auto s = current(h);
+    if (!s) return fail(BFQ_E_STATE, "no committed snapshot");
+    return lookup_in(s.get(), rank, key_out, key_cap, key_len, val_out, val_cap, val_len);
+}
 
 int32_t bfq_route_kind(bfq_index* h, int64_t rank, int32_t* kind) {
     if (!h || !kind) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
-    if (rank < 0 || rank >= (int64_t) h->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
-    *kind = h->flat.rkind[(size_t) rank];
-    return BFQ_OK;
+    auto s = current(h);
+    if (!s) return fail(BFQ_E_STATE, "no committed snapshot");
+    uint8_t k = 0;
+    int32_t rc = kinds_in(s.get(), &rank, 1, &k);
+    if (rc == BFQ_OK) *kind = k;
+    return rc;
 }
 
 int32_t bfq_route_kinds(bfq_index* h, const int64_t* ranks, int64_t n, uint8_t* kinds_out) {
     if (!h || n < 0 || (n > 0 && (!ranks || !kinds_out))) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot) return fail(BFQ_E_STATE, "no committed snapshot");
-    for (int64_t i = 0; i < n; i++) {
-        if (ranks[i] < 0 || ranks[i] >= (int64_t) h->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
-        kinds_out[i] = h->flat.rkind[(size_t) ranks[i]];
-    }
-    return BFQ_OK;
+    auto s = current(h);
+    if (!s) return fail(BFQ_E_STATE, "no committed snapshot");
+    return kinds_in(s.get(), ranks, n, kinds_out);
 }
+
+int32_t bfq_result_route_lookup(const bfq_result* r, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
+                                uint8_t* val_out, int64_t val_cap, int64_t* val_len) {
+    if (!r || !r->snap) return fail(BFQ_E_INVALID, "result is NULL");
+    return lookup_in(r->snap.get(), rank, key_out, key_cap, key_len, val_out, val_cap, val_len);
+}
+int32_t bfq_result_route_kinds(const bfq_result* r, const int64_t* ranks, int64_t n, uint8_t* kinds_out) {
+    if (!r || !r->snap || n < 0 || (n > 0 && (!ranks || !kinds_out))) return fail(BFQ_E_INVALID, "bad argument");
+    return kinds_in(r->snap.get(), ranks, n, kinds_out);
+}
+uint64_t bfq_result_generation(const bfq_result* r) { return r && r->snap ? r->snap->generation : 0; }
 
 int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                   const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n,
                   const int32_t* max_pfanout, const int32_t* max_gfanout, bfq_result** out) {
     if (!h || !out || n < 0 || n_tenants < 0) return fail(BFQ_E_INVALID, "bad argument");
     if (n > 0 && (!topics || !topic_off || !topic_tenant || !tenants || !tenant_off)) return fail(BFQ_E_INVALID, "NULL input");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot) return fail(BFQ_E_STATE, "bfq_match before the first bfq_index_commit");
-    // topic_tenant[i] is range-checked on the device (an index outside [0, n_tenants) yields an empty result)
+    if (n_tenants > 0 && (!tenants || !tenant_off)) return fail(BFQ_E_INVALID, "NULL tenant list");
     CUDA_TRY(cudaSetDevice(h->device));
+    std::shared_ptr<Snapshot> snap;
+    Workspace* w = nullptr;
+    int32_t rc = acquire(h, &snap, &w, "bfq_match");
+    if (rc != BFQ_OK) return rc;
+    // the workspace goes back to the pool on every error path; on success the result keeps it
+    struct Lease {
+        bfq_index* h;
+        Workspace* w;
+        ~Lease() { if (w) { cudaSetDevice(h->device); cudaDeviceSynchronize(); give_back(h, w); } }
+    } lease{h, w};
+    // topic_tenant[i] is range-checked on the device (an index outside [0, n_tenants) yields an empty result)
     auto t0 = std::chrono::steady_clock::now();
     const size_t nn = (size_t) std::max<int64_t>(n, 1);
     const int64_t blob_e = n ? topic_off[n] : 0;
-    CUDA_TRY(h->d_topics.reserve((size_t) std::max<int64_t>(blob_e, 1) + 64));
-    CUDA_TRY(h->d_topic_off.reserve(nn + 1));
-    CUDA_TRY(h->d_topic_tenant.reserve(nn));
-    CUDA_TRY(h->d_cnt.reserve(nn));
-    CUDA_TRY(h->d_new_begin.reserve(nn));
-    CUDA_TRY(h->h_span_begin.reserve(nn));
-    CUDA_TRY(h->h_span_count.reserve(nn));
-    CUDA_TRY(h->h_route_count.reserve(nn));
+    CUDA_TRY(w->d_topics.reserve((size_t) std::max<int64_t>(blob_e, 1) + 64));
+    CUDA_TRY(w->d_topic_off.reserve(nn + 1));
+    CUDA_TRY(w->d_topic_tenant.reserve(nn));
+    CUDA_TRY(w->d_cnt.reserve(nn));
+    CUDA_TRY(w->d_new_begin.reserve(nn));
+    CUDA_TRY(w->h_span_begin.reserve(nn));
+    CUDA_TRY(w->h_span_count.reserve(nn));
+    CUDA_TRY(w->h_route_count.reserve(nn));
 
     // Large batches are cut into sub-batches that flow through three streams: all H2D copies on one, the kernels +
     // compaction + D2H of consecutive sub-batches alternating on two others, so the copy of sub-batch c+1 and the
@@ -716,43 +983,45 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     int C = n >= (1 << 17) ? 4 : 1;
     CoreOut co;
     int64_t rbase = 0, tbase = 0;
+    double kernel_ms = -1;
     for (int attempt = 0;; attempt++) {
         if (attempt == 8) return fail(BFQ_E_STATE, "buffer sizing did not converge");
-        int32_t rc = prepare_workspace(h, n, C);
+        rc = prepare_workspace(h, w, n, C, n_tenants);
         if (rc != BFQ_OK) return rc;
-        CUDA_TRY(h->d_ranges_c.reserve(h->d_ranges.cap));
-        const uint64_t dyn_total = h->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
-        const uint64_t dyn_slice = dyn_total / (uint64_t) C, thr_slice = h->d_throttled.cap / (uint64_t) C;
+        CUDA_TRY(w->d_ranges_c.reserve(w->d_ranges.cap));
+        const uint64_t dyn_total = w->d_ranges.cap - (uint64_t) n * INLINE_RANGES;
+        const uint64_t dyn_slice = dyn_total / (uint64_t) C, thr_slice = w->d_throttled.cap / (uint64_t) C;
         size_t tmp_bytes = 0;
         {
             CompactParams q{};
             q.n_topics = (n + C - 1) / C + 1;
-            q.counts = h->d_cnt.p;
-            q.new_begin = h->d_new_begin.p;
-            CUDA_TRY(launch_compact(q, nullptr, &tmp_bytes, h->stream, 1));
-            CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes * 2 + 512));   // one scratch per compute stream
+            q.counts = w->d_cnt.p;
+            q.new_begin = w->d_new_begin.p;
+            CUDA_TRY(launch_compact(q, nullptr, &tmp_bytes, w->stream, 1));
+            CUDA_TRY(w->d_scan_tmp.reserve(tmp_bytes * 2 + 512));   // one scratch per compute stream
         }
         co = CoreOut();
         rbase = tbase = 0;
         // ---- H2D of every sub-batch, back to back on the copy stream
-        CUDA_TRY(cudaEventRecord(h->ev[0], h->copy_stream));
-        rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, h->copy_stream);
+        CUDA_TRY(cudaEventRecord(w->ev[0], w->copy_stream));
+        rc = resolve_tenants(w, snap.get(), tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, w->copy_stream);
         if (rc != BFQ_OK) return rc;
         int64_t bounds[MAX_CHUNKS + 1];
         for (int c = 0; c <= C; c++) bounds[c] = n * c / C;
         for (int c = 0; c < C && n > 0; c++) {
             const int64_t b = bounds[c], e = bounds[c + 1];
             const int64_t ob = topic_off[b], oe = topic_off[e];
-            CUDA_TRY(cudaMemcpyAsync(h->d_topic_off.p + b, topic_off + b, (size_t) (e - b + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->copy_stream));
-            CUDA_TRY(cudaMemcpyAsync(h->d_topic_tenant.p + b, topic_tenant + b, (size_t) (e - b) * sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
-            CUDA_TRY(cudaMemcpyAsync(h->d_topics.p + ob, topics + ob, (size_t) (oe - ob), cudaMemcpyHostToDevice, h->copy_stream));
-            CUDA_TRY(cudaEventRecord(h->ev_h2d[c], h->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(w->d_topic_off.p + b, topic_off + b, (size_t) (e - b + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, w->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(w->d_topic_tenant.p + b, topic_tenant + b, (size_t) (e - b) * sizeof(int32_t), cudaMemcpyHostToDevice, w->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(w->d_topics.p + ob, topics + ob, (size_t) (oe - ob), cudaMemcpyHostToDevice, w->copy_stream));
+            CUDA_TRY(cudaEventRecord(w->ev_h2d[c], w->copy_stream));
         }
-        CUDA_TRY(cudaEventRecord(h->ev[1], h->copy_stream));
+        CUDA_TRY(cudaEventRecord(w->ev[1], w->copy_stream));
+        if (n == 0) CUDA_TRY(cudaStreamSynchronize(w->copy_stream));
         bool retry = false;
         for (int c = 0; c < C && n > 0; c++) {
-            cudaStream_t st = C == 1 ? h->stream : h->work_stream[c & 1];
-            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[c], 0));
+            cudaStream_t st = C == 1 ? w->stream : w->work_stream[c & 1];
+            CUDA_TRY(cudaStreamWaitEvent(st, w->ev_h2d[c], 0));
             SubBatch sb;
             sb.begin = bounds[c];
             sb.n = bounds[c + 1] - bounds[c];
@@ -762,105 +1031,113 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
             sb.dyn_cap = dyn_slice;
             sb.thr_off = (uint64_t) c * thr_slice;
             sb.thr_cap = thr_slice;
-            rc = match_core(h, h->d_topics.p, h->d_topic_off.p, h->d_topic_tenant.p, n_tenants, st, sb, &co);
+            CoreCtx ctx{h, w, snap.get(), w->d_topics.p, w->d_topic_off.p, w->d_topic_tenant.p, n_tenants, st};
+            rc = enqueue_core(ctx, sb, &co);
+            if (rc != BFQ_OK) return rc;
+            // ---- compaction of this sub-batch: counts + scan + total (enqueued optimistically behind the match kernels),
+            // then, once the total is known on the host, the gather into the dense result position
+            unsigned long long* hc = w->h_counters.p + (size_t) c * CTR_COUNT;
+            const uint64_t region = (uint64_t) sb.begin * INLINE_RANGES + sb.dyn_off;   // this sub-batch's private slice of d_ranges_c
+            CompactParams cp{};
+            cp.n_topics = sb.n;
+            cp.span_begin = w->d_span_begin.p + sb.begin;
+            cp.span_count = w->d_span_count.p + sb.begin;
+            cp.ranges = w->d_ranges.p + (uint64_t) sb.begin * INLINE_RANGES;
+            cp.counts = w->d_cnt.p + sb.begin;
+            cp.new_begin = w->d_new_begin.p + sb.begin;
+            cp.ranges_out = w->d_ranges_c.p + region;
+            cp.ranges_out_cap = (uint64_t) sb.n * INLINE_RANGES + sb.dyn_cap;
+            cp.total_out = w->d_counters.p + (size_t) c * CTR_COUNT + CTR_ROUTES;
+            uint8_t* scan_tmp = w->d_scan_tmp.p + (size_t) (c & 1) * ((tmp_bytes + 256) / 256 * 256);
+            CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 1));
+            rc = copy_counters(ctx, sb);
+            if (rc != BFQ_OK) return rc;
+            bool reran = false;
+            rc = finish_core(ctx, sb, &co, &reran);
             if (rc == BFQ_RETRY_GROW) {
                 retry = true;
                 break;
             }
-            if (rc != BFQ_OK) {
-                cudaDeviceSynchronize();
-                return rc;
+            if (rc != BFQ_OK) return rc;
+            if (reran) {   // tier 2 changed spans: redo the counting pass
+                CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 1));
+                rc = copy_counters(ctx, sb);
+                if (rc != BFQ_OK) return rc;
+                CUDA_TRY(cudaStreamSynchronize(st));
+                co.n_launches += 3;
             }
-            // ---- compaction of this sub-batch: counts + scan + total, then gather into the dense result position
-            unsigned long long* d_ctr = h->d_counters.p + (size_t) c * CTR_COUNT;
-            unsigned long long* hc = h->h_counters.p + (size_t) c * CTR_COUNT;
-            const uint64_t region = (uint64_t) sb.begin * INLINE_RANGES + sb.dyn_off;   // this sub-batch's private slice of d_ranges_c
-            CompactParams cp{};
-            cp.n_topics = sb.n;
-            cp.span_begin = h->d_span_begin.p + sb.begin;
-            cp.span_count = h->d_span_count.p + sb.begin;
-            cp.ranges = h->d_ranges.p + (uint64_t) sb.begin * INLINE_RANGES;
-            cp.counts = h->d_cnt.p + sb.begin;
-            cp.new_begin = h->d_new_begin.p + sb.begin;
-            cp.ranges_out = h->d_ranges_c.p + region;
-            cp.ranges_out_cap = (uint64_t) sb.n * INLINE_RANGES + sb.dyn_cap;
-            cp.total_out = d_ctr + CTR_ROUTES;
-            uint8_t* scan_tmp = h->d_scan_tmp.p + (size_t) (c & 1) * (tmp_bytes + 256) / 256 * 256;
-            CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 1));
-            CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            if (c == 0) {
+                float kms = 0;
+                cudaEventElapsedTime(&kms, w->evk[0], w->evk[1]);
+                kernel_ms = kms;
+            }
             const int64_t total_c = (int64_t) hc[CTR_ROUTES], thr_c = co.chunk_throttled[c];
             // host result buffers grow by reallocation: wait for the copies in flight before moving them
-            if ((size_t) (rbase + total_c) > h->h_ranges.cap || (size_t) (tbase + thr_c) > h->h_throttled.cap) {
+            if ((size_t) (rbase + total_c) > w->h_ranges.cap || (size_t) (tbase + thr_c) > w->h_throttled.cap) {
                 CUDA_TRY(cudaDeviceSynchronize());
-                if ((size_t) (rbase + total_c) > h->h_ranges.cap) {
+                if ((size_t) (rbase + total_c) > w->h_ranges.cap) {
                     PinBuf<uint2> nb;
                     CUDA_TRY(nb.reserve((size_t) ((rbase + total_c) * (C - c > 1 ? 2 : 1) + (1 << 16))));
-                    if (rbase) memcpy(nb.p, h->h_ranges.p, (size_t) rbase * sizeof(uint2));
-                    h->h_ranges.release();
-                    h->h_ranges = nb;
+                    if (rbase) memcpy(nb.p, w->h_ranges.p, (size_t) rbase * sizeof(uint2));
+                    w->h_ranges.release();
+                    w->h_ranges = nb;
                 }
-                if ((size_t) (tbase + thr_c) > h->h_throttled.cap) {
+                if ((size_t) (tbase + thr_c) > w->h_throttled.cap) {
                     PinBuf<uint3> nb;
                     CUDA_TRY(nb.reserve((size_t) ((tbase + thr_c) * 2 + 1024)));
-                    if (tbase) memcpy(nb.p, h->h_throttled.p, (size_t) tbase * sizeof(uint3));
-                    h->h_throttled.release();
-                    h->h_throttled = nb;
+                    if (tbase) memcpy(nb.p, w->h_throttled.p, (size_t) tbase * sizeof(uint3));
+                    w->h_throttled.release();
+                    w->h_throttled = nb;
                 }
             }
             cp.out_base = (uint32_t) rbase;
             CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 2));
             co.n_launches += 4;
-            CUDA_TRY(cudaMemcpyAsync(h->h_span_begin.p + sb.begin, h->d_new_begin.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(h->h_span_count.p + sb.begin, h->d_cnt.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(h->h_route_count.p + sb.begin, h->d_route_count.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(w->h_span_begin.p + sb.begin, w->d_new_begin.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(w->h_span_count.p + sb.begin, w->d_cnt.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(w->h_route_count.p + sb.begin, w->d_route_count.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
             if (total_c > 0)
-                CUDA_TRY(cudaMemcpyAsync(h->h_ranges.p + rbase, h->d_ranges_c.p + region, (size_t) total_c * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(w->h_ranges.p + rbase, w->d_ranges_c.p + region, (size_t) total_c * sizeof(uint2), cudaMemcpyDeviceToHost, st));
             if (thr_c > 0)
-                CUDA_TRY(cudaMemcpyAsync(h->h_throttled.p + tbase, h->d_throttled.p + sb.thr_off, (size_t) thr_c * sizeof(uint3), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(w->h_throttled.p + tbase, w->d_throttled.p + sb.thr_off, (size_t) thr_c * sizeof(uint3), cudaMemcpyDeviceToHost, st));
             rbase += total_c;
             tbase += thr_c;
         }
         if (!retry) break;
         // a slice of the range / throttled buffers was too small: grow them and redo the batch un-chunked
         CUDA_TRY(cudaDeviceSynchronize());
-        if (co.want_dyn) {
-            const size_t want = (size_t) ((uint64_t) n * INLINE_RANGES + (co.want_dyn + co.want_dyn / 4 + 1024) * (uint64_t) C);
-            if (want >= 0xFFFFFFF0ull) return fail(BFQ_E_RANGE, "more than 2^32 matched ranges in one batch; split the batch");
-            CUDA_TRY(h->d_ranges.reserve(want));
-        }
-        if (co.want_thr) CUDA_TRY(h->d_throttled.reserve((size_t) ((co.want_thr + co.want_thr / 4 + 1024) * (uint64_t) C)));
+        rc = grow_for_retry(w, co, n, C);
+        if (rc != BFQ_OK) return rc;
         C = 1;
     }
-    CUDA_TRY(cudaStreamSynchronize(h->work_stream[0]));
-    CUDA_TRY(cudaStreamSynchronize(h->work_stream[1]));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
-    h->launches += co.n_launches;
-    h->overflow_topics += co.n_overflow;
-    h->deferred_topics += co.n_deferred;
-    h->flagged_topics += co.n_flagged;
-    h->last_n_topics = n;
+    CUDA_TRY(cudaStreamSynchronize(w->work_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(w->work_stream[1]));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->copy_stream));
+    add_stats(h, co, n, kernel_ms);
     co.n_ranges = rbase;
     co.n_throttled = tbase;
     if (co.n_throttled > 1) {
-        uint3* th = h->h_throttled.p;
+        uint3* th = w->h_throttled.p;
         std::sort(th, th + co.n_throttled, [](const uint3& a, const uint3& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
     }
     auto* r = new bfq_result();
     r->owner = h;
+    r->snap = std::move(snap);
+    r->ws = w;
+    lease.w = nullptr;   // the result holds the workspace from here on
     r->n_topics = n;
     r->n_ranges = co.n_ranges;
     r->n_throttled = co.n_throttled;
-    r->span_begin = h->h_span_begin.p;
-    r->span_count = h->h_span_count.p;
-    r->route_count = h->h_route_count.p;
-    r->ranges = reinterpret_cast<const bfq_range*>(h->h_ranges.p);
-    r->throttled = reinterpret_cast<const bfq_throttled*>(h->h_throttled.p);
+    r->span_begin = w->h_span_begin.p;
+    r->span_count = w->h_span_count.p;
+    r->route_count = w->h_route_count.p;
+    r->ranges = reinterpret_cast<const bfq_range*>(w->h_ranges.p);
+    r->throttled = reinterpret_cast<const bfq_throttled*>(w->h_throttled.p);
     float a = 0;
-    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&a, w->ev[0], w->ev[1]);
     r->ms[0] = a;                       // H2D stream busy time (overlapped with the kernels of earlier sub-batches)
-    r->ms[1] = h->last_kernel_ms;       // tier-0 kernel of the first sub-batch
+    r->ms[1] = kernel_ms < 0 ? 0 : kernel_ms;   // tier-0 kernel of the first sub-batch
     r->ms[2] = (double) C;              // number of sub-batches
     r->ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = r;
@@ -882,36 +1159,60 @@ const bfq_throttled* bfq_result_throttled(const bfq_result* r, int64_t* n_thrott
 
 int64_t bfq_result_expand(const bfq_result* r, int64_t* offsets, int64_t* ranks, int64_t rank_cap) {
     if (!r || !offsets) return BFQ_E_INVALID;
-    const std::vector<uint32_t>& segs = r->owner->flat.segs;
-    int64_t total = 0;
-    int64_t ti = 0;  // cursor into the (topic, rank)-sorted throttled list
-    std::vector<int64_t> tmp;
-    for (int64_t t = 0; t < r->n_topics; t++) {
-        offsets[t] = total;
-        tmp.clear();
-        const uint32_t b = r->span_begin[t], c = r->span_count[t];
-        for (uint32_t j = 0; j < c; j++) {
-            const bfq_range rg = r->ranges[b + j];
-            if (rg.count & RANGE_MULTI) {
-                const uint32_t nseg = segs[2 * (size_t) rg.first];
-                for (uint32_t s = 0; s < nseg; s++) {
-                    const uint32_t f = segs[2 * ((size_t) rg.first + 1 + s)], n = segs[2 * ((size_t) rg.first + 1 + s) + 1];
-                    for (uint32_t x = 0; x < n; x++) tmp.push_back((int64_t) f + x);
-                }
-            } else {
-                for (uint32_t x = 0; x < rg.count; x++) tmp.push_back((int64_t) rg.first + x);
-            }
-        }
-        std::sort(tmp.begin(), tmp.end());
-        while (ti < r->n_throttled && r->throttled[ti].topic < (uint32_t) t) ti++;
-        for (int64_t x : tmp) {
-            while (ti < r->n_throttled && r->throttled[ti].topic == (uint32_t) t && (int64_t) r->throttled[ti].rank < x) ti++;
-            if (ti < r->n_throttled && r->throttled[ti].topic == (uint32_t) t && (int64_t) r->throttled[ti].rank == x) continue;
-            if (ranks && total < rank_cap) ranks[total] = x;
-            total++;
+    const std::vector<uint32_t>& segs = r->snap->flat.segs;   // the snapshot the ranges were produced from
+    const int64_t n = r->n_topics;
+    // throttled[] is sorted by (topic, rank): first entry of every topic
+    std::vector<int64_t> thr_begin((size_t) n + 1, r->n_throttled);
+    {
+        int64_t ti = 0;
+        for (int64_t t = 0; t <= n; t++) {
+            while (ti < r->n_throttled && (int64_t) r->throttled[ti].topic < t) ti++;
+            thr_begin[(size_t) t] = ti;
         }
     }
-    offsets[r->n_topics] = total;
+    // pass 1: survivors per topic -> offsets (route_count counts every matched route, a multi-segment range included)
+    int64_t total = 0;
+    for (int64_t t = 0; t < n; t++) {
+        offsets[t] = total;
+        total += (int64_t) r->route_count[t] - (thr_begin[(size_t) t + 1] - thr_begin[(size_t) t]);
+    }
+    offsets[n] = total;
+    if (!ranks || total > rank_cap) return total;
+    // pass 2: topics are independent -> all host threads
+    auto fill = [&](int64_t t_lo, int64_t t_hi) {
+        std::vector<int64_t> tmp;
+        for (int64_t t = t_lo; t < t_hi; t++) {
+            tmp.clear();
+            const uint32_t b = r->span_begin[t], c = r->span_count[t];
+            for (uint32_t j = 0; j < c; j++) {
+                const bfq_range rg = r->ranges[b + j];
+                if (rg.count & RANGE_MULTI) {
+                    const uint32_t nseg = segs[2 * (size_t) rg.first];
+                    for (uint32_t s = 0; s < nseg; s++) {
+                        const uint32_t f = segs[2 * ((size_t) rg.first + 1 + s)], m = segs[2 * ((size_t) rg.first + 1 + s) + 1];
+                        for (uint32_t x = 0; x < m; x++) tmp.push_back((int64_t) f + x);
+                    }
+                } else {
+                    for (uint32_t x = 0; x < rg.count; x++) tmp.push_back((int64_t) rg.first + x);
+                }
+            }
+            if (c > 1) std::sort(tmp.begin(), tmp.end());
+            int64_t ti = thr_begin[(size_t) t], te = thr_begin[(size_t) t + 1], o = offsets[t];
+            for (int64_t x : tmp) {
+                while (ti < te && (int64_t) r->throttled[ti].rank < x) ti++;
+                if (ti < te && (int64_t) r->throttled[ti].rank == x) continue;
+                ranks[o++] = x;
+            }
+        }
+    };
+    const int64_t workers = std::max<int64_t>(1, std::min<int64_t>((int64_t) std::thread::hardware_concurrency(), std::min<int64_t>(64, total / 65536)));
+    if (workers <= 1) {
+        fill(0, n);
+    } else {
+        std::vector<std::thread> th;
+        for (int64_t k = 0; k < workers; k++) th.emplace_back(fill, n * k / workers, n * (k + 1) / workers);
+        for (auto& x : th) x.join();
+    }
     return total;
 }
 
@@ -920,81 +1221,120 @@ int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n) {
     for (int32_t i = 0; i < n && i < 4; i++) ms[i] = r->ms[i];
     return BFQ_OK;
 }
-void bfq_result_free(bfq_result* r) { delete r; }
+void bfq_result_free(bfq_result* r) {
+    if (!r) return;
+    give_back(r->owner, r->ws);
+    delete r;
+}
+
+int32_t bfq_match_device_async(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                               const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant, int64_t n,
+                               const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream, bfq_device_result* out) {
+    if (!h || !out || n < 0 || n_tenants < 0) return fail(BFQ_E_INVALID, "bad argument");
+    if (n_tenants > 0 && (!tenants || !tenant_off)) return fail(BFQ_E_INVALID, "NULL tenant list");
+    memset(out, 0, sizeof(*out));
+    CUDA_TRY(cudaSetDevice(h->device));
+    auto* L = new DeviceLease();
+    L->h = h;
+    int32_t rc = acquire(h, &L->snap, &L->ws, "bfq_match_device");
+    if (rc != BFQ_OK) {
+        delete L;
+        return rc;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    L->n = n;
+    L->ctx = CoreCtx{h, L->ws, L->snap.get(), d_topics, d_topic_off, d_topic_tenant, n_tenants, st};
+    rc = resolve_tenants(L->ws, L->snap.get(), tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
+    if (rc == BFQ_OK) rc = device_enqueue(L);
+    if (rc != BFQ_OK) {
+        cudaStreamSynchronize(st);
+        give_back(h, L->ws);
+        delete L;
+        return rc;
+    }
+    fill_device_result(L, out);
+    out->lease = L;
+    return BFQ_OK;
+}
+
+int32_t bfq_device_result_wait(bfq_device_result* out) {
+    if (!out || !out->lease) return fail(BFQ_E_INVALID, "no match in flight behind this result");
+    auto* L = static_cast<DeviceLease*>(out->lease);
+    if (cudaSetDevice(L->h->device) != cudaSuccess) return fail(BFQ_E_CUDA, "cudaSetDevice");
+    const int32_t rc = device_wait(L);
+    if (rc == BFQ_OK) fill_device_result(L, out);
+    return rc;
+}
+
+void bfq_device_result_release(bfq_device_result* out) {
+    if (!out || !out->lease) return;
+    auto* L = static_cast<DeviceLease*>(out->lease);
+    cudaSetDevice(L->h->device);
+    if (!L->done) cudaStreamSynchronize(L->ctx.stream);   // never hand a busy workspace back
+    give_back(L->h, L->ws);
+    delete L;
+    out->lease = nullptr;
+}
 
 int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                          const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant, int64_t n,
                          const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream, bfq_device_result* out) {
-    if (!h || !out || n < 0 || n_tenants < 0) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot) return fail(BFQ_E_STATE, "bfq_match_device before the first bfq_index_commit");
-    CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t) stream;
-    int32_t rc = resolve_tenants(h, tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, st);
+    int32_t rc = bfq_match_device_async(h, tenants, tenant_off, n_tenants, d_topics, d_topic_off, d_topic_tenant, n, max_pfanout,
+                                        max_gfanout, stream, out);
     if (rc != BFQ_OK) return rc;
-    CoreOut co;
-    rc = match_whole(h, d_topics, d_topic_off, d_topic_tenant, n, n_tenants, st, &co);
-    if (rc != BFQ_OK) return rc;
-    h->last_topic_tenant = d_topic_tenant;
-    h->last_n_tenants = n_tenants;
-    h->last_n_flagged = co.n_flagged;
-    out->d_span_begin = h->d_span_begin.p;
-    out->d_span_count = h->d_span_count.p;
-    out->d_route_count = h->d_route_count.p;
-    out->d_ranges = reinterpret_cast<const bfq_range*>(h->d_ranges.p);
-    out->d_throttled = reinterpret_cast<const bfq_throttled*>(h->d_throttled.p);
-    out->n_ranges = (int64_t) ((uint64_t) n * INLINE_RANGES) + co.n_ranges;   // extent of the sparse range array
-    out->n_throttled = co.n_throttled;
-    out->n_routes = -1;
-    out->n_overflow_topics = co.n_overflow;
-    out->n_flagged_topics = co.n_flagged;
-    out->n_launches = co.n_launches;
-    return BFQ_OK;
+    rc = bfq_device_result_wait(out);
+    if (rc != BFQ_OK) bfq_device_result_release(out);
+    return rc;
 }
 
-int32_t bfq_expand_device(bfq_index* h, int64_t n_topics, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap, void* stream,
+int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap, void* stream,
                           int64_t* n_ranks) {
-    if (!h || !d_offsets || n_topics < 0) return fail(BFQ_E_INVALID, "bad argument");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->have_snapshot || n_topics != h->last_n_topics || !h->last_topic_tenant)
-        return fail(BFQ_E_STATE, "bfq_expand_device must follow a bfq_match_device of the same batch");
+    if (!res || !res->lease || !d_offsets) return fail(BFQ_E_INVALID, "bad argument");
+    auto* L = static_cast<DeviceLease*>(res->lease);
+    if (!L->done || L->rc != BFQ_OK) return fail(BFQ_E_STATE, "bfq_expand_device needs a completed match (bfq_device_result_wait)");
+    bfq_index* h = L->h;
+    Workspace* w = L->ws;
+    const Snapshot* s = L->snap.get();
+    const int64_t n_topics = L->n;
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t) stream;
-    const size_t nt = (size_t) std::max(h->last_n_tenants, 1);
-    CUDA_TRY(h->d_exp_counts.reserve((size_t) n_topics + 1));
+    const size_t nt = (size_t) std::max(L->ctx.n_tenants, 1);
+    CUDA_TRY(w->d_exp_counts.reserve((size_t) n_topics + 1));
     ExpandParams p{};
     p.n_topics = n_topics;
-    p.span_begin = h->d_span_begin.p;
-    p.span_count = h->d_span_count.p;
-    p.route_count = h->d_route_count.p;
-    p.kept_count = h->d_kept.p;
-    p.ranges = h->d_ranges.p;
-    p.segs = h->d_segs.p;
-    p.counts = h->d_exp_counts.p;
+    p.span_begin = w->d_span_begin.p;
+    p.span_count = w->d_span_count.p;
+    p.route_count = w->d_route_count.p;
+    p.kept_count = w->d_kept.p;
+    p.ranges = w->d_ranges.p;
+    p.segs = s->d_segs.p;
+    p.counts = w->d_exp_counts.p;
     p.offsets = d_offsets;
     p.ranks = d_ranks;
     p.rank_cap = d_ranks ? rank_cap : 0;
-    p.flagged_list = h->d_flagged.p;
-    p.n_flagged = h->last_n_flagged;
-    p.topic_tenant = h->last_topic_tenant;
-    p.max_pfanout = h->d_tenant_tab.p + nt;
-    p.max_gfanout = h->d_tenant_tab.p + 2 * nt;
-    p.rkind = h->d_rkind.p;
-    p.pfx_persistent = h->d_pfxP.p;
-    p.pfx_group = h->d_pfxG.p;
+    p.flagged_list = w->d_flagged.p;
+    p.n_flagged = L->co.n_flagged;
+    p.topic_tenant = L->ctx.d_topic_tenant;
+    p.max_pfanout = w->d_tenant_tab.p + nt;
+    p.max_gfanout = w->d_tenant_tab.p + 2 * nt;
+    p.rkind = s->d_rkind.p;
+    p.pfx_persistent = s->d_pfxP.p;
+    p.pfx_group = s->d_pfxG.p;
     size_t tmp_bytes = 0;
     CUDA_TRY(launch_expand(p, nullptr, &tmp_bytes, st, 1));
-    CUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes + 256));
-    CUDA_TRY(launch_expand(p, h->d_scan_tmp.p, &tmp_bytes, st, 1));
+    CUDA_TRY(w->d_scan_tmp.reserve(tmp_bytes + 256));
+    CUDA_TRY(launch_expand(p, w->d_scan_tmp.p, &tmp_bytes, st, 1));
     long long total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, d_offsets + n_topics, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (n_ranks) *n_ranks = (int64_t) total;
-    h->launches += 2;
+    int64_t launches = 2;
     if (d_ranks && total <= rank_cap) {
-        CUDA_TRY(launch_expand(p, h->d_scan_tmp.p, &tmp_bytes, st, 2));
-        h->launches += 2;
+        CUDA_TRY(launch_expand(p, w->d_scan_tmp.p, &tmp_bytes, st, 2));
+        launches += 2;
     }
+    std::lock_guard<std::mutex> g(h->mu);
+    h->launches += launches;
     return BFQ_OK;
 }
 

@@ -59,6 +59,7 @@ public:
     const KVBlob& materialize();
     const KVBlob& base() const { return base_; }
     bool dirty() const { return dirty_; }
+    bool has_delta() const { return !delta_.empty(); }
 private:
     KVBlob base_;
     std::map<std::string, std::pair<bool, std::string>> delta_;  // key -> (present?, value)

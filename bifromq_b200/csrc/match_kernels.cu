@@ -17,7 +17,6 @@
 #include "match_kernels.cuh"
 #include "hash_probe.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -315,7 +314,8 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     LaneSmem& ws = sm[wid];
     const uint32_t lt_mask = (1u << lane) - 1;
-    const int64_t n = p.n_topics;
+    // in locality order only the batch's distinct topics are matched; their number was counted on the device
+    const int64_t n = (p.order && p.order_count) ? (int64_t) *p.order_count : p.n_topics;
 
     // warp-uniform work cursor over the current chunk [cstart, end)
     int64_t next = 0, end = 0, cstart = 0;
@@ -592,43 +592,106 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
 }
 
 // ------------------------------------------------------------------------------------------------ locality order
-// key = tenant index (T bits) | hash(level 0) | hash(level 1) | hash(level 2): equal leading levels => equal digits =>
-// adjacent after the sort. Hash collisions only merge groups. Topics with fewer levels use digit 0.
-__global__ void order_keys_kernel(const OrderParams q, int tenant_bits, int key_bits) {
+// topic-aligned 32-bit word k of the topic at byte address a (bytes 4k .. 4k+3; bytes at and after len are garbage and must be
+// masked by the caller). Only aligned words that hold at least one byte of the topic are read, so the reads stay inside
+// the 16-byte granules the blob occupies.
+struct TopicWords {
+    const uint32_t* base;
+    int sh, len, a3;
+    uint32_t lo;
+    int k;
+    __device__ __forceinline__ TopicWords(const uint8_t* topics, int64_t o, int len_) {
+        const uint64_t a = (uint64_t) (uintptr_t) topics + (uint64_t) o;
+        base = reinterpret_cast<const uint32_t*>(a & ~3ull);
+        a3 = (int) (a & 3);
+        sh = a3 * 8;
+        len = len_;
+        k = 0;
+        lo = len > 0 ? __ldg(base) : 0u;
+    }
+    // next word, masked to the topic's length (bytes past the end read as 0)
+    __device__ __forceinline__ uint32_t next() {
+        // aligned word k+1 starts at topic byte 4k + 4 - a3: it holds a topic byte iff that is < len
+        const uint32_t hi = (4 * k + 4 - a3 < len) ? __ldg(base + k + 1) : 0u;
+        uint32_t w = __funnelshift_r(lo, hi, sh);
+        const int rem = len - 4 * k;
+        if (rem < 4) w &= rem <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * rem));
+        lo = hi;
+        k++;
+        return w;
+    }
+};
+
+__device__ __forceinline__ bool same_topic(const uint8_t* topics, int64_t oa, int64_t ob, int len) {
+    TopicWords wa(topics, oa, len), wb(topics, ob, len);
+    for (int k = 0; 4 * k < len; k++)
+        if (wa.next() != wb.next()) return false;
+    return true;
+}
+
+constexpr int ORDER_WINDOW_WORDS = 10;   // the order key looks at the first 40 bytes: three levels of ordinary topics end well before
+
+// key = tenant index (T bits) | hash(level 0) | hash(levels 0..1) | hash(levels 0..2): equal leading levels => equal digits =>
+// one bucket. Hash collisions only merge groups. Topics with fewer levels use digit 0.
+__global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, int tenant_bits, int key_bits) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n_topics) return;
     const int64_t o = q.topic_off[i];
-    const int len = (int) max((int64_t) 0, min((int64_t) 40, q.topic_off[i + 1] - o));   // three levels of ordinary topics end well before this
+    const int64_t full_len = max((int64_t) 0, q.topic_off[i + 1] - o);
+    const int hlen = (int) min(full_len, (int64_t) 0x3FFFFFFF);
+    int tn = q.topic_tenant[i];
+    if (tn < 0 || tn >= q.n_tenants) tn = -1;   // all out-of-range tenant indices match nothing: one group
+    // ---- one pass over the topic's words: the first ORDER_WINDOW_WORDS feed the order key, all of them the 64-bit hash
+    uint32_t k[ORDER_WINDOW_WORDS];
+    uint64_t h = (uint64_t) (uint32_t) hlen * 0x9E3779B97F4A7C15ull + (uint64_t) (uint32_t) tn * 0xC2B2AE3D27D4EB4Full;
+    {
+        TopicWords tw(q.topics, o, hlen);
+#pragma unroll
+        for (int j = 0; j < ORDER_WINDOW_WORDS; j++) {
+            k[j] = 4 * j < hlen ? tw.next() : 0u;
+            h = (h ^ k[j]) * 0xFF51AFD7ED558CCDull;
+            h ^= h >> 32;
+        }
+        if (q.dedup)
+            for (int j = ORDER_WINDOW_WORDS; 4 * j < hlen; j++) {
+                h = (h ^ tw.next()) * 0xFF51AFD7ED558CCDull;
+                h ^= h >> 32;
+            }
+    }
+    // ---- de-duplication: first inserter leads
+    uint32_t lead = (uint32_t) i;
+    if (q.dedup) {
+        h = fmix64(h);
+        const unsigned long long mine = ((unsigned long long) (uint32_t) (h >> 32) << 32) | (unsigned long long) (uint32_t) i;
+        uint32_t slot = (uint32_t) h & q.hash_mask;
+        while (true) {
+            unsigned long long cur = q.hash_tab[slot];
+            if (cur == ~0ull) {
+                cur = atomicCAS(&q.hash_tab[slot], ~0ull, mine);
+                if (cur == ~0ull) break;   // claimed: this topic leads
+            }
+            if ((uint32_t) (cur >> 32) == (uint32_t) (h >> 32)) {
+                const uint32_t j = (uint32_t) cur;
+                int tj = q.topic_tenant[j];
+                if (tj < 0 || tj >= q.n_tenants) tj = -1;
+                const int64_t oj = q.topic_off[j];
+                if (tj == tn && q.topic_off[j + 1] - oj == full_len && full_len <= 0x3FFFFFFF && same_topic(q.topics, o, oj, hlen)) {
+                    lead = j;
+                    break;
+                }
+            }
+            slot = (slot + 1) & q.hash_mask;
+        }
+    }
+    q.leader[i] = lead;
+    if (lead != (uint32_t) i) return;
+    // ---- order key of a leader
+    const int len = min(hlen, 4 * ORDER_WINDOW_WORDS);
     const int rest = key_bits - tenant_bits;
     const int b0 = rest / 3 + (rest % 3 > 0), b1 = rest / 3 + (rest % 3 > 1), b2 = rest / 3;
-    int tn = q.topic_tenant[i];
-    if (tn < 0 || tn >= q.n_tenants) tn = 0;
-    // the first 40 bytes from four aligned 16-byte granules (as in the lane kernel: a granule is read only if it holds a
-    // byte of the topic), scanned in registers
-    const uint64_t a = (uint64_t) (uintptr_t) q.topics + (uint64_t) o;
-    const uint4* qp = reinterpret_cast<const uint4*>(a & ~15ull);
-    const int off = (int) (a & 15), need = off + len;
-    uint4 g[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) g[j] = need > 16 * j ? __ldg(qp + j) : make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t W[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
-                            g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
-    // topic-aligned words k[0..9] (word select + funnel shift), then a bitmap of the '/' positions (SWAR)
-    uint32_t k[10];
-    {
-        const bool by2 = off & 8, by1 = off & 4;
-        const int sh = (off & 3) * 8;
-        uint32_t Y[13], Z[11];
-#pragma unroll
-        for (int j = 0; j < 13; j++) Y[j] = by2 ? W[j + 2] : W[j];
-#pragma unroll
-        for (int j = 0; j < 11; j++) Z[j] = by1 ? Y[j + 1] : Y[j];
-#pragma unroll
-        for (int j = 0; j < 10; j++) k[j] = __funnelshift_r(Z[j], Z[j + 1], sh);
-    }
     uint64_t slashes = 0;
 #pragma unroll
-    for (int j = 0; j < 10; j++) slashes |= (uint64_t) nibble(match_bytes(k[j], 0x2F2F2F2Fu)) << (4 * j);
+    for (int j = 0; j < ORDER_WINDOW_WORDS; j++) slashes |= (uint64_t) nibble(match_bytes(k[j], 0x2F2F2F2Fu)) << (4 * j);
     slashes &= (1ull << len) - 1ull;   // len <= 40
     // ends of the first three levels (a level that runs to the end of the window ends at len); a digit is the hash of the
     // PREFIX up to that end, so equal leading levels give equal digits
@@ -642,18 +705,91 @@ __global__ void order_keys_kernel(const OrderParams q, int tenant_bits, int key_
     auto prefix_hash = [&](int nbytes) {
         const uint32_t C[10] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u,
                                 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u};
-        uint32_t h = (uint32_t) nbytes;
+        uint32_t hh = (uint32_t) nbytes;
 #pragma unroll
-        for (int j = 0; j < 10; j++)   // bytes at and after nbytes are cleared: 0xFFFFFFFF >> clamp(32(j+1) - 8 nbytes, 0, 32)
-            h += (k[j] & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (j + 1) - 8 * nbytes, 0))) * C[j];
-        return (h ^ (h >> 15)) * 0x9E3779B1u;
+        for (int j = 0; j < ORDER_WINDOW_WORDS; j++)   // bytes at and after nbytes are cleared: 0xFFFFFFFF >> clamp(32(j+1) - 8 nbytes, 0, 32)
+            hh += (k[j] & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (j + 1) - 8 * nbytes, 0))) * C[j];
+        return (hh ^ (hh >> 15)) * 0x9E3779B1u;
     };
-    uint32_t key = tenant_bits ? ((uint32_t) tn & ((1u << tenant_bits) - 1u)) : 0u;
+    uint32_t key = tenant_bits ? ((uint32_t) max(tn, 0) & ((1u << tenant_bits) - 1u)) : 0u;
     key = (key << b0) | (b0 ? prefix_hash(end[0]) >> (32 - b0) : 0u);
     key = (key << b1) | (b1 && lvl >= 1 ? prefix_hash(end[1]) >> (32 - b1) : 0u);
     key = (key << b2) | (b2 && lvl >= 2 ? prefix_hash(end[2]) >> (32 - b2) : 0u);
-    q.keys[i] = key;
-    q.vals[i] = (uint32_t) i;
+    const uint32_t bucket = key_bits > q.hist_bits ? key >> (key_bits - q.hist_bits) : key;
+    q.keys[i] = bucket;
+    atomicAdd(&q.hist[bucket], 1u);
+}
+
+// exclusive scan of the bucket histogram, in place: every block scans its 4096 counters and publishes its total; the last
+// block to finish (ticket) scans the <= 1024 block totals into blk_pfx and writes the grand total (= number of leaders)
+constexpr int SCAN_THREADS = 1024, SCAN_PER_BLOCK = 4096;
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t ws = warp_sums[lane];
+        uint32_t winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, winc, o);
+            if (lane >= o) winc += y;
+        }
+        warp_sums[lane] = winc - ws;
+        if (lane == 31) warp_sums[32] = winc;
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    const uint32_t r = warp_sums[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) order_scan_kernel(const OrderParams q) {
+    __shared__ uint32_t warp_sums[33];
+    __shared__ bool is_last;
+    uint4* hv = reinterpret_cast<uint4*>(q.hist + (size_t) blockIdx.x * SCAN_PER_BLOCK) + threadIdx.x;
+    const uint4 c = *hv;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(c.x + c.y + c.z + c.w, warp_sums, total);
+    *hv = make_uint4(ex, ex + c.x, ex + c.x + c.y, ex + c.x + c.y + c.z);
+    if (threadIdx.x == 0) {
+        q.blk_tot[blockIdx.x] = total;
+        __threadfence();
+        is_last = atomicAdd(q.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const uint32_t v = threadIdx.x < gridDim.x ? *((volatile uint32_t*) q.blk_tot + threadIdx.x) : 0u;
+    const uint32_t pfx = block_exclusive_scan(v, warp_sums, total);
+    if (threadIdx.x < gridDim.x) q.blk_pfx[threadIdx.x] = pfx;
+    if (threadIdx.x == 0) q.counters[CTR_NLEAD] = total;
+}
+__global__ void __launch_bounds__(256) order_scatter_kernel(const OrderParams q) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n_topics || q.leader[i] != (uint32_t) i) return;
+    const uint32_t b = q.keys[i];
+    q.order[q.blk_pfx[b / SCAN_PER_BLOCK] + atomicAdd(&q.hist[b], 1u)] = (uint32_t) i;
+}
+
+// followers take their leader's span; spans index the sparse range array, so the ranges themselves are shared
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_topics) return;
+    const uint32_t l = p.leader[i];
+    if (l == (uint32_t) i) return;
+    if (p.second_pass && p.span_count[i] != SPAN_OVERFLOW) return;
+    const uint32_t sc = p.span_count[l];
+    p.span_begin[i] = p.span_begin[l];
+    p.span_count[i] = sc;
+    p.route_count[i] = p.route_count[l];
+    if (sc & SPAN_FLAGGED) p.flagged_list[atomicAdd(&p.counters[CTR_FLAGGED], 1ull)] = (uint32_t) i;
 }
 
 // ------------------------------------------------------------------------------------------------ compaction
@@ -698,8 +834,20 @@ struct SegIter {  // iterate the segments {first,count} behind a topic's ranges 
     }
 };
 
+__device__ __forceinline__ void caps_one(const CapsParams& p, uint32_t t);
 __global__ void __launch_bounds__(CAPS_THREADS) caps_kernel(const CapsParams p) {
-    const uint32_t t = p.flagged_list[blockIdx.x];
+    if (p.n_flagged >= 0) {
+        caps_one(p, p.flagged_list[blockIdx.x]);
+        return;
+    }
+    // counts read on the device: a fixed grid strides over the flagged topics no earlier pass has handled
+    const unsigned long long b = p.counters[CTR_FLAGGED2], e = p.counters[CTR_FLAGGED];
+    for (unsigned long long j = b + blockIdx.x; j < e; j += gridDim.x) {
+        caps_one(p, p.flagged_list[j]);
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void caps_one(const CapsParams& p, uint32_t t) {
     const int tenant = p.topic_tenant[t];
     const uint64_t maxP = (uint64_t) max(p.max_pfanout[tenant], 0), maxG = (uint64_t) max(p.max_gfanout[tenant], 0);
     SegIter it{p.ranges + p.span_begin[t], p.segs, p.span_count[t] & SPAN_COUNT_MASK};
@@ -742,6 +890,8 @@ __global__ void __launch_bounds__(CAPS_THREADS) caps_kernel(const CapsParams p) 
     __syncthreads();
     if (threadIdx.x == 0 && p.kept_count) p.kept_count[t] = (uint32_t) kept;
 }
+// marks everything flagged so far as handled (the next device-counted caps pass starts behind it)
+__global__ void caps_advance_kernel(unsigned long long* counters) { counters[CTR_FLAGGED2] = counters[CTR_FLAGGED]; }
 
 // ------------------------------------------------------------------------------------------------ expand (device CSR)
 __global__ void expand_counts_kernel(const ExpandParams p) {
@@ -824,23 +974,49 @@ void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStrea
     match_topics_kernel<false><<<(unsigned) ctas, WARPS_PER_CTA * 32, 0, stream>>>(p);
 }
 
-cudaError_t launch_order(const OrderParams& q, void* d_tmp, size_t* tmp_bytes, cudaStream_t stream) {
-    const int n = (int) q.n_topics;
-    if (!d_tmp)
-        return cub::DeviceRadixSort::SortPairs(nullptr, *tmp_bytes, q.keys, q.keys + n, q.vals, q.vals + n, n, 0, 32, stream);
-    if (n <= 0) return cudaSuccess;
+static int order_tenant_bits(int32_t n_tenants) {
     int tenant_bits = 0;
-    while (tenant_bits < 20 && (1ll << tenant_bits) < (long long) q.n_tenants) tenant_bits++;
-    // width of the sort key: tenant bits + ~14 bits of level hashes, in whole 8-bit radix passes (1000 tenants: 24 bits, three
-    // passes; measured: a fourth pass costs 12 us and buys 1.5 % of kernel time). BFQ_ORDER_BITS overrides (experiments).
+    while (tenant_bits < 20 && (1ll << tenant_bits) < (long long) n_tenants) tenant_bits++;
+    return tenant_bits;
+}
+static int order_key_bits(int tenant_bits) {
+    // width of the order key: tenant bits + ~14 bits of level hashes (1000 tenants: 24 bits). BFQ_ORDER_BITS overrides (experiments).
     static const int forced_bits = [] {
         const char* e = getenv("BFQ_ORDER_BITS");
         return e ? std::min(std::max(atoi(e), 8), 32) : 0;
     }();
     int kb = forced_bits ? forced_bits : std::min(32, (tenant_bits + 12 + 7) / 8 * 8);
-    kb = std::max(kb, std::min(32, tenant_bits + 3));
-    order_keys_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(q, tenant_bits, kb);
-    return cub::DeviceRadixSort::SortPairs(d_tmp, *tmp_bytes, q.keys, q.keys + n, q.vals, q.vals + n, n, 0, kb, stream);
+    return std::max(kb, std::min(32, tenant_bits + 3));
+}
+static int order_hist_bits(int64_t n_topics, int32_t n_tenants) {
+    // buckets = the key's leading bits: at most 2^22 (a 16 MB histogram: zeroed and scanned in a few microseconds) and about
+    // four per topic for smaller batches; at least 2^12 (one scan block)
+    int nb = 12;
+    while (nb < 22 && (1ll << nb) < 4 * n_topics) nb++;
+    return std::max(12, std::min(nb, order_key_bits(order_tenant_bits(n_tenants))));
+}
+size_t order_hist_buckets(int64_t n_topics, int32_t n_tenants) { return (size_t) 1 << order_hist_bits(n_topics, n_tenants); }
+uint32_t order_hash_entries(int64_t n_topics) {
+    uint32_t e = 1024;
+    while (e < (1u << 31) && (int64_t) e < 2 * n_topics) e <<= 1;
+    return e;
+}
+
+cudaError_t launch_order(const OrderParams& q, cudaStream_t stream) {
+    const int64_t n = q.n_topics;
+    if (n <= 0) return cudaSuccess;
+    const int tenant_bits = order_tenant_bits(q.n_tenants);
+    const int kb = order_key_bits(tenant_bits);
+    const unsigned blocks = (unsigned) ((n + 255) / 256);
+    order_prep_kernel<<<blocks, 256, 0, stream>>>(q, tenant_bits, kb);
+    order_scan_kernel<<<(unsigned) (((size_t) 1 << q.hist_bits) / SCAN_PER_BLOCK), SCAN_THREADS, 0, stream>>>(q);
+    order_scatter_kernel<<<blocks, 256, 0, stream>>>(q);
+    return cudaGetLastError();
+}
+
+void launch_finalize(const FinalizeParams& p, cudaStream_t stream) {
+    if (p.n_topics <= 0) return;
+    finalize_kernel<<<(unsigned) ((p.n_topics + 255) / 256), 256, 0, stream>>>(p);
 }
 
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
@@ -919,8 +1095,14 @@ cudaError_t launch_expand(const ExpandParams& p, void* d_scan_tmp, size_t* tmp_b
 }
 
 void launch_caps(const CapsParams& p, cudaStream_t stream) {
-    if (p.n_flagged <= 0) return;
-    caps_kernel<<<(unsigned) p.n_flagged, CAPS_THREADS, 0, stream>>>(p);
+    if (p.n_flagged == 0) return;
+    if (p.n_flagged > 0) {
+        caps_kernel<<<(unsigned) p.n_flagged, CAPS_THREADS, 0, stream>>>(p);
+        return;
+    }
+    // counts on the device (the optimistic, sync-free enqueue): a fixed grid, then advance the handled mark
+    caps_kernel<<<148 * 4, CAPS_THREADS, 0, stream>>>(p);
+    caps_advance_kernel<<<1, 1, 0, stream>>>(p.counters);
 }
 
 }  // namespace bfq

@@ -17,7 +17,9 @@ enum : int {
     CTR_ERROR = 5,       // tier-2 scratch exhausted (cannot happen with correctly sized scratch)
     CTR_DEFER = 6,       // topics the lane-per-topic tier handed to the warp-per-topic tier
     CTR_CHUNK = 7,       // tier-0 work distribution: next unclaimed topic index
-    CTR_COUNT = 8,
+    CTR_NLEAD = 8,       // number of distinct (tenant, topic) pairs of the batch = length of the locality order
+    CTR_FLAGGED2 = 9,    // flagged topics already handled by an earlier caps pass (the rare tier-2 path runs a second one)
+    CTR_COUNT = 12,
 };
 
 constexpr uint32_t SPAN_FLAGGED = 0x80000000u;   // in span_count: caps must be applied to this topic
@@ -42,6 +44,7 @@ struct MatchParams {
     // tier 0: optional processing order (topic indices grouped by tenant and leading levels, see launch_order); nullptr =>
     // 0..n_topics. Only the order in which lanes pick topics changes; every output stays indexed by topic.
     const uint32_t* order;
+    const unsigned long long* order_count;   // device scalar: entries of `order` (the batch's distinct topics); with order only
     // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
     int64_t n_work;
@@ -65,7 +68,7 @@ struct MatchParams {
 
 struct CapsParams {
     const uint32_t* flagged_list;
-    int64_t n_flagged;
+    int64_t n_flagged;              // < 0: flagged_list[counters[CTR_FLAGGED2] ... counters[CTR_FLAGGED]) (counts read on the device)
     const int32_t* topic_tenant;
     const int32_t* max_pfanout;
     const int32_t* max_gfanout;
@@ -109,20 +112,53 @@ struct ExpandParams {
 // phase 2 = write the ranks (unordered within a topic). tmp as for launch_compact.
 cudaError_t launch_expand(const ExpandParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase);
 
-// Locality ordering for tier 0: 32-bit key = tenant index | hashes of the first three levels, radix-sorted (cub) with the
-// topic index as payload -> order_out[n]. Topics that walk the same top of the trie are then matched by neighbouring
-// lanes at the same time: their node reads hit L1/L2 instead of being ~18 random DRAM accesses per topic.
-// keys/vals: scratch of 2 * n uint32 each; d_tmp / tmp_bytes as for launch_compact (query with d_tmp == nullptr).
+// Locality ordering + de-duplication for tier 0, all own kernels (no library sort):
+//   prep     one thread per topic: 64-bit hash of (tenant, topic bytes) -> insert into an open-addressing table; the first
+//            inserter of a (tenant, topic) pair is its LEADER, later identical ones (verified byte by byte) are followers that
+//            only remember their leader. Leaders get an order key = tenant index | hashes of the level-0 / 0..1 / 0..2 prefixes
+//            and count themselves into a bucket histogram (bucket = the key's leading hist_bits).
+//   scan     exclusive prefix sum of the histogram (block-local scans; the last block to finish scans the block totals)
+//   scatter  leaders -> order[bucket base + atomic cursor]: a counting sort, unstable inside a bucket (only grouping matters)
+// Tier 0 then matches order[0 .. n_leaders) — topics that walk the same top of the trie are matched by neighbouring lanes at
+// the same time — and finalize_kernel copies each follower's span from its leader (spans are indices into the sparse range
+// array, so no range is copied). The reference never sees duplicates (matchAll takes a Set<String>,
+// DW/cache/ITenantRouteMatcher.java:28-38; DW/cache/TenantRouteCache.java:100-139 serves repeats from its cache).
 struct OrderParams {
     int64_t n_topics;
     const uint8_t* topics;
     const int64_t* topic_off;
     const int32_t* topic_tenant;
     int32_t n_tenants;
-    uint32_t* keys;                 // [2n]
-    uint32_t* vals;                 // [2n]; the sorted order ends up in vals + n
+    uint32_t* keys;                 // [n] bucket of each leader
+    uint32_t* leader;               // [n] out: i for a leader, else the index of the identical topic that leads
+    uint32_t* order;                // [n] out: the leaders, grouped by bucket
+    unsigned long long* hash_tab;   // [hash_mask + 1] pre-set to 0xFF bytes
+    uint32_t hash_mask;
+    uint32_t* hist;                 // [n_buckets] zeroed; n_buckets = 2^hist_bits, a multiple of 4096
+    uint32_t* blk_tot;              // [n_buckets / 4096]
+    uint32_t* blk_pfx;              // [n_buckets / 4096]
+    uint32_t* ticket;               // zeroed
+    int hist_bits;
+    int dedup;                      // 0: every topic is its own leader
+    unsigned long long* counters;   // CTR_NLEAD is written by the scan
 };
-cudaError_t launch_order(const OrderParams& q, void* d_tmp, size_t* tmp_bytes, cudaStream_t stream);
+size_t order_hist_buckets(int64_t n_topics, int32_t n_tenants);   // histogram entries launch_order will use
+uint32_t order_hash_entries(int64_t n_topics);                    // dedup table entries (power of two)
+cudaError_t launch_order(const OrderParams& q, cudaStream_t stream);
+
+// followers copy their leader's span (and join the flagged list if it needs caps). second_pass: only the followers whose
+// span still carries the tier-2 marker (their leader was finished by tier 2 after the first pass).
+struct FinalizeParams {
+    int64_t n_topics;
+    const uint32_t* leader;
+    uint32_t* span_begin;
+    uint32_t* span_count;
+    uint32_t* route_count;
+    uint32_t* flagged_list;
+    unsigned long long* counters;
+    int second_pass;
+};
+void launch_finalize(const FinalizeParams& p, cudaStream_t stream);
 
 // tier 0: one LANE per topic (DFS, bounded smem); tier 1: one WARP per topic; tier 2: warp per topic, global scratch
 void launch_match_lanes(const MatchParams& p, cudaStream_t stream);

@@ -30,7 +30,8 @@ GroupFanoutThrottled = namedtuple("GroupFanoutThrottled", "tenant_id topic mqtt_
 
 
 class BatchResult:
-    """Numpy views over one bfq_match result (valid until the next match on the same index)."""
+    """Numpy views over one bfq_match result. The arrays are private to this result and stay valid until close();
+    route()/route_kinds() resolve ranks against the snapshot the match ran on, whatever was committed since."""
 
     def __init__(self, handle, n):
         self._h = handle
@@ -62,6 +63,24 @@ class BatchResult:
         N.lib.bfq_result_expand(self._h, offsets.ctypes.data, ranks.ctypes.data, total)
         return offsets, ranks[:total]
 
+    @property
+    def generation(self):
+        return int(N.lib.bfq_result_generation(self._h))
+
+    def route(self, rank):
+        """(key, value) of a route rank of THIS result (bfq_result_route_lookup)"""
+        kl, vl = C.c_int64(0), C.c_int64(0)
+        N.check(N.lib.bfq_result_route_lookup(self._h, int(rank), None, 0, C.byref(kl), None, 0, C.byref(vl)))
+        kb, vb = C.create_string_buffer(max(kl.value, 1)), C.create_string_buffer(max(vl.value, 1))
+        N.check(N.lib.bfq_result_route_lookup(self._h, int(rank), C.addressof(kb), kl.value, C.byref(kl), C.addressof(vb), vl.value, C.byref(vl)))
+        return kb.raw[:kl.value], vb.raw[:vl.value]
+
+    def route_kinds(self, ranks):
+        ranks = np.ascontiguousarray(ranks, dtype=np.int64)
+        out = np.zeros(max(len(ranks), 1), np.uint8)
+        N.check(N.lib.bfq_result_route_kinds(self._h, ranks.ctypes.data, len(ranks), out.ctypes.data))
+        return out[:len(ranks)]
+
     def close(self):
         if self._h:
             N.lib.bfq_result_free(self._h)
@@ -69,6 +88,40 @@ class BatchResult:
 
     def __del__(self):
         self.close()
+
+
+class DeviceResult:
+    """One bfq_match_device[_async] result: device pointers + counts; the buffers stay valid until release()."""
+
+    def __init__(self, raw):
+        self.raw = raw
+
+    def __getattr__(self, name):   # d_span_begin, n_ranges, tier0_ms, ... straight from the C struct
+        if name == "raw":
+            raise AttributeError(name)
+        return getattr(self.raw, name)
+
+    def wait(self):
+        N.check(N.lib.bfq_device_result_wait(C.byref(self.raw)))
+        return self
+
+    def expand(self, d_offsets_ptr, d_ranks_ptr, rank_cap, stream=0):
+        """device CSR of the surviving routes; returns the total number"""
+        total = C.c_int64(0)
+        N.check(N.lib.bfq_expand_device(C.byref(self.raw), d_offsets_ptr, d_ranks_ptr, rank_cap, stream, C.byref(total)))
+        return total.value
+
+    def release(self):
+        if getattr(self, "raw", None) is not None and self.raw.lease:
+            N.lib.bfq_device_result_release(C.byref(self.raw))
+
+    close = release
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class GpuRouteIndex:
@@ -115,11 +168,17 @@ class GpuRouteIndex:
         N.check(N.lib.bfq_index_commit(self._h))
 
     def stats(self):
-        s = np.zeros(12, np.int64)
-        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 12))
+        s = np.zeros(13, np.int64)
+        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 13))
         names = ["routes", "tenants", "nodes", "slots", "device_bytes", "max_nodes_per_depth", "launches",
-                 "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks", "deferred_topics"]
+                 "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks", "deferred_topics",
+                 "duplicate_topics"]
         return dict(zip(names, s.tolist()))
+
+    def generation(self):
+        g = C.c_uint64(0)
+        N.check(N.lib.bfq_index_generation(self._h, C.byref(g)))
+        return g.value
 
     def last_kernel_ms(self):
         ms = C.c_double(0)
@@ -173,21 +232,17 @@ class GpuRouteIndex:
         return self.match(tenants, blob, off, tt, max_pfanout, max_gfanout)
 
     def match_device(self, tenants, d_topics_ptr, d_topic_off_ptr, d_topic_tenant_ptr, n, max_pfanout=None,
-                     max_gfanout=None, stream=0):
+                     max_gfanout=None, stream=0, wait=True):
+        """batch resident in device memory, result left there. wait=False only enqueues (bfq_match_device_async): call
+        .wait() on the returned DeviceResult before reading its counts; .release() hands the buffers back."""
         tb, toff, nt = self._tenants(tenants)
         mp = np.full(max(nt, 1), INT_MAX, np.int32) if max_pfanout is None else np.ascontiguousarray(max_pfanout, dtype=np.int32)
         mg = np.full(max(nt, 1), INT_MAX, np.int32) if max_gfanout is None else np.ascontiguousarray(max_gfanout, dtype=np.int32)
         out = N.BfqDeviceResult()
-        N.check(N.lib.bfq_match_device(self._h, N.ptr(tb), N.ptr(toff), nt, d_topics_ptr, d_topic_off_ptr, d_topic_tenant_ptr,
-                                       n, N.ptr(mp), N.ptr(mg), stream, C.byref(out)))
-        return out
-
-
-    def expand_device(self, n, d_offsets_ptr, d_ranks_ptr, rank_cap, stream=0):
-        """device CSR of the latest match_device result; returns the total number of surviving routes"""
-        total = C.c_int64(0)
-        N.check(N.lib.bfq_expand_device(self._h, n, d_offsets_ptr, d_ranks_ptr, rank_cap, stream, C.byref(total)))
-        return total.value
+        fn = N.lib.bfq_match_device if wait else N.lib.bfq_match_device_async
+        N.check(fn(self._h, N.ptr(tb), N.ptr(toff), nt, d_topics_ptr, d_topic_off_ptr, d_topic_tenant_ptr,
+                   n, N.ptr(mp), N.ptr(mg), stream, C.byref(out)))
+        return DeviceResult(out)
 
 
 class MatchedRoutes:
@@ -232,14 +287,14 @@ class GpuTenantRouteMatcher:
         topics = list(topics)
         res = self.index.match_topics([self.tenant_id], topics, None, [max_persistent_fanout_count], [max_group_fanout_count])
         offsets, ranks = res.expand()
-        kinds = self.index.route_kinds(ranks)
+        kinds = res.route_kinds(ranks)   # resolved against the snapshot the match ran on
         out = {}
         cache = {}
 
         def matching(rank):
             m = cache.get(rank)
             if m is None:
-                m = cache[rank] = schema.build_match_route(*self.index.route(rank))
+                m = cache[rank] = schema.build_match_route(*res.route(rank))
             return m
         for i, topic in enumerate(topics):
             rk = ranks[offsets[i]:offsets[i + 1]]

@@ -11,9 +11,20 @@
  *
  * Conventions: every function returns 0 (BFQ_OK) or a negative BFQ_E_* code; bfq_last_error()
  * gives the text. All buffers are caller-owned plain memory (host unless the name says device);
- * strings are (blob, int64 offsets[n+1]) pairs, never NUL-terminated. A handle may be used from
- * several threads, calls are serialised internally. There is no CPU fallback: every match runs
- * on the GPU and the library fails (BFQ_E_CUDA) if no device is usable.
+ * strings are (blob, int64 offsets[n+1]) pairs, never NUL-terminated. There is no CPU fallback: every
+ * match runs on the GPU and the library fails (BFQ_E_CUDA) if no device is usable.
+ *
+ * Threading (what ITenantRouteMatcher's callers need: matchAll runs on the shared "topic-matcher" ForkJoinPool,
+ * DW/DistWorkerCoProcFactory.java:74-85, while mutate() runs on the range's raft-apply thread): a handle may be used
+ * from any number of threads at once. Every match leases its own workspace (streams, device scratch, pinned result
+ * buffers) and pins the snapshot it ran on; the result keeps both until it is freed, so results of concurrent matches
+ * never share memory and a commit never changes what an existing result resolves to. load/apply/commit serialise
+ * among themselves and never block matches.
+ *
+ * Semantics: the matcher implements the match PREDICATE of the reference. It equals the reference's
+ * literal merge-join (TenantRouteMatcher.java:96-156) whenever that neither skips routes after its 20 probes nor seeks
+ * backwards, i.e. for filters/topics without empty levels next to a shared prefix; the two documented divergences are
+ * pinned in tests/test_oracle_golden.py and cannot be cross-checked against a JVM in this repository.
  */
 #ifndef BFQ_GPUMATCH_H
 #define BFQ_GPUMATCH_H
@@ -66,16 +77,20 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
                         int64_t n_del);
 
 /* Publish the staged state as a new immutable device snapshot. The host-side rebuild and the upload run while matches
- * continue on the previous snapshot; the swap is atomic with respect to matches (they always see a whole snapshot). */
+ * continue on the previous snapshot; the swap is atomic with respect to matches (they always see a whole snapshot).
+ * Every snapshot has a generation (1, 2, ...); results report the generation they were produced from. The previous
+ * snapshot is freed when the last match / result that pins it is gone. bfq_index_apply is all-or-nothing: an
+ * undecodable key leaves the staging area untouched. */
 int32_t bfq_index_commit(bfq_index* h);
+int32_t bfq_index_generation(bfq_index* h, uint64_t* generation);   /* 0 before the first commit */
 
 /* stats[k], k < n: 0 routes, 1 tenants, 2 trie nodes, 3 hash-table slots, 4 device bytes, 5 max nodes per
  * depth, 6 kernel launches so far, 7 overflow (tier-2) topics so far, 8 cap-flagged topics so far,
  * 9 multi-segment filters, 10 long-token chunks, 11 topics handed from the lane-per-topic tier to the
- * warp-per-topic tier so far */
+ * warp-per-topic tier so far, 12 duplicate (tenant, topic) pairs answered from their first occurrence so far */
 int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n);
-/* device time of the tier-1 match kernel of the latest match call on this handle, measured with CUDA events
- * recorded on the launching stream around the launch (for roofline accounting) */
+/* device time of the tier-0 (lane-per-topic) match kernel of the latest completed match call on this handle, measured with
+ * CUDA events recorded on the launching stream around the launch (for roofline accounting) */
 int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms);
 
 /* Host-only diagnostic: run the index builder on a sorted KV snapshot without touching a device and report
@@ -87,7 +102,10 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
 
 /* Map a route rank (position in the committed KV order) back to its stored key/value so the Java side
  * re-hydrates Matching objects with its own KVSchemaUtil.buildMatchRoute (DWS/KVSchemaUtil.java:73-79).
- * Lengths are returned even if the capacities are too small (nothing is copied then). */
+ * Lengths are returned even if the capacities are too small (nothing is copied then).
+ * These three resolve against the CURRENT snapshot: ranks shift with every add/remove, so a rank taken from a match
+ * result must be resolved with bfq_result_route_lookup / bfq_result_route_kinds (below), which use the snapshot the
+ * result was produced from — the reference reads keys and values from one consistent KV reader too. */
 int32_t bfq_route_lookup(bfq_index* h, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
                          uint8_t* val_out, int64_t val_cap, int64_t* val_len);
 /* per-rank route kind: 0 normal, 1 normal persistent (subBrokerId == 1), 2 group (shared subscription) */
@@ -108,8 +126,8 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
                   const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n_topics,
                   const int32_t* max_pfanout, const int32_t* max_gfanout, bfq_result** out);
 
-/* Result layout. The arrays live in pinned memory owned by the index: they are valid until bfq_result_free() or the
- * NEXT bfq_match on the same handle, whichever comes first (copy what must outlive that):
+/* Result layout. The arrays live in pinned memory leased to this result: they stay valid, and private to it, until
+ * bfq_result_free() — other matches on the same handle (from any thread) and commits do not touch them:
  *   span_begin[i], span_count[i]   topic i's matched route RANGES are ranges[span_begin[i] ... +span_count[i])
  *   ranges[j] = {first rank, count} a run of consecutive route ranks (one matched filter's routes)
  *   route_count[i]                 routes matched by topic i before caps
@@ -125,8 +143,13 @@ const uint32_t* bfq_result_route_count(const bfq_result* r);
 const bfq_range* bfq_result_ranges(const bfq_result* r, int64_t* n_ranges);
 const bfq_throttled* bfq_result_throttled(const bfq_result* r, int64_t* n_throttled);
 /* Convenience: flatten to CSR of surviving ranks, ascending per topic. offsets[n_topics+1]; returns the
- * total, copies only if it fits rank_cap. */
+ * total, copies only if it fits rank_cap (large results are filled by several host threads). */
 int64_t bfq_result_expand(const bfq_result* r, int64_t* offsets, int64_t* ranks, int64_t rank_cap);
+/* rank -> stored key/value and route kind, resolved against the snapshot THIS result was produced from */
+int32_t bfq_result_route_lookup(const bfq_result* r, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len,
+                                uint8_t* val_out, int64_t val_cap, int64_t* val_len);
+int32_t bfq_result_route_kinds(const bfq_result* r, const int64_t* ranks, int64_t n, uint8_t* kinds_out);
+uint64_t bfq_result_generation(const bfq_result* r);
 /* timings of the call in milliseconds: 0 busy time of the H2D copy stream (overlapped with kernels), 1 device time
  * of the tier-0 kernel of the first sub-batch, 2 number of pipelined sub-batches, 3 wall time of the whole call */
 int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n);
@@ -134,11 +157,18 @@ void bfq_result_free(bfq_result* r);
 
 /* Same match with the topic batch already resident in device memory and the result left there
  * (used by bench.py's kernel-only leg and by callers that pipeline batches). d_* are device pointers
- * (the kernels read d_topics in whole 16-byte aligned granules that hold at least one topic byte, so the
+ * (the kernels read d_topics in whole aligned words / 16-byte granules that hold at least one topic byte, so the
  * blob must lie in memory that is readable up to its enclosing 16-byte boundaries: any cudaMalloc'd buffer),
- * stream is a cudaStream_t (NULL = default stream). The call enqueues the kernels, then synchronises
- * the stream once to read the counters. The device result buffers belong to the index and stay valid
- * until the next match on it. */
+ * stream is a cudaStream_t (NULL = default stream).
+ *   bfq_match_device_async  enqueues every kernel of the match on `stream` and returns without synchronising: all
+ *                           counts the later kernels need are read on the device. The d_* result pointers are valid
+ *                           for work enqueued on the same stream afterwards; the n_* fields are not filled yet.
+ *   bfq_device_result_wait  waits for the match, fills the n_* fields and handles the rare cases the optimistic
+ *                           enqueue cannot (topics that need the global-scratch tier, buffers that must grow: the
+ *                           batch is then re-run and the d_* pointers may change — read them after the wait).
+ *   bfq_match_device        = async + wait.
+ * The result buffers belong to a workspace leased to this result: they stay valid until bfq_device_result_release,
+ * whatever else runs on the handle. Several matches may be in flight on one handle (and one stream) at a time. */
 typedef struct {
     const uint32_t* d_span_begin;   /* [n_topics] */
     const uint32_t* d_span_count;   /* [n_topics] */
@@ -148,15 +178,25 @@ typedef struct {
     const bfq_throttled* d_throttled; /* [n_throttled] */
     int64_t n_ranges, n_throttled, n_routes;
     int64_t n_overflow_topics, n_flagged_topics, n_launches;
+    int64_t n_distinct_topics;      /* (tenant, topic) pairs actually walked; duplicates share their first occurrence's span */
+    double tier0_ms;                /* device time of the lane-per-topic kernel of this match (CUDA events on `stream`) */
+    uint64_t generation;            /* snapshot the match ran on */
+    void* lease;                    /* opaque; owned by the library until bfq_device_result_release */
 } bfq_device_result;
 int32_t bfq_match_device(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                          const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
                          int64_t n_topics, const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream,
                          bfq_device_result* out);
-/* Flatten the result of the latest bfq_match_device into a device CSR: d_offsets[n_topics+1] (int64) is always
- * written, the surviving ranks (caps applied, unordered within a topic) are written to d_ranks if the total fits
- * rank_cap (pass d_ranks = NULL to only size). Returns the total via *n_ranks. */
-int32_t bfq_expand_device(bfq_index* h, int64_t n_topics, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap,
+int32_t bfq_match_device_async(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                               const uint8_t* d_topics, const int64_t* d_topic_off, const int32_t* d_topic_tenant,
+                               int64_t n_topics, const int32_t* max_pfanout, const int32_t* max_gfanout, void* stream,
+                               bfq_device_result* out);
+int32_t bfq_device_result_wait(bfq_device_result* res);
+void bfq_device_result_release(bfq_device_result* res);
+/* Flatten a completed device result into a device CSR: d_offsets[n_topics+1] (int64) is always written, the surviving
+ * ranks (caps applied, unordered within a topic) are written to d_ranks if the total fits rank_cap (pass
+ * d_ranks = NULL to only size). Returns the total via *n_ranks. Resolves against the result's own snapshot and caps. */
+int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap,
                           void* stream, int64_t* n_ranks);
 
 /* ------------------------------------------------------------------------------------------------

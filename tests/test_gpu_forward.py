@@ -531,9 +531,9 @@ def test_device_resident_match_and_expand(B, caps):
     stream = torch.cuda.current_stream(dev).cuda_stream
     out = idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, [caps[0]] * nt, [caps[1]] * nt, stream)
     d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    total = idx.expand_device(n, d_offsets.data_ptr(), None, 0, stream)
+    total = out.expand(d_offsets.data_ptr(), None, 0, stream)
     d_ranks = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
-    assert idx.expand_device(n, d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream) == total
+    assert out.expand(d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream) == total
     torch.cuda.synchronize()
     res = idx.match(tenants, w.topics, w.topic_off, w.topic_tenant[:n], [caps[0]] * nt, [caps[1]] * nt)
     offsets, ranks = res.expand()
@@ -542,7 +542,170 @@ def test_device_resident_match_and_expand(B, caps):
     for i in range(n):   # unordered within a topic on the device
         assert sorted(got[offsets[i]:offsets[i + 1]].tolist()) == ranks[offsets[i]:offsets[i + 1]].tolist()
     assert out.n_throttled == len(res.throttled)
+    assert out.generation == res.generation == idx.generation()
     res.close()
+    out.release()
+
+
+def test_async_device_matches_in_flight_together(B):
+    """bfq_match_device_async: three batches enqueued back to back on one stream without a host sync, each on its own leased
+    workspace; waited afterwards, each equals the host path on its batch"""
+    import torch
+    w = B.workload.Workload("C3", scale=0.05)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    tenants = w.tenants
+    nt = len(tenants)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    cuts = [(0, w.n_topics), (0, w.n_topics // 2), (w.n_topics // 3, w.n_topics)]
+    keep, outs = [], []
+    for b, e in cuts:
+        off = np.ascontiguousarray(w.topic_off[b:e + 1])
+        d_topics = torch.from_numpy(np.ascontiguousarray(w.topics)).to(dev)
+        d_off = torch.from_numpy(off).to(dev)
+        d_tt = torch.from_numpy(np.ascontiguousarray(w.topic_tenant[b:e])).to(dev)
+        keep.append((d_topics, d_off, d_tt))
+        outs.append(idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), e - b, [3] * nt, [1] * nt,
+                                     stream, wait=False))
+    for (b, e), out in zip(cuts, outs):
+        out.wait()
+        n = e - b
+        d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        total = out.expand(d_offsets.data_ptr(), None, 0, stream)
+        d_ranks = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+        out.expand(d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream)
+        torch.cuda.synchronize()
+        res = idx.match(tenants, w.topics, np.ascontiguousarray(w.topic_off[b:e + 1]), w.topic_tenant[b:e], [3] * nt, [1] * nt)
+        offsets, ranks = res.expand()
+        assert d_offsets.cpu().numpy().tolist() == offsets.tolist()
+        got = d_ranks.cpu().numpy()[:total]
+        for i in range(n):
+            assert sorted(got[offsets[i]:offsets[i + 1]].tolist()) == ranks[offsets[i]:offsets[i + 1]].tolist()
+        assert out.n_throttled == len(res.throttled) and out.n_distinct_topics <= n
+        res.close()
+    for out in outs:
+        out.release()
+
+
+def test_concurrent_matches_on_one_handle(B):
+    """ITenantRouteMatcher.matchAll is called from the shared topic-matcher pool (DW/DistWorkerCoProcFactory.java:74-85): six
+    threads match DIFFERENT batches on ONE handle at the same time, hold their results while the others run, and every
+    result equals the oracle's answer for its own batch (results own their buffers)"""
+    import threading
+    w = B.workload.Workload("C3", scale=0.05)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    tenants = w.tenants
+    nt = len(tenants)
+    all_topics = w.topic_list()
+    T = 6
+    per = len(all_topics) // T
+    want, got, errs = {}, {}, []
+    for k in range(T):
+        b = k * per
+        tt = np.ascontiguousarray(w.topic_tenant[b:b + per])
+        want[k] = kv.match_batch(tenants, all_topics[b:b + per], tt, 3, 1, O.MODE_TRIE, False, 8)
+    barrier = threading.Barrier(T)
+
+    def worker(k):
+        try:
+            b = k * per
+            tt = np.ascontiguousarray(w.topic_tenant[b:b + per])
+            for rep in range(3):
+                barrier.wait()
+                res = idx.match_topics(tenants, all_topics[b:b + per], tt, [3] * nt, [1] * nt)
+                barrier.wait()   # every thread now holds a result while the others' are alive too
+                offsets, ranks = res.expand()
+                ev = sorted((int(kk), int(t), int(r)) for t, r, kk in res.throttled.tolist())
+                got[(k, rep)] = (offsets.tolist(), ranks.tolist(), ev)
+                res.close()
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+            barrier.abort()
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(T)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for (k, rep), (offsets, ranks, ev) in got.items():
+        assert offsets == want[k].offsets.tolist() and ranks == want[k].ranks.tolist()
+        assert ev == sorted((kk, t, r) for kk, t, r, _ in want[k].events)
+    assert len(got) == 3 * T
+
+
+def test_results_resolve_against_their_own_snapshot(B):
+    """ranks are positions in KV order, so every add/remove shifts them: a result taken before a commit must keep resolving
+    (expand, route lookup, kinds) against the snapshot it was produced from, while lookups through the handle follow the
+    latest commit. The reference reads keys and values from one consistent KV reader (TenantRouteMatcher.java:81-98)."""
+    import threading
+    pairs = []
+    for i in range(50):
+        normal(B, pairs, "t", "a/%02d" % i, 0, "r%02d" % i, "d", 1)
+    normal(B, pairs, "t", "a/+", 1, "wild", "d", 1)
+    pairs.sort()
+    idx = make_index(B, pairs)
+    res_old = idx.match_topics(["t"], ["a/07", "a/33"])
+    off_old, ranks_old = res_old.expand()
+    keys_old = [res_old.route(int(r))[0] for r in ranks_old]
+    gen_old = res_old.generation
+    # a route that sorts FIRST in the tenant shifts every rank by one; concurrent lookups on the old result run meanwhile
+    stop, errs = threading.Event(), []
+
+    def reader():
+        try:
+            while not stop.is_set():
+                o, r = res_old.expand()
+                assert r.tolist() == ranks_old.tolist()
+                assert [res_old.route(int(x))[0] for x in r] == keys_old
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+    th = threading.Thread(target=reader)
+    th.start()
+    for rnd in range(5):
+        adds = []
+        normal(B, adds, "t", "!first%d" % rnd, 0, "x", "d", 1)
+        idx.apply(adds=adds)
+        idx.commit()
+    stop.set()
+    th.join()
+    assert not errs, errs
+    assert idx.generation() == gen_old + 5 and res_old.generation == gen_old
+    res_new = idx.match_topics(["t"], ["a/07", "a/33"])
+    off_new, ranks_new = res_new.expand()
+    assert ranks_new.tolist() == [r + 5 for r in ranks_old.tolist()]
+    assert [res_new.route(int(r))[0] for r in ranks_new] == keys_old          # same routes, new ranks
+    assert [res_old.route(int(r))[0] for r in ranks_old] == keys_old          # the old result still resolves its own ranks
+    assert [idx.route(int(r))[0] for r in ranks_new] == keys_old              # the handle follows the latest commit
+    assert res_old.route_kinds(ranks_old).tolist() == res_new.route_kinds(ranks_new).tolist()
+    res_old.close()
+    res_new.close()
+
+
+def test_duplicate_topics_share_one_walk(B):
+    """a batch with many repeats of the same (tenant, topic) pairs (above the ordering threshold, so the dedup pass runs):
+    every occurrence gets the answer of its own tenant, including cap events per occurrence"""
+    w = B.workload.Workload("C3", scale=0.02)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    base = w.topic_list()[:3000]
+    btt = w.topic_tenant[:3000]
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, 3000, 40000)
+    topics = [base[i] for i in pick]
+    tt = np.ascontiguousarray(btt[pick]).astype(np.int32)
+    # the same topic string under a DIFFERENT tenant must not be merged with it
+    topics[:100] = [base[0]] * 100
+    tt[:100] = np.arange(100) % len(w.tenants)
+    before = idx.stats()["duplicate_topics"]
+    compare_with_oracle(B, idx, kv, w.tenants, topics, tt, 3, 1, O.MODE_TRIE)
+    assert idx.stats()["duplicate_topics"] - before >= 40000 - 3100
 
 
 def test_caps_with_saturated_node_counters(B):
