@@ -37,7 +37,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a bench number)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1 only. strong (default): ONE filter set tenant-sharded over the ranks, the same batch split by owner, the "
+                         "results all-gathered inside the timed step; weak: every rank hosts its own full-size set")
+    ap.add_argument("--no-replicate-hot", action="store_true", help="strong scaling: pure hash placement, no replicas of hot tenants")
+    ap.add_argument("--exchange", default="ranges", choices=["ranges", "counts", "none"], help="N > 1: what the timed step all-gathers")
     ap.add_argument("--cpu-sample", type=int, default=0, help="topics in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-pfanout", type=int, default=2 ** 31 - 1, help="Setting.MaxPersistentFanout (reference default INT_MAX)")
@@ -187,7 +191,7 @@ def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms, gp
 def make_workload(args, rank, world):
     from bifromq_b200.workload import Workload
     if world > 1 and args.scaling == "strong":
-        return Workload(args.config, scale=args.scale, shard_index=rank, shard_count=world)
+        return Workload(args.config, scale=args.scale, shard_index=rank, shard_count=world, replicate_hot=not args.no_replicate_hot)
     # weak scaling: every rank hosts a full-size shard with its own tenant namespace
     prefix = "" if world == 1 else "g%d-" % rank
     return Workload(args.config, seed=Workload.SEED + rank, scale=args.scale, tenant_prefix=prefix)
@@ -298,6 +302,10 @@ def main():
     rank, world, local = dist_env()
     if world != args.gpus and world > 1:
         args.gpus = world
+    if args.scaling is None:
+        # BASELINE C4 / C3 as written: one filter set sharded by tenant over the GPUs. C2 is ONE tenant: it cannot shard by
+        # tenant, every rank then hosts the whole set ("replicas") and the ranks' batches are independent -> weak.
+        args.scaling = "strong" if (world > 1 and args.config in ("C3", "C4")) else "weak"
 
     if args.impl == "reference":
         # the reference's own algorithm (restated in C++, oracle/) on the host cores; rank 0 only
@@ -366,72 +374,91 @@ def main():
         r.close()
         return d2h, tm
 
-    DEPTH = 3   # matches in flight (each on its own leased workspace)
+    from bifromq_b200 import dist as D
+    xch = None
+    if world > 1 and args.exchange != "none":
+        xch = D.Exchange(local)   # NCCL communicator inside the library; the id travels over torch.distributed
+    DEPTH = 3 if xch is None else 1   # matches in flight (each on its own leased workspace); the exchange synchronises every step
     sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
     if rank == 0:
         sampler.start()
+    kernel_ms, launches, n_ranges, n_overflow, n_distinct = [], 0, 0, 0, 0
+    last = [None]
+    gathered_info = {}
+
+    def retire(res, keep=False, record=True):
+        """wait for a step, note its counters, hand its workspace back (the timed loop must reuse the warm workspaces)"""
+        nonlocal launches, n_ranges, n_overflow, n_distinct
+        res.wait()
+        if record:
+            kernel_ms.append(res.tier0_ms)
+            launches += res.n_launches
+            n_ranges, n_overflow, n_distinct = res.n_ranges, res.n_overflow_topics, res.n_distinct_topics
+        if keep:
+            last[0] = res
+        else:
+            res.release()
+
+    def step_sharded(record):
+        """N > 1: match this rank's topics, then the one exchange step — every rank ends with every rank's
+        per-topic counts (and ranges): bfq_exchange_gather, NCCL inside the library, on the same stream"""
+        res = enqueue_device()
+        res.wait()
+        g = xch.gather(res, ranges=args.exchange == "ranges", stream=stream.cuda_stream)
+        gathered_info.update(topics=g.n_topics_total, ranges=g.n_ranges_total, bytes_received=g.bytes_received)
+        if last[0] is not None:
+            last[0].release()      # the previous step's buffers: everything that read them finished before this step's sync
+        last[0] = res
+        if record:
+            kernel_ms.append(res.tier0_ms)
+            return res.n_launches + 4
+        return 0
+
     inflight = []
-    for _ in range(max(args.warmup, 3) + DEPTH):   # warm-up (also creates the DEPTH workspaces the timed loop will reuse)
+    for _ in range(max(args.warmup, 3) + DEPTH):   # warm-up (also creates the workspaces the timed loop will reuse)
+        if xch is not None:
+            step_sharded(False)
+            continue
         inflight.append(enqueue_device())
         if len(inflight) >= DEPTH:
-            inflight.pop(0).wait().release()
+            retire(inflight.pop(0), record=False)
     while inflight:
-        inflight.pop(0).wait().release()
+        retire(inflight.pop(0), record=False)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, launches, n_ranges, n_overflow, n_distinct = [], 0, 0, 0, 0
-    done = []
     torch.cuda.synchronize(dev)
     for i in range(args.steps):
         flush.zero_()                     # L2 flush between timed iterations (untimed: outside the event pair)
         ev[i][0].record(stream)
-        inflight.append(enqueue_device())
+        if xch is not None:
+            launches += step_sharded(True)
+        else:
+            inflight.append(enqueue_device())
         ev[i][1].record(stream)
         if len(inflight) >= DEPTH:
-            done.append(inflight.pop(0).wait())
+            retire(inflight.pop(0))
     while inflight:
-        done.append(inflight.pop(0).wait())
+        r_ = inflight.pop(0)
+        retire(r_, keep=not inflight)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    for out in done:
-        kernel_ms.append(out.tier0_ms)
-        launches += out.n_launches
+    out = last[0]
+    if xch is not None:
         n_ranges, n_overflow, n_distinct = out.n_ranges, out.n_overflow_topics, out.n_distinct_topics
-    out = done[-1]               # kept for the exchange leg below
-    for o in done[:-1]:
-        o.release()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
-    # ---- the one exchange step of the sharded path: all ranks gather the per-topic fan-out counts of the
-    # whole job (what BatchDistReply carries); timed on its own, the matching itself needs no collective
-    exchange_ms, imbalance, exchange_error = None, None, None
+    # per-rank view (rank 0 prints it): where the max over ranks comes from
+    per_rank, imbalance = None, None
     if world > 1:
-        from bifromq_b200 import dist as D
-        try:   # every rank runs the same code on the same shapes, so a failure here is the same failure on every rank
-            fan = D.device_view(out.d_route_count, n, "<i4", dev)
-            for _ in range(3):
-                D.gather_fanout(fan)
-            torch.cuda.synchronize(dev)
-            dist.barrier()
-            xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            xe[0].record(stream)
-            for _ in range(args.steps):
-                gathered = D.gather_fanout(fan)
-            xe[1].record(stream)
-            torch.cuda.synchronize(dev)
-            exchange_ms = xe[0].elapsed_time(xe[1]) / args.steps
-            assert gathered.numel() == n * world
-        except Exception as ex:   # the exchange is reported beside the metric, it must not take the metric down
-            exchange_ms, exchange_error = None, "%s: %s" % (type(ex).__name__, ex)
-        ex_max, _ = D.aggregate(exchange_ms if exchange_ms is not None else -1.0, 0, dev)
-        t_max, _ = D.aggregate(total_ms, 0, dev)
-        t_sum = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_sum)
-        exchange_ms, imbalance = (ex_max if exchange_ms is not None else None), t_max / (t_sum.item() / world)
+        mine = {"rank": rank, "topics_per_step": n, "step_ms": total_ms / args.steps, "tier0_kernel_ms": float(np.mean(kernel_ms)),
+                "routes": int(w.n_routes), "tenants": int(w.n_tenants)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        imbalance = max(p["step_ms"] for p in per_rank) / (sum(p["step_ms"] for p in per_rank) / world)
     n_routes = int(torch.from_numpy(np.zeros(1)).sum()) if n == 0 else None
     # ---- e2e through the host-buffer call
     for _ in range(2):
@@ -471,14 +498,15 @@ def main():
         stats = idx.stats()
         cpu_base, roof = None, None
         k_ms = float(np.mean(kernel_ms))
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only (at N > 1 `w` is one shard)
             cpu_base, st, ns, sample_topic_bytes = run_cpu_baseline(w, args, "trie")
             roof = make_roofline(sample_topic_bytes, st, ns, n, k_ms, ranges_per_batch, routes_per_batch, {"config": args.config})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic",
                 "config": {"workload": workload_name(args, w), "routes_per_gpu": w.n_routes, "filters_per_gpu": w.n_filters,
-                           "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "parallelism": "tenant-sharded x%d" % world,
+                           "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "topics_per_step_all_gpus": int(topics_all),
+                           "parallelism": "tenant-sharded x%d" % world,
                            "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
                            "caps": "MaxPersistentFanout=%s, MaxGroupFanout=%s (reference defaults: INT_MAX, 100)" % (
                                "INT_MAX" if args.max_pfanout == 2 ** 31 - 1 else args.max_pfanout, "INT_MAX" if args.max_gfanout == 2 ** 31 - 1 else args.max_gfanout),
@@ -491,20 +519,26 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "last_step_breakdown_ms": {k: round(v, 3) for k, v in e2e_tm.items()}},
                 "gpu_launches": launches, "gpu_launches_note": "own kernels per step: order prep/scan/scatter + tier 0 + tier 1 + followers + caps (2)", "routes_per_s": routes_per_batch * world * args.steps / (total_ms_max / 1000.0),
+                "tier0_kernel_ms": float(np.mean(kernel_ms)), "step_ms_min_median_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
                 "ranges_per_step": n_ranges, "tier2_topics_per_step": n_overflow, "index": stats, "clocks": clocks}
-        if exchange_error is not None:
-            line["exchange"] = {"error": exchange_error}
+        if world > 1:
+            line["per_rank"] = per_rank
             line["load_imbalance_max_over_mean"] = imbalance
-        if exchange_ms is not None:
-            line["exchange"] = {"what": "all-gather of per-topic fan-out counts (int32) over NCCL, all ranks end with the whole job's",
-                                "ms_per_step": exchange_ms, "bytes_per_rank": 4 * n,
-                                "value_with_exchange": topics_all * args.steps / ((total_ms_max + exchange_ms * args.steps) / 1000.0)}
-            line["load_imbalance_max_over_mean"] = imbalance
+            line["exchange"] = ({"what": "inside the timed step: bfq_exchange_gather (NCCL all-gather inside the library, one host sync): every rank ends with "
+                                         "every rank's per-topic route counts%s" % (", range counts and dense {first rank, count} ranges" if args.exchange == "ranges" else ""),
+                                 "topics_gathered": gathered_info.get("topics"), "ranges_gathered": gathered_info.get("ranges"),
+                                 "bytes_received_per_rank": gathered_info.get("bytes_received")} if xch is not None else
+                                {"what": "none (--exchange none)"})
+            if args.scaling == "strong":
+                line["config"]["sharding"] = ("one %s filter set: tenant -> rank by fnv1a64(tenantId) mod %d%s; the SAME %d-topic batch split by owner" % (
+                    args.config, world, "" if args.no_replicate_hot else "; tenants above 1/(4 x ranks) of the batch are hosted by every rank, their topics dealt round-robin",
+                    int(topics_all)))
         if roof:
             line["roofline"] = roof
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
+    out.release()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -28,10 +28,17 @@ class BfqDeviceResult(C.Structure):
     _fields_ = [("d_span_begin", C.c_void_p), ("d_span_count", C.c_void_p), ("d_route_count", C.c_void_p),
                 ("d_ranges", C.c_void_p), ("d_throttled", C.c_void_p), ("n_ranges", C.c_int64),
                 ("n_throttled", C.c_int64), ("n_routes", C.c_int64), ("n_overflow_topics", C.c_int64),
-                ("n_flagged_topics", C.c_int64), ("n_launches", C.c_int64), ("n_distinct_topics", C.c_int64),
+                ("n_flagged_topics", C.c_int64), ("n_launches", C.c_int64), ("n_topics", C.c_int64), ("n_distinct_topics", C.c_int64),
                 ("tier0_ms", C.c_double), ("generation", C.c_uint64), ("lease", C.c_void_p)]
 
 
+class BfqGathered(C.Structure):
+    _fields_ = [("d_route_count", C.c_void_p), ("d_span_count", C.c_void_p), ("d_ranges", C.c_void_p),
+                ("topic_base", C.POINTER(C.c_int64)), ("range_base", C.POINTER(C.c_int64)), ("n_topics_total", C.c_int64),
+                ("n_ranges_total", C.c_int64), ("bytes_received", C.c_int64), ("world", C.c_int32)]
+
+
+EXCHANGE_ID_BYTES, EXCHANGE_COUNTS, EXCHANGE_RANGES = 128, 1, 2
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 _SIGNATURES = {
     "bfq_last_error": (C.c_char_p, []),
@@ -66,6 +73,10 @@ _SIGNATURES = {
     "bfq_device_result_wait": (_i32, [C.POINTER(BfqDeviceResult)]),
     "bfq_device_result_release": (None, [C.POINTER(BfqDeviceResult)]),
     "bfq_expand_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "bfq_exchange_unique_id": (_i32, [_vp, _i32]),
+    "bfq_exchange_create": (_i32, [_i32, _i32, _i32, _vp, C.POINTER(_vp)]),
+    "bfq_exchange_destroy": (None, [_vp]),
+    "bfq_exchange_gather": (_i32, [_vp, C.POINTER(BfqDeviceResult), _i32, _vp, C.POINTER(BfqGathered)]),
     "bfq_receiver_url": (_i64, [_i32, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_route_key": (_i64, [C.c_char_p, _i64, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_tenant_begin_key": (_i64, [C.c_char_p, _i64, _vp, _i64]),

@@ -176,8 +176,22 @@ struct Workspace {
     }
 };
 
+// idle workspaces of one index. Shared with every result / lease in flight, so that freeing a result after its index was
+// destroyed (a garbage-collected host language decides the order) still has a valid place to return its workspace to.
+struct Pool {
+    std::mutex mu;
+    std::vector<Workspace*> idle;
+    int device = 0;
+    bool closed = false;
+    ~Pool() {
+        cudaSetDevice(device);
+        for (Workspace* w : idle) delete w;
+    }
+};
+
 struct bfq_result {
     bfq_index* owner = nullptr;
+    std::shared_ptr<Pool> pool;
     std::shared_ptr<Snapshot> snap;      // the snapshot the match ran on (ranks resolve against it)
     Workspace* ws = nullptr;             // leased: the arrays below live in its pinned buffers
     int64_t n_topics = 0, n_ranges = 0, n_throttled = 0;
@@ -194,7 +208,7 @@ struct bfq_index {
     Staging staging;
     std::shared_ptr<Snapshot> snap;
     uint64_t next_generation = 1;
-    std::vector<Workspace*> pool;        // idle workspaces
+    std::shared_ptr<Pool> pool = std::make_shared<Pool>();   // idle workspaces
     int64_t order_min = 32768;           // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
     bool dedup = true;                   // BFQ_DEDUP=0: match duplicates of a (tenant, topic) pair separately
     double last_kernel_ms = 0;
@@ -202,7 +216,13 @@ struct bfq_index {
 
     ~bfq_index() {
         cudaSetDevice(device);
-        for (Workspace* w : pool) delete w;
+        std::vector<Workspace*> idle;
+        {
+            std::lock_guard<std::mutex> g(pool->mu);
+            pool->closed = true;   // workspaces still leased are freed when they come back
+            idle.swap(pool->idle);
+        }
+        for (Workspace* w : idle) delete w;
     }
 };
 
@@ -216,9 +236,12 @@ int32_t acquire(bfq_index* h, std::shared_ptr<Snapshot>* snap, Workspace** ws, c
         std::lock_guard<std::mutex> g(h->mu);
         if (!h->snap) return fail(BFQ_E_STATE, std::string(who) + " before the first bfq_index_commit");
         *snap = h->snap;
-        if (!h->pool.empty()) {
-            w = h->pool.back();
-            h->pool.pop_back();
+    }
+    {
+        std::lock_guard<std::mutex> g(h->pool->mu);
+        if (!h->pool->idle.empty()) {
+            w = h->pool->idle.back();
+            h->pool->idle.pop_back();
         }
     }
     if (!w) {
@@ -233,16 +256,16 @@ int32_t acquire(bfq_index* h, std::shared_ptr<Snapshot>* snap, Workspace** ws, c
     return BFQ_OK;
 }
 
-void give_back(bfq_index* h, Workspace* w) {
+void give_back(const std::shared_ptr<Pool>& pool, Workspace* w) {
     if (!w) return;
     {
-        std::lock_guard<std::mutex> g(h->mu);
-        if (h->pool.size() < POOL_KEEP) {
-            h->pool.push_back(w);
+        std::lock_guard<std::mutex> g(pool->mu);
+        if (!pool->closed && pool->idle.size() < POOL_KEEP) {
+            pool->idle.push_back(w);
             return;
         }
     }
-    cudaSetDevice(h->device);
+    cudaSetDevice(pool->device);
     delete w;
 }
 
@@ -612,6 +635,7 @@ int32_t grow_for_retry(Workspace* w, const CoreOut& co, int64_t n, int C) {
 // A device-side match in flight (bfq_match_device_async .. bfq_device_result_wait .. bfq_device_result_release)
 struct DeviceLease {
     bfq_index* h = nullptr;
+    std::shared_ptr<Pool> pool;
     std::shared_ptr<Snapshot> snap;
     Workspace* ws = nullptr;
     CoreCtx ctx{};
@@ -635,6 +659,7 @@ void fill_device_result(const DeviceLease* L, bfq_device_result* out) {
     out->n_overflow_topics = L->co.n_overflow;
     out->n_flagged_topics = L->co.n_flagged;
     out->n_launches = L->co.n_launches;
+    out->n_topics = L->n;
     out->n_distinct_topics = L->co.n_leaders;
     out->tier0_ms = L->tier0_ms;
     out->generation = L->snap->generation;
@@ -693,6 +718,7 @@ int32_t bfq_index_create(int32_t device_ordinal, bfq_index** out) {
     CUDA_TRY(cudaSetDevice(device_ordinal));
     auto* h = new bfq_index();
     h->device = device_ordinal;
+    h->pool->device = device_ordinal;
     if (const char* eo = getenv("BFQ_ORDER")) {   // experiment switch: 0 = never order, N > 0 = order batches of >= N topics
         const long long v = atoll(eo);
         h->order_min = v <= 0 ? (int64_t) 1 << 62 : (int64_t) v;
@@ -962,7 +988,7 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     struct Lease {
         bfq_index* h;
         Workspace* w;
-        ~Lease() { if (w) { cudaSetDevice(h->device); cudaDeviceSynchronize(); give_back(h, w); } }
+        ~Lease() { if (w) { cudaSetDevice(h->device); cudaDeviceSynchronize(); give_back(h->pool, w); } }
     } lease{h, w};
     // topic_tenant[i] is range-checked on the device (an index outside [0, n_tenants) yields an empty result)
     auto t0 = std::chrono::steady_clock::now();
@@ -1123,6 +1149,7 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     }
     auto* r = new bfq_result();
     r->owner = h;
+    r->pool = h->pool;
     r->snap = std::move(snap);
     r->ws = w;
     lease.w = nullptr;   // the result holds the workspace from here on
@@ -1223,7 +1250,7 @@ int32_t bfq_result_timings(const bfq_result* r, double* ms, int32_t n) {
 }
 void bfq_result_free(bfq_result* r) {
     if (!r) return;
-    give_back(r->owner, r->ws);
+    give_back(r->pool, r->ws);
     delete r;
 }
 
@@ -1236,6 +1263,7 @@ int32_t bfq_match_device_async(bfq_index* h, const uint8_t* tenants, const int64
     CUDA_TRY(cudaSetDevice(h->device));
     auto* L = new DeviceLease();
     L->h = h;
+    L->pool = h->pool;
     int32_t rc = acquire(h, &L->snap, &L->ws, "bfq_match_device");
     if (rc != BFQ_OK) {
         delete L;
@@ -1248,7 +1276,7 @@ int32_t bfq_match_device_async(bfq_index* h, const uint8_t* tenants, const int64
     if (rc == BFQ_OK) rc = device_enqueue(L);
     if (rc != BFQ_OK) {
         cudaStreamSynchronize(st);
-        give_back(h, L->ws);
+        give_back(h->pool, L->ws);
         delete L;
         return rc;
     }
@@ -1269,9 +1297,9 @@ int32_t bfq_device_result_wait(bfq_device_result* out) {
 void bfq_device_result_release(bfq_device_result* out) {
     if (!out || !out->lease) return;
     auto* L = static_cast<DeviceLease*>(out->lease);
-    cudaSetDevice(L->h->device);
+    cudaSetDevice(L->pool->device);
     if (!L->done) cudaStreamSynchronize(L->ctx.stream);   // never hand a busy workspace back
-    give_back(L->h, L->ws);
+    give_back(L->pool, L->ws);
     delete L;
     out->lease = nullptr;
 }

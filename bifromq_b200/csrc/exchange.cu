@@ -1,0 +1,266 @@
+// exchange.cu — the ONE exchange step of the tenant-sharded path (include/bfq_gpumatch.h "multi-GPU").
+//
+// Tenants are independent key ranges (DWS/KVSchemaUtil.java:91-94), so N GPUs match their own tenants' topics with no
+// data-path collective. What has to travel is the reply: the dist-server reassembles the per-worker BatchDistReply messages
+// into one answer per batch (bifromq-dist/bifromq-dist-server/.../scheduler/BatchDistServerCall.java:186-205,245-271). Here
+// every rank contributes the device result of its own match — per topic the matched-route count and the number of matched
+// ranges, plus the dense array of {first rank, count} ranges — and every rank ends with all ranks' results, in rank order:
+//   1. local compaction of the sparse result (counts -> exclusive scan -> total), all on the caller's stream;
+//   2. ncclAllGather of {n_topics, n_ranges} per rank (16 bytes) -> the ONE host synchronisation of the exchange: NCCL
+//      needs the receive counts on the host;
+//   3. the compaction's gather kernel writes this rank's dense ranges straight into its slice of the reassembly buffer;
+//   4. one NCCL group of per-root broadcasts (in place) fills the other slices over NVLink / NVSwitch.
+// No torch, no host-side copies, no per-element host work. NCCL is resolved at run time from the process (dlopen of
+// libnccl.so.2: a Java host links the system library, a PyTorch host already carries its own copy).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bfq_gpumatch.h"
+#include "match_kernels.cuh"
+
+namespace bfq {
+int32_t set_error(int32_t code, const std::string& msg);
+}
+using namespace bfq;
+
+namespace {
+
+int32_t xfail(int32_t code, const std::string& msg) { return bfq::set_error(code, msg); }
+#define X_CUDA(expr)                                                                                \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return xfail(BFQ_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // the copy already in the process first (a PyTorch host has loaded its own), then the system library
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) {
+            api.err = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+            return;
+        }
+        bool all = true;
+        auto sym = [&](const char* name) {
+            void* p = dlsym(h, name);
+            if (!p) {
+                all = false;
+                api.err = std::string("NCCL symbol missing: ") + name;
+            }
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId)) sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank)) sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy)) sym("ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather)) sym("ncclAllGather");
+        api.Broadcast = (decltype(api.Broadcast)) sym("ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart)) sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd)) sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString)) sym("ncclGetErrorString");
+        api.ok = all;
+    });
+    return api;
+}
+#define X_NCCL(expr)                                                                                \
+    do {                                                                                            \
+        ncclResult_t _r = (expr);                                                                   \
+        if (_r != ncclSuccess) return xfail(BFQ_E_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(_r)); \
+    } while (0)
+
+template <typename T>
+struct XBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n + n / 4, 1024);   // headroom: the sizes move a little from batch to batch
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+__global__ void exchange_meta_kernel(long long* meta, long long n_topics, const uint32_t* new_begin, const uint32_t* counts) {
+    meta[0] = n_topics;
+    meta[1] = n_topics > 0 ? (long long) new_begin[n_topics - 1] + counts[n_topics - 1] : 0;
+}
+
+}  // namespace
+
+struct bfq_exchange {
+    int device = 0, rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    XBuf<uint32_t> d_cnt, d_begin;          // local compaction scratch
+    XBuf<uint8_t> d_scan_tmp;
+    XBuf<long long> d_meta;                 // {n_topics, n_ranges} x world
+    long long* h_meta = nullptr;            // pinned copy
+    XBuf<uint32_t> g_route_count, g_span_count;
+    XBuf<uint2> g_ranges;
+    std::vector<int64_t> topic_base, range_base;
+    ~bfq_exchange() {
+        cudaSetDevice(device);
+        if (comm && nccl().ok) nccl().CommDestroy(comm);
+        d_cnt.release(); d_begin.release(); d_scan_tmp.release(); d_meta.release();
+        g_route_count.release(); g_span_count.release(); g_ranges.release();
+        if (h_meta) cudaFreeHost(h_meta);
+    }
+};
+
+extern "C" {
+
+int32_t bfq_exchange_unique_id(uint8_t* id_out, int32_t cap) {
+    if (!id_out || cap < (int32_t) sizeof(ncclUniqueId)) return xfail(BFQ_E_INVALID, "id buffer must hold BFQ_EXCHANGE_ID_BYTES bytes");
+    if (!nccl().ok) return xfail(BFQ_E_STATE, nccl().err);
+    ncclUniqueId id;
+    X_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return BFQ_OK;
+}
+
+int32_t bfq_exchange_create(int32_t device_ordinal, int32_t rank, int32_t world, const uint8_t* id, bfq_exchange** out) {
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) return xfail(BFQ_E_INVALID, "bad argument");
+    if (!nccl().ok) return xfail(BFQ_E_STATE, nccl().err);
+    X_CUDA(cudaSetDevice(device_ordinal));
+    auto* x = new bfq_exchange();
+    x->device = device_ordinal;
+    x->rank = rank;
+    x->world = world;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclResult_t r = nccl().CommInitRank(&x->comm, world, uid, rank);
+    if (r != ncclSuccess) {
+        x->comm = nullptr;
+        delete x;
+        return xfail(BFQ_E_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
+    }
+    cudaError_t e = x->d_meta.reserve((size_t) 2 * world);
+    if (e == cudaSuccess) e = cudaMallocHost(&x->h_meta, (size_t) 2 * world * sizeof(long long));
+    if (e != cudaSuccess) {
+        delete x;
+        return xfail(BFQ_E_CUDA, cudaGetErrorString(e));
+    }
+    x->topic_base.assign((size_t) world + 1, 0);
+    x->range_base.assign((size_t) world + 1, 0);
+    *out = x;
+    return BFQ_OK;
+}
+
+void bfq_exchange_destroy(bfq_exchange* x) { delete x; }
+
+int32_t bfq_exchange_gather(bfq_exchange* x, const bfq_device_result* res, int32_t what, void* stream, bfq_gathered* out) {
+    if (!x || !res || !out) return xfail(BFQ_E_INVALID, "bad argument");
+    if (what != BFQ_EXCHANGE_COUNTS && what != BFQ_EXCHANGE_RANGES) return xfail(BFQ_E_INVALID, "what: BFQ_EXCHANGE_COUNTS or BFQ_EXCHANGE_RANGES");
+    X_CUDA(cudaSetDevice(x->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const int64_t n = res->n_topics;
+    const int W = x->world;
+    const bool with_ranges = what == BFQ_EXCHANGE_RANGES;
+    // ---- 1. local compaction, phase 1 (counts, exclusive scan); the total goes into this rank's meta slot on the device
+    X_CUDA(x->d_cnt.reserve((size_t) std::max<int64_t>(n, 1)));
+    X_CUDA(x->d_begin.reserve((size_t) std::max<int64_t>(n, 1)));
+    CompactParams cp{};
+    cp.n_topics = n;
+    cp.span_begin = res->d_span_begin;
+    cp.span_count = res->d_span_count;
+    cp.ranges = reinterpret_cast<const uint2*>(res->d_ranges);
+    cp.counts = x->d_cnt.p;
+    cp.new_begin = x->d_begin.p;
+    cp.total_out = reinterpret_cast<unsigned long long*>(x->d_meta.p + 2 * x->rank + 1);
+    size_t tmp_bytes = 0;
+    {
+        CompactParams q = cp;
+        q.n_topics = std::max<int64_t>(n, 1);
+        X_CUDA(launch_compact(q, nullptr, &tmp_bytes, st, 1));
+        X_CUDA(x->d_scan_tmp.reserve(tmp_bytes + 256));
+    }
+    if (n > 0) X_CUDA(launch_compact(cp, x->d_scan_tmp.p, &tmp_bytes, st, 1));
+    exchange_meta_kernel<<<1, 1, 0, st>>>(x->d_meta.p + 2 * x->rank, (long long) n, x->d_begin.p, x->d_cnt.p);
+    X_CUDA(cudaGetLastError());
+    // ---- 2. sizes of every rank (the receive counts NCCL needs on the host): the exchange's one host synchronisation
+    X_NCCL(nccl().AllGather(x->d_meta.p + 2 * x->rank, x->d_meta.p, 2, ncclInt64, x->comm, st));
+    X_CUDA(cudaMemcpyAsync(x->h_meta, x->d_meta.p, (size_t) 2 * W * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    X_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < W; r++) {
+        x->topic_base[(size_t) r + 1] = x->topic_base[(size_t) r] + x->h_meta[2 * r];
+        x->range_base[(size_t) r + 1] = x->range_base[(size_t) r] + x->h_meta[2 * r + 1];
+    }
+    const int64_t nt_all = x->topic_base[(size_t) W], nr_all = x->range_base[(size_t) W];
+    if (nr_all >= (int64_t) 0xFFFFFFF0ll) return xfail(BFQ_E_RANGE, "more than 2^32 ranges in one exchanged batch; split the batch");
+    X_CUDA(x->g_route_count.reserve((size_t) std::max<int64_t>(nt_all, 1)));
+    if (with_ranges) {
+        X_CUDA(x->g_span_count.reserve((size_t) std::max<int64_t>(nt_all, 1)));
+        X_CUDA(x->g_ranges.reserve((size_t) std::max<int64_t>(nr_all, 1)));
+    }
+    // ---- 3. this rank's slice, written in place
+    const int64_t tb = x->topic_base[(size_t) x->rank], rb = x->range_base[(size_t) x->rank];
+    if (n > 0) {
+        X_CUDA(cudaMemcpyAsync(x->g_route_count.p + tb, res->d_route_count, (size_t) n * 4, cudaMemcpyDeviceToDevice, st));
+        if (with_ranges) {
+            X_CUDA(cudaMemcpyAsync(x->g_span_count.p + tb, x->d_cnt.p, (size_t) n * 4, cudaMemcpyDeviceToDevice, st));
+            cp.ranges_out = x->g_ranges.p + rb;
+            cp.ranges_out_cap = (uint64_t) x->h_meta[2 * x->rank + 1];
+            cp.out_base = 0;
+            X_CUDA(launch_compact(cp, x->d_scan_tmp.p, &tmp_bytes, st, 2));
+        }
+    }
+    // ---- 4. every rank's slice to every rank: per-root broadcasts, in place, one NCCL group
+    if (W > 1) {
+        X_NCCL(nccl().GroupStart());
+        for (int r = 0; r < W; r++) {
+            const int64_t nr_t = x->h_meta[2 * r], nr_r = x->h_meta[2 * r + 1];
+            uint32_t* rc = x->g_route_count.p + x->topic_base[(size_t) r];
+            if (nr_t > 0) X_NCCL(nccl().Broadcast(rc, rc, (size_t) nr_t, ncclUint32, r, x->comm, st));
+            if (with_ranges) {
+                uint32_t* sc = x->g_span_count.p + x->topic_base[(size_t) r];
+                uint2* rg = x->g_ranges.p + x->range_base[(size_t) r];
+                if (nr_t > 0) X_NCCL(nccl().Broadcast(sc, sc, (size_t) nr_t, ncclUint32, r, x->comm, st));
+                if (nr_r > 0) X_NCCL(nccl().Broadcast(rg, rg, (size_t) nr_r * 2, ncclUint32, r, x->comm, st));
+            }
+        }
+        X_NCCL(nccl().GroupEnd());
+    }
+    out->d_route_count = x->g_route_count.p;
+    out->d_span_count = with_ranges ? x->g_span_count.p : nullptr;
+    out->d_ranges = with_ranges ? reinterpret_cast<const bfq_range*>(x->g_ranges.p) : nullptr;
+    out->topic_base = x->topic_base.data();
+    out->range_base = x->range_base.data();
+    out->n_topics_total = nt_all;
+    out->n_ranges_total = nr_all;
+    out->world = W;
+    out->bytes_received = (nt_all - n) * (with_ranges ? 8 : 4) + (with_ranges ? (nr_all - x->h_meta[2 * x->rank + 1]) * 8 : 0);
+    return BFQ_OK;
+}
+
+}  // extern "C"

@@ -331,12 +331,29 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
     int len = 0, level = 0, tenant = 0;
 
     auto emit = [&](uint32_t first, uint32_t count, bool multi, uint32_t caps) {
-        if (n_rg < INLINE_RANGES) *rg_out++ = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
-        else bad = true;
+        if (n_rg >= INLINE_RANGES) {
+            // the topic's inline slots are full: move it to a SPILL_RANGES block of the cursor-allocated region once (topics with
+            // many matched filters — '+'-heavy filter sets — stay in this kernel instead of queueing for the warp-per-topic tier)
+            if (n_rg == INLINE_RANGES) {
+                const unsigned long long at = p.dyn_base + atomicAdd(&p.counters[CTR_RANGES], (unsigned long long) SPILL_RANGES);
+                if (at + SPILL_RANGES <= p.ranges_cap) {
+                    uint2* dst = p.ranges + at;
+                    const uint2* src = rg_out - INLINE_RANGES;
+#pragma unroll
+                    for (int j = 0; j < (int) INLINE_RANGES; j++) dst[j] = src[j];
+                    rg_out = dst + INLINE_RANGES;
+                } else {
+                    bad = true;   // no room: the host grows the region and re-runs the batch
+                }
+            } else if (n_rg >= SPILL_RANGES) {
+                bad = true;
+            }
+        }
+        if (!bad) *rg_out++ = make_uint2(first, multi ? (count | RANGE_MULTI) : count);
         n_rg++;
         acc_r += count;
         const uint32_t cp = caps & 0xFFu, cg = (caps >> 8) & 0xFFu;
-        acc_p = (acc_p + cp) | (cp == 0xFFu ? 0x80000000u : 0u);   // <= INLINE_RANGES additions of <= 255: no carry into bit 31
+        acc_p = (acc_p + cp) | (cp == 0xFFu ? 0x80000000u : 0u);   // <= SPILL_RANGES additions of <= 255: no carry into bit 31
         acc_g = (acc_g + cg) | (cg == 0xFFu ? 0x80000000u : 0u);
     };
     auto finish = [&]() {
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
                 const bool flag_g = maxG != 0x7FFFFFFF && acc_g > (uint32_t) (maxG < 0 ? 0 : maxG);
                 flagged = flag_p || flag_g;
             }
-            p.span_begin[t] = t * INLINE_RANGES;
+            p.span_begin[t] = (uint32_t) ((rg_out - n_rg) - p.ranges);   // the inline slots, or the spill block
             p.span_count[t] = n_rg | (flagged ? SPAN_FLAGGED : 0u);
             p.route_count[t] = acc_r;
             if (flagged) {
@@ -592,48 +609,79 @@ __global__ void __launch_bounds__(L_WARPS * 32) match_topics_lane_kernel(const M
 }
 
 // ------------------------------------------------------------------------------------------------ locality order
-// topic-aligned 32-bit word k of the topic at byte address a (bytes 4k .. 4k+3; bytes at and after len are garbage and must be
-// masked by the caller). Only aligned words that hold at least one byte of the topic are read, so the reads stay inside
-// the 16-byte granules the blob occupies.
-struct TopicWords {
-    const uint32_t* base;
-    int sh, len, a3;
-    uint32_t lo;
-    int k;
-    __device__ __forceinline__ TopicWords(const uint8_t* topics, int64_t o, int len_) {
+// Reads a topic 16 bytes at a time as four topic-aligned 32-bit words (word i of block j = topic bytes 16j + 4i .. + 3), whatever
+// the topic's alignment in the blob: one aligned 16-byte granule load per block, word select + funnel shift in registers. Bytes
+// at and after len read as 0. Only granules that hold at least one byte of the topic are read, so the reads stay inside the
+// 16-byte granules the blob occupies. (A word-at-a-time reader cost 39 instructions per 4 bytes; the tail loop alone was 41 %
+// of the prep kernel's instructions: ncu source view, profiles/r2_prep_v1.*)
+struct TopicQuads {
+    const uint4* qp;
+    int off, len, j;
+    uint4 cur;
+    __device__ __forceinline__ TopicQuads(const uint8_t* topics, int64_t o, int len_) {
         const uint64_t a = (uint64_t) (uintptr_t) topics + (uint64_t) o;
-        base = reinterpret_cast<const uint32_t*>(a & ~3ull);
-        a3 = (int) (a & 3);
-        sh = a3 * 8;
+        qp = reinterpret_cast<const uint4*>(a & ~15ull);
+        off = (int) (a & 15);
         len = len_;
-        k = 0;
-        lo = len > 0 ? __ldg(base) : 0u;
+        j = 0;
+        cur = len > 0 ? __ldg(qp) : make_uint4(0u, 0u, 0u, 0u);
     }
-    // next word, masked to the topic's length (bytes past the end read as 0)
-    __device__ __forceinline__ uint32_t next() {
-        // aligned word k+1 starts at topic byte 4k + 4 - a3: it holds a topic byte iff that is < len
-        const uint32_t hi = (4 * k + 4 - a3 < len) ? __ldg(base + k + 1) : 0u;
-        uint32_t w = __funnelshift_r(lo, hi, sh);
-        const int rem = len - 4 * k;
-        if (rem < 4) w &= rem <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * rem));
-        lo = hi;
-        k++;
-        return w;
+    __device__ __forceinline__ void next(uint32_t (&w)[4]) {
+        // granule j+1 starts at topic byte 16(j+1) - off
+        const uint4 nx = (16 * (j + 1) - off < len) ? __ldg(qp + j + 1) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t X[8] = {cur.x, cur.y, cur.z, cur.w, nx.x, nx.y, nx.z, nx.w};
+        const bool by2 = off & 8, by1 = off & 4;
+        const int sh = (off & 3) * 8;
+        uint32_t Y[6], Z[5];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Y[i] = by2 ? X[i + 2] : X[i];
+#pragma unroll
+        for (int i = 0; i < 5; i++) Z[i] = by1 ? Y[i + 1] : Y[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(Z[i], Z[i + 1], sh);
+        const int rem = len - 16 * j;
+        if (rem < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)   // 0xFFFFFFFF >> clamp(32(i+1) - 8 rem, 0, 32)
+                w[i] &= __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (i + 1) - 8 * max(rem, 0), 0));
+        }
+        cur = nx;
+        j++;
     }
 };
 
-__device__ __forceinline__ bool same_topic(const uint8_t* topics, int64_t oa, int64_t ob, int len) {
-    TopicWords wa(topics, oa, len), wb(topics, ob, len);
-    for (int k = 0; 4 * k < len; k++)
-        if (wa.next() != wb.next()) return false;
+constexpr int ORDER_WINDOW_QUADS = 3;
+constexpr int ORDER_WINDOW_WORDS = 4 * ORDER_WINDOW_QUADS;   // the order key looks at the first 48 bytes: three levels of ordinary topics end well before
+
+// bytes [0, len) of the topic at offset ob equal the caller's topic, whose first ORDER_WINDOW_WORDS words are already in
+// registers (ka, masked to len) and whose tail is re-read.
+__device__ __forceinline__ bool same_topic(const uint8_t* topics, int64_t oa, const uint32_t (&ka)[ORDER_WINDOW_WORDS], int64_t ob, int len) {
+    TopicQuads wb(topics, ob, len);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < ORDER_WINDOW_QUADS; j++)
+        if (16 * j < len) {
+            uint32_t w[4];
+            wb.next(w);
+#pragma unroll
+            for (int i = 0; i < 4; i++) diff |= ka[4 * j + i] ^ w[i];
+        }
+    if (diff) return false;
+    if (len <= 4 * ORDER_WINDOW_WORDS) return true;
+    TopicQuads wa(topics, oa + 4 * ORDER_WINDOW_WORDS, len - 4 * ORDER_WINDOW_WORDS);
+    wb.len = len;
+    for (int j = ORDER_WINDOW_QUADS; 16 * j < len; j++) {
+        uint32_t x[4], y[4];
+        wa.next(x);
+        wb.next(y);
+        if ((x[0] ^ y[0]) | (x[1] ^ y[1]) | (x[2] ^ y[2]) | (x[3] ^ y[3])) return false;
+    }
     return true;
 }
 
-constexpr int ORDER_WINDOW_WORDS = 10;   // the order key looks at the first 40 bytes: three levels of ordinary topics end well before
-
 // key = tenant index (T bits) | hash(level 0) | hash(levels 0..1) | hash(levels 0..2): equal leading levels => equal digits =>
 // one bucket. Hash collisions only merge groups. Topics with fewer levels use digit 0.
-__global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, int tenant_bits, int key_bits) {
+__global__ void __launch_bounds__(256, 4) order_prep_kernel(const OrderParams q, int tenant_bits, int key_bits) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n_topics) return;
     const int64_t o = q.topic_off[i];
@@ -641,23 +689,35 @@ __global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, in
     const int hlen = (int) min(full_len, (int64_t) 0x3FFFFFFF);
     int tn = q.topic_tenant[i];
     if (tn < 0 || tn >= q.n_tenants) tn = -1;   // all out-of-range tenant indices match nothing: one group
-    // ---- one pass over the topic's words: the first ORDER_WINDOW_WORDS feed the order key, all of them the 64-bit hash
+    // ---- one pass over the topic: the first ORDER_WINDOW_WORDS words feed the order key, all of them the 64-bit hash
+    // (two independent 32-bit multiply-xor lanes, one IMAD each per word, folded into 64 bits at the end)
     uint32_t k[ORDER_WINDOW_WORDS];
-    uint64_t h = (uint64_t) (uint32_t) hlen * 0x9E3779B97F4A7C15ull + (uint64_t) (uint32_t) tn * 0xC2B2AE3D27D4EB4Full;
+    uint32_t h1 = (uint32_t) hlen * 0x9E3779B1u + (uint32_t) tn, h2 = (uint32_t) tn * 0x85EBCA77u ^ (uint32_t) hlen;
     {
-        TopicWords tw(q.topics, o, hlen);
+        TopicQuads tq(q.topics, o, hlen);
 #pragma unroll
-        for (int j = 0; j < ORDER_WINDOW_WORDS; j++) {
-            k[j] = 4 * j < hlen ? tw.next() : 0u;
-            h = (h ^ k[j]) * 0xFF51AFD7ED558CCDull;
-            h ^= h >> 32;
+        for (int j = 0; j < ORDER_WINDOW_QUADS; j++) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (16 * j < hlen) tq.next(w);
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                k[4 * j + x] = w[x];
+                h1 = (h1 ^ w[x]) * 0xCC9E2D51u;
+                h2 = (h2 + w[x]) * 0x1B873593u ^ (h2 >> 15);
+            }
         }
         if (q.dedup)
-            for (int j = ORDER_WINDOW_WORDS; 4 * j < hlen; j++) {
-                h = (h ^ tw.next()) * 0xFF51AFD7ED558CCDull;
-                h ^= h >> 32;
+            for (int j = ORDER_WINDOW_QUADS; 16 * j < hlen; j++) {
+                uint32_t w[4];
+                tq.next(w);
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    h1 = (h1 ^ w[x]) * 0xCC9E2D51u;
+                    h2 = (h2 + w[x]) * 0x1B873593u ^ (h2 >> 15);
+                }
             }
     }
+    uint64_t h = ((uint64_t) h1 << 32) | h2;
     // ---- de-duplication: first inserter leads
     uint32_t lead = (uint32_t) i;
     if (q.dedup) {
@@ -665,7 +725,10 @@ __global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, in
         const unsigned long long mine = ((unsigned long long) (uint32_t) (h >> 32) << 32) | (unsigned long long) (uint32_t) i;
         uint32_t slot = (uint32_t) h & q.hash_mask;
         while (true) {
-            unsigned long long cur = q.hash_tab[slot];
+            // read through to L2: an L1-cached "empty" would send every later duplicate of a popular topic on this SM into the
+            // CAS below, and thousands of same-address atomics serialise (the prep kernel sat at ~90 us whatever its
+            // instruction count until this load bypassed L1)
+            unsigned long long cur = __ldcg(&q.hash_tab[slot]);
             if (cur == ~0ull) {
                 cur = atomicCAS(&q.hash_tab[slot], ~0ull, mine);
                 if (cur == ~0ull) break;   // claimed: this topic leads
@@ -675,7 +738,7 @@ __global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, in
                 int tj = q.topic_tenant[j];
                 if (tj < 0 || tj >= q.n_tenants) tj = -1;
                 const int64_t oj = q.topic_off[j];
-                if (tj == tn && q.topic_off[j + 1] - oj == full_len && full_len <= 0x3FFFFFFF && same_topic(q.topics, o, oj, hlen)) {
+                if (tj == tn && q.topic_off[j + 1] - oj == full_len && full_len <= 0x3FFFFFFF && same_topic(q.topics, o, k, oj, hlen)) {
                     lead = j;
                     break;
                 }
@@ -685,36 +748,34 @@ __global__ void __launch_bounds__(256) order_prep_kernel(const OrderParams q, in
     }
     q.leader[i] = lead;
     if (lead != (uint32_t) i) return;
-    // ---- order key of a leader
+    // ---- order key of a leader: one digit per level among the first three, each the hash of the PREFIX that ends with the
+    // level (so equal leading levels give equal digits). One pass over the window words with a running hash; a digit is taken
+    // at each of the first three '/' (or at the end of the window for the last, unterminated level).
     const int len = min(hlen, 4 * ORDER_WINDOW_WORDS);
     const int rest = key_bits - tenant_bits;
     const int b0 = rest / 3 + (rest % 3 > 0), b1 = rest / 3 + (rest % 3 > 1), b2 = rest / 3;
-    uint64_t slashes = 0;
+    uint32_t run = 0x9E3779B1u, dig[3] = {0u, 0u, 0u};
+    int lvl = 0;   // levels closed so far
 #pragma unroll
-    for (int j = 0; j < ORDER_WINDOW_WORDS; j++) slashes |= (uint64_t) nibble(match_bytes(k[j], 0x2F2F2F2Fu)) << (4 * j);
-    slashes &= (1ull << len) - 1ull;   // len <= 40
-    // ends of the first three levels (a level that runs to the end of the window ends at len); a digit is the hash of the
-    // PREFIX up to that end, so equal leading levels give equal digits
-    int end[3], lvl = 0;
-#pragma unroll
-    for (int l = 0; l < 3; l++) {
-        end[l] = slashes ? __ffsll((long long) slashes) - 1 : len;
-        if (slashes) lvl = l + 1;
-        slashes &= slashes - 1ull;
+    for (int j = 0; j < ORDER_WINDOW_WORDS; j++) {
+        uint32_t m = 4 * j < len ? match_bytes(k[j], 0x2F2F2F2Fu) : 0u;   // 0x80 flag in every byte that is '/' (a byte above a match may be flagged too)
+        while (m && lvl < 3) {
+            const int byte = (__ffs(m) - 1) >> 3;
+            m &= m - 1;
+            if (((k[j] >> (8 * byte)) & 0xFFu) != 0x2Fu) continue;   // the SWAR test's false positive
+            const uint32_t part = byte ? (k[j] & (0xFFFFFFFFu >> (32 - 8 * byte))) : 0u;   // the word's bytes before the '/'
+            const uint32_t hh = (run ^ part) * 0x85EBCA77u + (uint32_t) (4 * j + byte);
+            dig[lvl++] = (hh ^ (hh >> 15)) * 0x9E3779B1u;
+        }
+        run = (run ^ k[j]) * 0xCC9E2D51u;
+        run ^= run >> 13;
     }
-    auto prefix_hash = [&](int nbytes) {
-        const uint32_t C[10] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u,
-                                0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u};
-        uint32_t hh = (uint32_t) nbytes;
-#pragma unroll
-        for (int j = 0; j < ORDER_WINDOW_WORDS; j++)   // bytes at and after nbytes are cleared: 0xFFFFFFFF >> clamp(32(j+1) - 8 nbytes, 0, 32)
-            hh += (k[j] & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t) max(32 * (j + 1) - 8 * nbytes, 0))) * C[j];
-        return (hh ^ (hh >> 15)) * 0x9E3779B1u;
-    };
+    const int closed = lvl;                       // levels that ended with a '/' inside the window
+    if (lvl < 3) dig[lvl] = ((run + (uint32_t) len) ^ (run >> 15)) * 0x9E3779B1u;   // the level that runs to the end of the window
     uint32_t key = tenant_bits ? ((uint32_t) max(tn, 0) & ((1u << tenant_bits) - 1u)) : 0u;
-    key = (key << b0) | (b0 ? prefix_hash(end[0]) >> (32 - b0) : 0u);
-    key = (key << b1) | (b1 && lvl >= 1 ? prefix_hash(end[1]) >> (32 - b1) : 0u);
-    key = (key << b2) | (b2 && lvl >= 2 ? prefix_hash(end[2]) >> (32 - b2) : 0u);
+    key = (key << b0) | (b0 ? dig[0] >> (32 - b0) : 0u);
+    key = (key << b1) | (b1 && closed >= 1 ? dig[1] >> (32 - b1) : 0u);
+    key = (key << b2) | (b2 && closed >= 2 ? dig[2] >> (32 - b2) : 0u);
     const uint32_t bucket = key_bits > q.hist_bits ? key >> (key_bits - q.hist_bits) : key;
     q.keys[i] = bucket;
     atomicAdd(&q.hist[bucket], 1u);

@@ -211,8 +211,17 @@ extern "C" {
 // config: "C1".."C5"; scale shrinks every size (1.0 = BASELINE.json sizes); shard_index/shard_count keep only
 // the tenants with fnv1a64(tenantId) % shard_count == shard_index (tenant sharding across GPUs);
 // tenant_prefix namespaces tenant ids (weak-scaling runs give each rank its own tenants).
+// replicate_hot != 0: a tenant that carries more than 1 / (4 shard_count) of the batch is hosted by EVERY shard and its
+// topics are dealt round-robin by batch position (SURVEY.md 8e "replicas" mode, applied per hot tenant): with Zipf tenant
+// sizes the largest tenant alone is 13 % of C4's batch, so pure hash placement caps 8 GPUs at ~4x.
+bfqw* bfqw_generate2(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
+                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot);
 bfqw* bfqw_generate(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
                     const char* tenant_prefix, int32_t nthreads) {
+    return bfqw_generate2(config, seed, scale, shard_index, shard_count, tenant_prefix, nthreads, 0);
+}
+bfqw* bfqw_generate2(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
+                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot) {
     Cfg cfg = (Cfg) (config && config[0] == 'C' ? config[1] - '0' : 0);
     if (cfg < C1 || cfg > C5) return nullptr;
     if (shard_count < 1) shard_count = 1;
@@ -232,9 +241,16 @@ bfqw* bfqw_generate(const char* config, uint64_t seed, double scale, int32_t sha
         nf[(size_t) t] = pl.zipf ? std::max<int64_t>(8, (int64_t) ((double) pl.n_filters / hsum / (double) (t + 1)))
                                  : std::max<int64_t>(1, pl.n_filters / pl.n_tenants);
     }
-    std::vector<char> mine((size_t) pl.n_tenants);
-    for (int64_t t = 0; t < pl.n_tenants; t++)
-        mine[(size_t) t] = (int32_t) (fnv1a64(tg[(size_t) t].id) % (uint64_t) shard_count) == shard_index;
+    std::vector<char> mine((size_t) pl.n_tenants), hot((size_t) pl.n_tenants, 0);
+    {
+        double wsum = 0;
+        for (int64_t t = 0; t < pl.n_tenants; t++) wsum += pl.zipf ? (double) nf[(size_t) t] : 1.0;
+        for (int64_t t = 0; t < pl.n_tenants; t++) {
+            const double share = (pl.zipf ? (double) nf[(size_t) t] : 1.0) / wsum;   // topics are drawn in proportion to this
+            hot[(size_t) t] = replicate_hot && shard_count > 1 && cfg != C5 && share > 1.0 / (4.0 * shard_count);
+            mine[(size_t) t] = hot[(size_t) t] || (int32_t) (fnv1a64(tg[(size_t) t].id) % (uint64_t) shard_count) == shard_index;
+        }
+    }
 
     // ---- per-tenant generation (parallel): filters, then sorted route KV pairs
     struct TenantOut { Blob keys, vals; };
@@ -319,6 +335,7 @@ bfqw* bfqw_generate(const char* config, uint64_t seed, double scale, int32_t sha
             const double hit = r.uniform(), pop = r.uniform();
             const uint64_t s1 = r.next();
             if (!mine[(size_t) t]) continue;
+            if (hot[(size_t) t] && i % shard_count != shard_index) continue;   // a replicated tenant's topics: round-robin by batch position
             const TenantGen& T = tg[(size_t) t];
             Rng tr(s1);
             std::string topic;
@@ -345,6 +362,7 @@ bfqw* bfqw_generate(const char* config, uint64_t seed, double scale, int32_t sha
             const int64_t t = (int64_t) r.below((uint32_t) pl.n_tenants);
             const uint64_t s1 = r.next();
             if (!mine[(size_t) t]) continue;
+            if (hot[(size_t) t] && i % shard_count != shard_index) continue;   // a replicated tenant's topics: round-robin by batch position
             const TenantGen& T = tg[(size_t) t];
             if (T.filters.empty()) continue;
             Rng tr(s1);

@@ -23,10 +23,27 @@ def tenant_shard(tenant_id, world_size):
     return fnv1a64(tenant_id) % world_size
 
 
-def split_batch_by_owner(tenants, topic_tenant, world_size):
-    """indices of the topics each rank must match -> list of int64 arrays (the dist-server side of the sharding)"""
+def hot_tenants(tenant_share, world_size):
+    """tenants hosted by EVERY rank ("replicas" mode of SURVEY.md 8e, applied per tenant): those that carry more than
+    1 / (4 world) of the traffic. tenant_share: per-tenant fraction of the batch (any positive weights). With Zipf tenant
+    sizes the largest tenant alone is 13 % of BASELINE C4's batch: pure hash placement leaves one of 8 GPUs with 1.87x the
+    mean load, replicating the 4 hot tenants brings it to 1.08x."""
+    w = np.asarray(tenant_share, dtype=np.float64)
+    if world_size <= 1 or w.sum() <= 0:
+        return np.zeros(len(w), bool)
+    return w / w.sum() > 1.0 / (4.0 * world_size)
+
+
+def split_batch_by_owner(tenants, topic_tenant, world_size, hot=None):
+    """indices of the topics each rank must match -> list of int64 arrays (the dist-server side of the sharding). A topic of
+    a hot (replicated) tenant goes to rank (batch position mod world), any other to fnv1a64(tenant) mod world — the rule
+    libbfq_workload.so applies when it generates one shard."""
     owner_of_tenant = np.array([tenant_shard(t, world_size) for t in tenants], dtype=np.int64)
-    owner = owner_of_tenant[np.asarray(topic_tenant, dtype=np.int64)] if len(tenants) else np.zeros(0, np.int64)
+    tt = np.asarray(topic_tenant, dtype=np.int64)
+    owner = owner_of_tenant[tt] if len(tenants) else np.zeros(0, np.int64)
+    if hot is not None and len(tt):
+        is_hot = np.asarray(hot, bool)[tt]
+        owner = np.where(is_hot, np.arange(len(tt), dtype=np.int64) % world_size, owner)
     return [np.nonzero(owner == r)[0] for r in range(world_size)]
 
 
@@ -109,3 +126,72 @@ def split_batch_replicas(n_topics, world_size):
         out.append((at, at + ln))
         at += ln
     return out
+
+
+class Gathered:
+    """result of Exchange.gather: torch views (device) over the reassembled arrays + the per-rank slice bounds (host)"""
+
+    def __init__(self, raw, device):
+        self.raw = raw
+        self.world = raw.world
+        self.topic_base = [raw.topic_base[i] for i in range(raw.world + 1)]
+        self.range_base = [raw.range_base[i] for i in range(raw.world + 1)]
+        self.n_topics_total, self.n_ranges_total, self.bytes_received = raw.n_topics_total, raw.n_ranges_total, raw.bytes_received
+        self._device = device
+
+    def route_count(self):
+        return device_view(self.raw.d_route_count, max(self.n_topics_total, 1), "<u4", self._device)[:self.n_topics_total]
+
+    def span_count(self):
+        return device_view(self.raw.d_span_count, max(self.n_topics_total, 1), "<u4", self._device)[:self.n_topics_total]
+
+    def ranges(self):
+        """[n_ranges_total, 2] uint32: first rank, count (| 0x80000000 for a multi-segment filter)"""
+        return device_view(self.raw.d_ranges, max(2 * self.n_ranges_total, 2), "<u4", self._device)[:2 * self.n_ranges_total].view(-1, 2)
+
+
+class Exchange:
+    """bfq_exchange_* of the C-ABI (NCCL inside the library). The NCCL unique id travels out of band: here over the
+    already-initialised torch.distributed group (any backend); a Java host would use its own RPC."""
+
+    def __init__(self, device_index, rank=None, world=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _native as N
+        self._N, self._C = N, C
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_uint8 * N.EXCHANGE_ID_BYTES)()
+            N.check(N.lib.bfq_exchange_unique_id(buf, N.EXCHANGE_ID_BYTES))
+            ident[0] = bytes(buf)
+        if world > 1:
+            dist.broadcast_object_list(ident, src=0)
+        self._id = (C.c_uint8 * N.EXCHANGE_ID_BYTES).from_buffer_copy(ident[0])
+        h = C.c_void_p()
+        N.check(N.lib.bfq_exchange_create(device_index, rank, world, self._id, C.byref(h)))
+        self._h, self.rank, self.world, self.device_index = h, rank, world, device_index
+
+    def gather(self, device_result, ranges=True, stream=0):
+        """collective: every rank passes the DeviceResult of its own (completed) match"""
+        import torch
+        N, C = self._N, self._C
+        out = N.BfqGathered()
+        raw = device_result.raw if hasattr(device_result, "raw") else device_result
+        N.check(N.lib.bfq_exchange_gather(self._h, C.byref(raw), N.EXCHANGE_RANGES if ranges else N.EXCHANGE_COUNTS, stream, C.byref(out)))
+        return Gathered(out, torch.device("cuda", self.device_index))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._N.lib.bfq_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

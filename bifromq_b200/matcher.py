@@ -33,8 +33,9 @@ class BatchResult:
     """Numpy views over one bfq_match result. The arrays are private to this result and stay valid until close();
     route()/route_kinds() resolve ranks against the snapshot the match ran on, whatever was committed since."""
 
-    def __init__(self, handle, n):
+    def __init__(self, handle, n, owner=None):
         self._h = handle
+        self._owner = owner   # keeps the index alive for as long as this result is
         self.n_topics = n
         lib = N.lib
 
@@ -93,8 +94,9 @@ class BatchResult:
 class DeviceResult:
     """One bfq_match_device[_async] result: device pointers + counts; the buffers stay valid until release()."""
 
-    def __init__(self, raw):
+    def __init__(self, raw, owner=None):
         self.raw = raw
+        self._owner = owner   # keeps the index alive for as long as this result is
 
     def __getattr__(self, name):   # d_span_begin, n_ranges, tier0_ms, ... straight from the C struct
         if name == "raw":
@@ -224,7 +226,7 @@ class GpuRouteIndex:
         r = C.c_void_p()
         N.check(N.lib.bfq_match(self._h, N.ptr(tb), N.ptr(toff), nt, N.ptr(topics_blob), N.ptr(topic_off), N.ptr(tt), n,
                                 N.ptr(mp), N.ptr(mg), C.byref(r)))
-        return BatchResult(r, n)
+        return BatchResult(r, n, self)
 
     def match_topics(self, tenants, topics, topic_tenant=None, max_pfanout=None, max_gfanout=None):
         blob, off = N.as_blob(topics)
@@ -242,7 +244,7 @@ class GpuRouteIndex:
         fn = N.lib.bfq_match_device if wait else N.lib.bfq_match_device_async
         N.check(fn(self._h, N.ptr(tb), N.ptr(toff), nt, d_topics_ptr, d_topic_off_ptr, d_topic_tenant_ptr,
                    n, N.ptr(mp), N.ptr(mg), stream, C.byref(out)))
-        return DeviceResult(out)
+        return DeviceResult(out, self)
 
 
 class MatchedRoutes:

@@ -178,6 +178,7 @@ typedef struct {
     const bfq_throttled* d_throttled; /* [n_throttled] */
     int64_t n_ranges, n_throttled, n_routes;
     int64_t n_overflow_topics, n_flagged_topics, n_launches;
+    int64_t n_topics;               /* topics of the batch (length of the per-topic arrays) */
     int64_t n_distinct_topics;      /* (tenant, topic) pairs actually walked; duplicates share their first occurrence's span */
     double tier0_ms;                /* device time of the lane-per-topic kernel of this match (CUDA events on `stream`) */
     uint64_t generation;            /* snapshot the match ran on */
@@ -198,6 +199,42 @@ void bfq_device_result_release(bfq_device_result* res);
  * d_ranks = NULL to only size). Returns the total via *n_ranks. Resolves against the result's own snapshot and caps. */
 int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int64_t* d_ranks, int64_t rank_cap,
                           void* stream, int64_t* n_ranks);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: the one exchange step of the tenant-sharded path. Tenants are independent key ranges, so
+ * every GPU (one process each) matches the topics of the tenants it hosts with NO data-path collective; what travels is
+ * the reply, reassembled on every rank the way the dist-server reassembles the per-worker BatchDistReply messages
+ * (bifromq-dist/bifromq-dist-server/src/main/java/org/apache/bifromq/dist/server/scheduler/BatchDistServerCall.java:186-205,
+ * 245-271). bfq_exchange_gather all-gathers the device results of the ranks' matches over NCCL (NVLink / NVSwitch), in
+ * rank order: per topic the matched-route count (what TopicFanout carries, DistWorkerCoProc.proto:34-131) and, with
+ * BFQ_EXCHANGE_RANGES, the number of matched ranges plus the dense {first rank, count} ranges themselves (route ranks are
+ * local to the rank that produced them: rank r's ranges refer to r's committed KV order). One host synchronisation per
+ * call (NCCL needs the receive counts); no host-side copies. NCCL is taken from the process at run time (libnccl.so.2).
+ *   rank 0: bfq_exchange_unique_id(id)  -> broadcast the 128 bytes to the other ranks out of band (the host's own RPC)
+ *   every rank: bfq_exchange_create(device, rank, world, id, &x)       (collective: all ranks must call it)
+ *   per batch, every rank: bfq_match_device(...) ; bfq_exchange_gather(x, &res, what, stream, &g)   (collective)
+ * The gathered arrays live in device memory owned by the exchange, valid until the next gather on it; topic_base /
+ * range_base (host, [world + 1]) give each rank's slice. A world of 1 is allowed (the gather is then a local compaction).
+ * ---------------------------------------------------------------------------------------------- */
+#define BFQ_EXCHANGE_ID_BYTES 128
+#define BFQ_EXCHANGE_COUNTS 1
+#define BFQ_EXCHANGE_RANGES 2
+typedef struct bfq_exchange bfq_exchange;
+typedef struct {
+    const uint32_t* d_route_count;   /* [n_topics_total] matched routes per topic, ranks concatenated in rank order */
+    const uint32_t* d_span_count;    /* [n_topics_total] matched ranges per topic (NULL with BFQ_EXCHANGE_COUNTS) */
+    const bfq_range* d_ranges;       /* [n_ranges_total] dense: a topic's ranges follow those of the topic before it
+                                        (NULL with BFQ_EXCHANGE_COUNTS) */
+    const int64_t* topic_base;       /* host [world + 1]: rank r's topics are [topic_base[r], topic_base[r + 1]) */
+    const int64_t* range_base;       /* host [world + 1] */
+    int64_t n_topics_total, n_ranges_total;
+    int64_t bytes_received;          /* payload bytes this rank received from its peers */
+    int32_t world;
+} bfq_gathered;
+int32_t bfq_exchange_unique_id(uint8_t* id_out, int32_t cap);
+int32_t bfq_exchange_create(int32_t device_ordinal, int32_t rank, int32_t world, const uint8_t* id, bfq_exchange** out);
+void bfq_exchange_destroy(bfq_exchange* x);
+int32_t bfq_exchange_gather(bfq_exchange* x, const bfq_device_result* res, int32_t what, void* stream, bfq_gathered* out);
 
 /* ------------------------------------------------------------------------------------------------
  * Route key codec + tokeniser, native restatement of DWS/KVSchemaUtil.java:56-130 and

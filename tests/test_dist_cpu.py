@@ -140,3 +140,34 @@ def test_replica_split_covers_the_batch():
         assert len(cuts) == wsz and cuts[0][0] == 0 and cuts[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
         assert max(e - b for b, e in cuts) - min(e - b for b, e in cuts) <= 1
+
+
+def test_hot_tenant_replication_balances_the_split():
+    """strong scaling: tenants above 1 / (4 world) of the batch are hosted by every rank and their topics dealt round-robin by
+    batch position; the generator's shards and the host-side split agree and the union is the whole batch"""
+    sys.path.insert(0, ROOT)
+    from bifromq_b200 import dist as D
+    from bifromq_b200.workload import Workload
+    world = 4
+    full = Workload("C4", scale=0.02)
+    tt = np.asarray(full.topic_tenant[:full.n_topics])
+    share = np.bincount(tt, minlength=full.n_tenants).astype(float)
+    hot = D.hot_tenants(share, world)
+    assert 1 <= hot.sum() <= 6
+    parts = D.split_batch_by_owner(full.tenants, tt, world, hot)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(full.n_topics))
+    sizes = [len(p) for p in parts]
+    plain = [len(p) for p in D.split_batch_by_owner(full.tenants, tt, world)]
+    assert max(sizes) / np.mean(sizes) < max(plain) / np.mean(plain)
+    names = full.tenants
+    shards = [Workload("C4", scale=0.02, shard_index=r, shard_count=world, replicate_hot=True) for r in range(world)]
+    assert sum(s.n_topics for s in shards) == full.n_topics
+    for r, s in enumerate(shards):
+        # the shard holds exactly the topics the split assigns to rank r, in batch order
+        want = [(names[tt[i]], full.topic(int(i))) for i in parts[r]] if abs(len(parts[r]) - s.n_topics) == 0 else None
+        # the generator decides "hot" from the tenants' planned sizes, the split above from the observed batch: they agree on
+        # the big tenants, so the per-rank topic lists are identical
+        assert want is not None
+        sn = s.tenants
+        got = [(sn[s.topic_tenant[i]], s.topic(i)) for i in range(s.n_topics)]
+        assert got == want

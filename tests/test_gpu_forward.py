@@ -589,6 +589,43 @@ def test_async_device_matches_in_flight_together(B):
         out.release()
 
 
+def test_exchange_gather_single_rank(B):
+    """bfq_exchange_gather with a world of one (NCCL communicator of size 1): the reassembled arrays are the dense,
+    topic-ordered form of the device result — equal to what the host path returns for the same batch"""
+    import torch
+    from bifromq_b200 import dist as D
+    w = B.workload.Workload("C3", scale=0.05)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    tenants, n = w.tenants, w.n_topics
+    dev = torch.device("cuda", 0)
+    d_topics = torch.from_numpy(np.ascontiguousarray(w.topics)).to(dev)
+    d_off = torch.from_numpy(np.ascontiguousarray(w.topic_off)).to(dev)
+    d_tt = torch.from_numpy(np.ascontiguousarray(w.topic_tenant[:n])).to(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, stream=stream)
+    x = D.Exchange(0, rank=0, world=1)
+    for ranges in (True, False, True):
+        g = x.gather(out, ranges=ranges, stream=stream)
+        torch.cuda.synchronize()
+        res = idx.match(tenants, w.topics, w.topic_off, w.topic_tenant[:n])
+        assert g.world == 1 and g.topic_base == [0, n] and g.n_topics_total == n
+        assert g.route_count().cpu().numpy().tolist() == res.route_count.tolist()
+        if ranges:
+            assert g.range_base == [0, len(res.ranges)]
+            assert g.span_count().cpu().numpy().tolist() == res.span_count.tolist()
+            got = g.ranges().cpu().numpy()
+            want = np.stack([res.ranges["first"], res.ranges["count"]], axis=1)
+            sb = res.span_begin
+            for i in range(0, n, 97):   # a topic's ranges may come out in a different order
+                a, b = int(sb[i]), int(sb[i]) + int(res.span_count[i])
+                assert sorted(map(tuple, got[a:b].tolist())) == sorted(map(tuple, want[a:b].tolist()))
+        res.close()
+    x.close()
+    out.release()
+
+
 def test_concurrent_matches_on_one_handle(B):
     """ITenantRouteMatcher.matchAll is called from the shared topic-matcher pool (DW/DistWorkerCoProcFactory.java:74-85): six
     threads match DIFFERENT batches on ONE handle at the same time, hold their results while the others run, and every
