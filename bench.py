@@ -29,18 +29,26 @@ METRIC = "publish-topics matched/sec @10M filters"
 UNIT = "topics/s"
 
 
+def metric_name(args):
+    """BASELINE.json's metric is quoted on C4 (10M filters); the other forward configs carry their own filter count"""
+    return {"C1": "publish-topics matched/sec @10k filters (BASELINE config C1)", "C2": "publish-topics matched/sec @1M filters, 1 tenant (BASELINE config C2)",
+            "C3": "publish-topics matched/sec @10M filters, 1000 tenants x 10k (BASELINE config C3)"}.get(args.config, METRIC)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="C4 is the headline (and the default); C5 = the inverse path (retained topics matched BY wildcard filters)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a bench number)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1 only. strong (default): ONE filter set tenant-sharded over the ranks, the same batch split by owner, the "
                          "results all-gathered inside the timed step; weak: every rank hosts its own full-size set")
     ap.add_argument("--no-replicate-hot", action="store_true", help="strong scaling: pure hash placement, no replicas of hot tenants")
+    ap.add_argument("--retain-limit", type=int, default=10, help="C5: ids returned per filter (RetainMessageMatchLimit default 10; -1 = unlimited)")
     ap.add_argument("--exchange", default="ranges", choices=["ranges", "counts", "none"], help="N > 1: what the timed step all-gathers")
     ap.add_argument("--cpu-sample", type=int, default=0, help="topics in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,9 +305,139 @@ def run_cpu_baseline(w, args, mode_name, cached=False):
     return res, stats, n, float(poff[-1] - poff[0]) if not cached else None
 
 
+def inverse_cpu_baseline(w, ids):
+    """the oracle's TopicLevelTrie restatement (U/index/TopicLevelTrie.java:190-249 + RetainTopicIndex's selectors) over the same
+    1M retained topics, every query filter, all host cores; also counts the trie nodes the lookups visit (V of SURVEY.md 8d)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    orc = O.TopicLevelIndex()
+    tenants = w.tenants
+    tl = w.topic_list()
+    for i in range(w.n_topics):
+        orc.add(tl[i], int(ids[i]), tenants[w.topic_tenant[i]])
+    n = w.n_query_filters
+    tb, toff = O.blob(tenants)
+    counts = np.zeros(n, np.int64)
+    vis = np.zeros(1, np.uint64)
+    ft = np.ascontiguousarray(w.filter_tenant[:n])
+    fo = np.ascontiguousarray(w.filter_off[:n + 1])
+    passes = []
+    for _ in range(5):
+        dt, reps = 0.0, 0
+        while dt < 1.0 and reps < 64:
+            t0 = time.perf_counter()
+            O.lib.orc_tli_match_batch(orc.h, tb.ctypes.data, toff, ft.ctypes.data, w.filters.ctypes.data, fo, n, cores, counts, vis.ctypes.data)
+            dt += time.perf_counter() - t0
+            reps += 1
+        passes.append(dt / reps)
+    dt = float(np.median(passes))
+    return ({"value": n / dt, "unit": "filters/s", "cores": cores, "kind": "port",
+             "sample": "C5: all %d query filters against the %d retained topics; oracle restatement of TopicLevelTrie.lookup with RetainTopicIndex's "
+                       "selectors, std::thread x %d, unlimited results; median of 5 passes of >= 1 s (%.3f s per batch)" % (n, w.n_topics, cores, dt)},
+            int(vis[0]), int(counts.sum()))
+
+
+def main_inverse(args, rank, world, local):
+    """BASELINE config C5: RetainStoreCoProc.match's index lookup (RS/RetainStoreCoProc.java:167-190 over
+    RS/index/RetainTopicIndex.java:36-124) — 1M retained topics matched BY 100k wildcard SUBSCRIBE filters. The C-ABI of this
+    direction takes host buffers only (bfq_rmatch), so `value` is the DEVICE time of its kernels, measured by the library with
+    CUDA events on the call's stream from "inputs enqueued" to "ids expanded" (bfq_rresult_timings[4]), and `e2e` is the wall
+    time of the whole call (H2D + kernels + D2H of the ids)."""
+    import torch
+
+    import bifromq_b200
+    from bifromq_b200 import retain
+    bifromq_b200.load_library()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
+    w = make_workload(args, 0, 1)
+    idx = retain.GpuTopicMatchIndex(local)
+    tenants = w.tenants
+    t0 = time.perf_counter()
+    ids = idx.add_blobs(tenants, w.topics, w.topic_off, w.topic_tenant[:w.n_topics])
+    idx.commit()
+    t_build = time.perf_counter() - t0
+    n = w.n_query_filters
+    limit = np.full(n, args.retain_limit, np.int64) if args.retain_limit >= 0 else None
+    f_blob = torch.from_numpy(np.ascontiguousarray(w.filters)).pin_memory().numpy()
+    f_off = torch.from_numpy(np.ascontiguousarray(w.filter_off[:n + 1])).pin_memory().numpy()
+    f_tt = torch.from_numpy(np.ascontiguousarray(w.filter_tenant[:n])).pin_memory().numpy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        idx.match_blobs(tenants, f_blob, f_off, f_tt, limit)
+    torch.cuda.synchronize(dev)
+    sampler.begin()
+    dev_ms, k_ms, wall, last = [], [], [], None
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        last = idx.match_blobs(tenants, f_blob, f_off, f_tt, limit)
+        wall.append(time.perf_counter() - t0)
+        dev_ms.append(last.timings_ms["device_all_kernels"])
+        k_ms.append(last.timings_ms["device_rmatch_kernel"])
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
+    unl = idx.match_blobs(tenants, f_blob, f_off, f_tt, None)
+    if numa:
+        try:
+            os.sched_setaffinity(0, numa["previous"])
+        except Exception:
+            pass
+    if rank != 0:
+        return
+    total_dev = float(sum(dev_ms)) / 1000.0
+    value = n * args.steps / total_dev
+    e2e = n * args.steps / float(sum(wall))
+    fbytes = int(w.filter_off[n] - w.filter_off[0])
+    line = {"metric": "retained-topic SUBSCRIBE filters matched/sec @1M retained topics (inverse path, BASELINE config C5)", "value": value,
+            "unit": "filters/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1000.0 * total_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (byte and integer work)", "data": "synthetic",
+            "config": {"workload": workload_name(args, w), "retained_topics": w.n_topics, "filters_per_step": n, "tenants": w.n_tenants,
+                       "limit": "RetainMessageMatchLimit = %d per filter" % args.retain_limit if args.retain_limit >= 0 else "unlimited",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)", "build_s": round(t_build, 1),
+                       "value_is": "device time of the call's kernels (CUDA events inside bfq_rmatch), inputs enqueued before the first event"},
+            "e2e": {"value": e2e, "unit": "filters/s", "h2d_bytes_per_step": fbytes + 8 * (n + 1) + 4 * n + (8 * n if limit is not None else 0),
+                    "d2h_bytes_per_step": 24 * n + 8 * int(len(last.ids)), "last_step_breakdown_ms": {k: round(v, 3) for k, v in last.timings_ms.items()}},
+            "gpu_launches": 5 * args.steps, "ids_returned_per_step": int(len(last.ids)), "matches_total_per_step": int(last.totals.sum()),
+            "unlimited": {"ids_returned": int(len(unl.ids)), "device_ms": unl.timings_ms["device_all_kernels"], "wall_ms": unl.timings_ms["total"],
+                          "filters_per_s_e2e": n / (unl.timings_ms["total"] / 1000.0)},
+            "tier2_filters_per_step": last.n_overflow_filters, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        base, visited, matches = inverse_cpu_baseline(w, ids)
+        # SURVEY.md 8(d), inverse path: per filter  len + 4 + 32 V + 8 ranges, V = topic-trie nodes the reference's lookup visits
+        # (counted by the oracle), ranges = rank ranges the kernel emits (a '#' subtree or a final '+' level is ONE range)
+        alg = fbytes + 4 * n + 32 * visited + 8 * last.n_ranges
+        k = float(np.mean(k_ms))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = alg / (k / 1000.0) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
+                            "kernel": "rmatch_kernel (one warp per filter over the BFS-numbered topic trie)", "kernel_ms": k,
+                            "alg_bytes_per_filter": alg / n, "alg_counters_per_filter": {"V": visited / n, "ranges": last.n_ranges / n},
+                            "note": "V counted by the oracle over all %d filters; the reference's lookup visits EVERY child of a '+' level "
+                                    "(TopicLevelTrie.java:200-249) while the kernel maps a '+' level to one id interval, so the achieved "
+                                    "figure can exceed what the kernel really moves" % n,
+                            "counts_check": {"oracle_matches": matches, "gpu_matches": int(unl.totals.sum()), "equal": matches == int(unl.totals.sum())}}
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
+    if args.config == "C5" and args.impl != "reference":
+        return main_inverse(args, rank, world, local)
     if world != args.gpus and world > 1:
         args.gpus = world
     if args.scaling is None:
@@ -312,10 +450,20 @@ def main():
         if rank != 0:
             return
         w = make_workload(args, 0, 1)
+        if args.config == "C5":
+            base, visited, matches = inverse_cpu_baseline(w, np.arange(w.n_topics))
+            v = base["value"]
+            print(json.dumps({"metric": "retained-topic SUBSCRIBE filters matched/sec @1M retained topics (inverse path, BASELINE config C5)",
+                              "value": v, "unit": "filters/s", "n_gpus": args.gpus, "steps": 5, "warmup": 1, "ms_per_step": 1000.0 * w.n_query_filters / v,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (byte and integer work)",
+                              "data": "synthetic", "impl": "reference", "config": {"workload": workload_name(args, w),
+                              "note": "C++ restatement of the Java reference, not the JVM (no JDK in the image)"}, "cpu_baseline": base,
+                              "e2e": {"value": v, "unit": "filters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+            return
         base, _, n, _ = run_cpu_baseline(w, args, "reference")
         cached, _, _, _ = run_cpu_baseline(w, args, "reference", cached=True)
         v = base["value"]
-        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 5, "warmup": 1,
+        line = {"metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 5, "warmup": 1,
                 "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic", "impl": "reference",
                 "config": {"workload": workload_name(args, w), "note": "C++ restatement of the Java reference, not the JVM (no JDK in the image)"},
@@ -501,7 +649,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only (at N > 1 `w` is one shard)
             cpu_base, st, ns, sample_topic_bytes = run_cpu_baseline(w, args, "trie")
             roof = make_roofline(sample_topic_bytes, st, ns, n, k_ms, ranges_per_batch, routes_per_batch, {"config": args.config})
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic",
                 "config": {"workload": workload_name(args, w), "routes_per_gpu": w.n_routes, "filters_per_gpu": w.n_filters,
@@ -547,7 +695,8 @@ def main():
 def workload_name(args, w):
     names = {"C1": "C1: 1 tenant, 10k exact filters, 1k topics", "C2": "C2: 1 tenant, 1M filters (50% '+'), 100k-topic batch",
              "C3": "C3: 1000 tenants x 10k filters mixed +/#, 1M-topic batch",
-             "C4": "C4: 10M filters over 1000 tenants (Zipf sizes, Zipf fan-out and topic popularity), 1M-topic batch"}
+             "C4": "C4: 10M filters over 1000 tenants (Zipf sizes, Zipf fan-out and topic popularity), 1M-topic batch",
+             "C5": "C5: retain-store inverse match, 1M retained topics vs 100k wildcard SUBSCRIBE filters"}
     s = names[args.config]
     if args.scale != 1.0:
         s += " [scale %.4g — NOT a valid bench size]" % args.scale

@@ -442,13 +442,14 @@ struct DBuf {
 
 struct bfq_rresult {
     std::vector<int64_t> offsets, ids, totals;
-    double ms[4] = {0, 0, 0, 0};
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct bfq_rindex {
     int device = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] around all kernels of a match, [2,3] around rmatch_kernel
     // staging: (tenant, topic) -> id ; id -> (tenant, topic)
     std::map<std::pair<std::string, std::string>, int64_t> staged;
     std::vector<std::pair<std::string, std::string>> by_id;   // id -> strings (tombstones keep their slot)
@@ -477,6 +478,7 @@ struct bfq_rindex {
         d_scan_tmp.release(); d_filter_off.release(); d_limit.release(); d_ids.release(); d_filter_tenant.release();
         d_tenant_root.release(); d_span_begin.release(); d_span_count.release(); d_overflow.release(); d_total.release();
         d_kept.release(); d_offsets.release(); d_counters.release(); d_ranges.release(); d_scratch.release();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -797,6 +799,9 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     RCUDA_TRY(cudaMemcpyAsync(h->d_tenant_root.p, troot.data(), nt * 4, cudaMemcpyHostToDevice, st));
     if (limit) RCUDA_TRY(cudaMemcpyAsync(h->d_limit.p, limit, (size_t) n * 8, cudaMemcpyHostToDevice, st));
     auto t1 = std::chrono::steady_clock::now();
+    for (auto& e : h->ev)
+        if (!e) RCUDA_TRY(cudaEventCreate(&e));
+    RCUDA_TRY(cudaEventRecord(h->ev[0], st));   // the inputs are (enqueued to be) resident: device time of the kernels from here
 
     RMatchParams p{};
     p.nodes = h->d_nodes.p;
@@ -824,7 +829,9 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
         p.n_work = 0;
         RCUDA_TRY(cudaMemsetAsync(h->d_counters.p, 0, sizeof(hc), st));
         int64_t ctas = std::min<int64_t>((n + R_WARPS - 1) / R_WARPS, (int64_t) sms * 4);
+        RCUDA_TRY(cudaEventRecord(h->ev[2], st));
         rmatch_kernel<false><<<(unsigned) std::max<int64_t>(ctas, 1), R_WARPS * 32, 0, st>>>(p);
+        RCUDA_TRY(cudaEventRecord(h->ev[3], st));
         h->launches++;
         RCUDA_TRY(cudaGetLastError());
         RCUDA_TRY(cudaMemcpyAsync(hc, h->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -878,6 +885,7 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
                                                                       h->d_bfs_to_id.p, h->d_ids.p);
     h->launches++;
     RCUDA_TRY(cudaGetLastError());
+    RCUDA_TRY(cudaEventRecord(h->ev[1], st));
     auto t2 = std::chrono::steady_clock::now();
     res->ids.resize((size_t) total_ids);
     if (total_ids) RCUDA_TRY(cudaMemcpyAsync(res->ids.data(), h->d_ids.p, (size_t) total_ids * 8, cudaMemcpyDeviceToHost, st));
@@ -893,6 +901,15 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     res->ms[1] = ms(t1, t2);
     res->ms[2] = ms(t2, t3);
     res->ms[3] = ms(t0, t3);
+    {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
+        res->ms[4] = a;                       // device time from "inputs resident" to "ids expanded" (all kernels + the host's counter reads between them)
+        res->ms[5] = b;                       // device time of rmatch_kernel (the last attempt)
+        res->ms[6] = (double) hc[RC_RANGES];  // rank ranges emitted (8 bytes each): the kernel's output size
+        res->ms[7] = (double) hc[RC_OVERFLOW];
+    }
     *out = res;
     return BFQ_OK;
 }
@@ -906,7 +923,7 @@ const int64_t* bfq_rresult_ids(const bfq_rresult* r, int64_t* n) {
 const int64_t* bfq_rresult_total_matches(const bfq_rresult* r) { return r->totals.data(); }
 int32_t bfq_rresult_timings(const bfq_rresult* r, double* ms, int32_t n) {
     if (!r || !ms) return rfail(BFQ_E_INVALID, "bad argument");
-    for (int32_t i = 0; i < n && i < 4; i++) ms[i] = r->ms[i];
+    for (int32_t i = 0; i < n && i < 8; i++) ms[i] = r->ms[i];
     return BFQ_OK;
 }
 void bfq_rresult_free(bfq_rresult* r) { delete r; }

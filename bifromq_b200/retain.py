@@ -29,9 +29,10 @@ class RMatchResult:
         p = lib.bfq_rresult_ids(handle, C.byref(nid))
         self.ids = arr(p, nid.value)
         self.totals = arr(lib.bfq_rresult_total_matches(handle), n)
-        ms = np.zeros(4, np.float64)
-        lib.bfq_rresult_timings(handle, ms.ctypes.data, 4)
-        self.timings_ms = dict(zip(["h2d", "kernels", "d2h", "total"], ms.tolist()))
+        ms = np.zeros(8, np.float64)
+        lib.bfq_rresult_timings(handle, ms.ctypes.data, 8)
+        self.timings_ms = dict(zip(["h2d", "kernels", "d2h", "total", "device_all_kernels", "device_rmatch_kernel"], ms[:6].tolist()))
+        self.n_ranges, self.n_overflow_filters = int(ms[6]), int(ms[7])
         lib.bfq_rresult_free(handle)
 
     def matches(self, i):

@@ -271,7 +271,11 @@ int32_t bfq_rindex_lookup(bfq_rindex* h, int64_t id, uint8_t* tenant_out, int64_
                           uint8_t* topic_out, int64_t topic_cap, int64_t* topic_len);
 /* match n filters; filter i is scoped to tenant filter_tenant[i]; limit[i] < 0 = unlimited, else at most
  * limit[i] ids are returned for filter i (RS/RetainStoreCoProc.java:167-190 stops after `limit` messages;
- * which ones is unspecified there too — it iterates a HashSet). */
+ * which ones is unspecified there too — it iterates a HashSet). NOTE: the reference applies its expiry filter INSIDE that
+ * loop (it keeps iterating until `limit` LIVE messages are found, RetainStoreCoProc.java:177-188), whereas this call
+ * truncates to `limit` topic ids before the caller has looked at any message: a caller that drops expired messages must
+ * ask for more than `limit` (total_matches tells how many exist) or pass limit < 0 and cut after its own expiry check.
+ * Thread-safe: calls on one handle are serialised, every result owns its arrays. */
 int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                    const uint8_t* filters, const int64_t* filter_off, const int32_t* filter_tenant, int64_t n_filters,
                    const int64_t* limit, bfq_rresult** out);
@@ -279,6 +283,9 @@ int64_t bfq_rresult_num_filters(const bfq_rresult* r);
 const int64_t* bfq_rresult_offsets(const bfq_rresult* r);            /* [n_filters+1] */
 const int64_t* bfq_rresult_ids(const bfq_rresult* r, int64_t* n);    /* topic ids, ascending per filter */
 const int64_t* bfq_rresult_total_matches(const bfq_rresult* r);      /* [n_filters] matches before the limit */
+/* ms[0..3]: wall time of the H2D section, the kernel section, the D2H section, the whole call; ms[4]: DEVICE time from
+ * "inputs resident" to "ids expanded" (CUDA events on the call's stream); ms[5]: device time of rmatch_kernel alone;
+ * ms[6]: rank ranges the kernel emitted (8 bytes each); ms[7]: filters that needed the global-scratch tier */
 int32_t bfq_rresult_timings(const bfq_rresult* r, double* ms, int32_t n);
 void bfq_rresult_free(bfq_rresult* r);
 
