@@ -36,6 +36,7 @@
 #include "codec.h"
 #include "trie_layout.h"
 #include "hash_probe.cuh"
+#include "match_kernels.cuh"
 
 using namespace bfq;
 
@@ -381,8 +382,9 @@ __global__ void __launch_bounds__(R_WARPS * 32) rmatch_kernel(const RMatchParams
                              (uint32_t) min((uint64_t) 0x3FFFFFFFull, p.scratch_frontier_cap),
                              (uint32_t) min((uint64_t) 0x3FFFFFFFull, p.scratch_ranges_cap));
     } else {
+        // p.work_list here = the locality order of the batch (filters grouped by tenant and leading levels), or nullptr
         for (int64_t it = gw; it < p.n_filters; it += nw)
-            rmatch_one<false>(p, ws, (uint32_t) it, lane, ws.fr[0], ws.fr[1], ws.rg, R_FR_CAP, R_RG_CAP);
+            rmatch_one<false>(p, ws, p.work_list ? p.work_list[it] : (uint32_t) it, lane, ws.fr[0], ws.fr[1], ws.rg, R_FR_CAP, R_RG_CAP);
     }
 }
 
@@ -470,6 +472,9 @@ struct bfq_rindex {
     DBuf<uint32_t> d_span_begin, d_span_count, d_overflow;
     DBuf<unsigned long long> d_total, d_kept, d_offsets, d_counters;
     DBuf<uint2> d_ranges, d_scratch;
+    // locality order of a batch of filters (match_kernels.cu: launch_order, without de-duplication)
+    DBuf<uint32_t> d_ord_keys, d_ord_leader, d_order, d_hist;
+    DBuf<unsigned long long> d_ord_ctr;
     int64_t launches = 0;
 
     ~bfq_rindex() {
@@ -478,6 +483,7 @@ struct bfq_rindex {
         d_scan_tmp.release(); d_filter_off.release(); d_limit.release(); d_ids.release(); d_filter_tenant.release();
         d_tenant_root.release(); d_span_begin.release(); d_span_count.release(); d_overflow.release(); d_total.release();
         d_kept.release(); d_offsets.release(); d_counters.release(); d_ranges.release(); d_scratch.release();
+        d_ord_keys.release(); d_ord_leader.release(); d_order.release(); d_hist.release(); d_ord_ctr.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -822,13 +828,51 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ctas_per_sm = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rmatch_kernel<false>, R_WARPS * 32, 0);
+    ctas_per_sm = std::max(1, ctas_per_sm);
+    // filters that share a tenant and leading levels walk the same part of the topic trie: group them so that the warps
+    // running at the same time hit the same node records in L2 (the forward path's locality order, reused)
+    const uint32_t* order = nullptr;
+    if (n >= 4096) {
+        const size_t buckets = order_hist_buckets(n, n_tenants);
+        const size_t hist_words = (buckets + 2 * (buckets / 4096) + 64 + 63) / 64 * 64;
+        RCUDA_TRY(h->d_ord_keys.reserve(nn));
+        RCUDA_TRY(h->d_ord_leader.reserve(nn));
+        RCUDA_TRY(h->d_order.reserve(nn));
+        RCUDA_TRY(h->d_hist.reserve(hist_words));
+        RCUDA_TRY(h->d_ord_ctr.reserve(CTR_COUNT));
+        OrderParams q{};
+        q.n_topics = n;
+        q.topics = h->d_filters.p;
+        q.topic_off = h->d_filter_off.p;
+        q.topic_tenant = h->d_filter_tenant.p;
+        q.n_tenants = n_tenants;
+        q.keys = h->d_ord_keys.p;
+        q.leader = h->d_ord_leader.p;
+        q.order = h->d_order.p;
+        q.hash_tab = nullptr;
+        q.hash_mask = 0;
+        q.hist = h->d_hist.p;
+        q.blk_tot = q.hist + buckets;
+        q.blk_pfx = q.blk_tot + buckets / 4096;
+        q.ticket = q.blk_pfx + buckets / 4096;
+        q.hist_bits = 0;
+        while (((size_t) 1 << q.hist_bits) < buckets) q.hist_bits++;
+        q.dedup = 0;
+        q.counters = h->d_ord_ctr.p;
+        RCUDA_TRY(cudaMemsetAsync(q.hist, 0, hist_words * sizeof(uint32_t), st));
+        RCUDA_TRY(launch_order(q, st));
+        h->launches += 3;
+        order = q.order;
+    }
     for (int attempt = 0; attempt < 8; attempt++) {
         p.ranges = h->d_ranges.p;
         p.ranges_cap = h->d_ranges.cap;
-        p.work_list = nullptr;
+        p.work_list = order;
         p.n_work = 0;
         RCUDA_TRY(cudaMemsetAsync(h->d_counters.p, 0, sizeof(hc), st));
-        int64_t ctas = std::min<int64_t>((n + R_WARPS - 1) / R_WARPS, (int64_t) sms * 4);
+        int64_t ctas = std::min<int64_t>((n + R_WARPS - 1) / R_WARPS, (int64_t) sms * ctas_per_sm);
         RCUDA_TRY(cudaEventRecord(h->ev[2], st));
         rmatch_kernel<false><<<(unsigned) std::max<int64_t>(ctas, 1), R_WARPS * 32, 0, st>>>(p);
         RCUDA_TRY(cudaEventRecord(h->ev[3], st));

@@ -134,3 +134,58 @@ def test_c2_c3_full_size_exhaustive(config):
     _, _, _, n_ranks, _ = f.check(0, n, INT_MAX, 100)
     assert n_ranks > n // 4
     f.check(0, min(n, 200_000), 4, 4)
+
+
+def test_c5_full_size_exhaustive():
+    """BASELINE config C5 at scale 1.0 (1M retained topics, 100k wildcard SUBSCRIBE filters): with limit = unlimited every
+    filter's id set equals the oracle's TopicLevelTrie restatement; with the default limit of 10 every filter returns
+    min(total, 10) ids and each of them is a member of its full match set (which `limit` ids come back is unpinned in the
+    reference too: it iterates a HashSet, RetainStoreCoProc.java:177-188). Also concurrently from four threads on one handle."""
+    import threading
+    from bifromq_b200 import retain, workload
+    w = workload.Workload("C5")
+    assert w.n_topics >= 990_000 and w.n_query_filters == 100_000
+    idx = retain.GpuTopicMatchIndex(0)
+    tenants = w.tenants
+    ids = idx.add_blobs(tenants, w.topics, w.topic_off, w.topic_tenant[:w.n_topics])
+    idx.commit()
+    orc = O.TopicLevelIndex()
+    tl = w.topic_list()
+    for i in range(w.n_topics):
+        orc.add(tl[i], int(ids[i]), tenants[w.topic_tenant[i]])
+    n = w.n_query_filters
+    ft = np.ascontiguousarray(w.filter_tenant[:n])
+    res = idx.match_blobs(tenants, w.filters, w.filter_off, ft)
+    fl = w.query_filter_list()
+    hits = 0
+    for i in range(n):
+        want = orc.match(fl[i], tenants[ft[i]])
+        got = np.sort(res.matches(i))
+        assert len(got) == len(want) and got.tolist() == want, fl[i]
+        hits += bool(want)
+    assert hits > 0.5 * n and int(res.totals.sum()) > 1_000_000
+    lim = np.full(n, 10, np.int64)
+    res10 = idx.match_blobs(tenants, w.filters, w.filter_off, ft, lim)
+    assert (np.diff(res10.offsets) == np.minimum(res.totals, 10)).all() and (res10.totals == res.totals).all()
+    for i in range(0, n, 7):
+        assert np.isin(res10.matches(i), res.matches(i)).all()
+    # four threads, different slices of the filter batch, one handle: every result is its own (results own their arrays)
+    outs, errs = {}, []
+
+    def worker(k):
+        try:
+            b, e = k * (n // 4), (k + 1) * (n // 4)
+            off = np.ascontiguousarray(w.filter_off[b:e + 1])
+            for _ in range(3):
+                outs[k] = idx.match_blobs(tenants, w.filters, off, np.ascontiguousarray(ft[b:e]))
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for k in range(4):
+        b = k * (n // 4)
+        assert (outs[k].totals == res.totals[b:b + n // 4]).all()
+        for i in range(0, n // 4, 101):
+            assert np.sort(outs[k].matches(i)).tolist() == np.sort(res.matches(b + i)).tolist()
