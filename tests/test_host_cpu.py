@@ -243,3 +243,23 @@ def test_builder_places_every_child_array_kind():
     assert n_nodes == 2 + sum(1 + n + 1 for n in widths.values()) + 2 * 2500
     assert st[3] >= n_nodes - 2            # slots: private arrays + tag-table blocks
     assert st[9] + st[10] + st[11] + st[12] + st[13] == n_nodes   # child-count histogram covers every node
+
+
+def test_jni_shim_covers_every_native_method_and_type_checks():
+    """jni/bfq_gpumatch_jni.c (the shim a maintainer adds) defines one function per `static native` method of
+    jni/java/.../BfqNative.java, calls only functions include/bfq_gpumatch.h declares, and compiles against the JNI stand-in
+    header (no JDK in this image; __graft_entry__.build() runs the same check)"""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    java = open(os.path.join(root, "jni", "java", "org", "apache", "bifromq", "dist", "worker", "gpumatch", "BfqNative.java")).read()
+    csrc = open(os.path.join(root, "jni", "bfq_gpumatch_jni.c")).read()
+    natives = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", java))
+    defined = set(re.findall(r"JFN\((\w+)\)\(", csrc))
+    assert natives and natives == defined, (natives - defined, defined - natives)
+    header = open(os.path.join(root, "include", "bfq_gpumatch.h")).read()
+    declared = set(re.findall(r"\b(bfq_\w+)\s*\(", header))
+    called = set(re.findall(r"\b(bfq_\w+)\s*\(", csrc)) - {"bfq_gpumatch_jni"}
+    assert called <= declared, called - declared
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-DBFQ_JNI_STUB",
+                           os.path.join(root, "jni", "bfq_gpumatch_jni.c")])
