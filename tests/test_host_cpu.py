@@ -66,7 +66,8 @@ def test_product_package_does_not_touch_the_oracle():
     for i in uses:   # the one place: oracle_for_sample(), called by run_cpu_baseline() only (cpu_baseline and --impl reference)
         head = bench[:i]
         fn = head[head.rindex("\ndef ") + 5:].split("(")[0]
-        assert fn in ("oracle_for_sample",), "bench.py imports the oracle in %s()" % fn
+        # forward configs / the inverse config C5: both are cpu_baseline / --impl reference legs, nothing the GPU arm calls
+        assert fn in ("oracle_for_sample", "inverse_cpu_baseline"), "bench.py imports the oracle in %s()" % fn
 
 
 # ------------------------------------------------------------------ codec parity (product C++ vs oracle C++)
