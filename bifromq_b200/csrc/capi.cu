@@ -89,9 +89,30 @@ struct Snapshot {
     DevBuf<Slot> d_slots, d_roots;
     DevBuf<uint32_t> d_segs, d_pfxP, d_pfxG;
     DevBuf<uint8_t> d_rkind, d_tags;
-    FlatIndex flat;          // host copy (segs / rkind / tenant map / statistics; the uploaded arrays are dropped)
-    KVBlob committed;        // committed KV (route lookups)
+    FlatIndex flat;          // host copy (segs / tenant map / tenant table / statistics; the uploaded arrays are dropped)
+    // per tenant, aligned with flat.tenants (key order): the committed KV (route lookups; shared with the staging area and
+    // with the neighbouring snapshots, a delta commit replaces only the touched tenants') and the route kinds
+    struct TenantHost {
+        std::shared_ptr<const KVBlob> kv;
+        std::shared_ptr<const std::vector<uint8_t>> rkind;
+    };
+    std::vector<TenantHost> th;
+    uint64_t garbage_slots = 0;   // slots of regions that delta commits replaced (reclaimed by the next full build)
+    int64_t delta_commits = 0;    // delta commits since the last full build
     size_t l2_window_bytes = 0;
+    // rank -> (index into flat.tenants, rank inside the tenant); false if out of range
+    bool locate(int64_t rank, size_t* ti, int64_t* local) const {
+        if (rank < 0 || rank >= flat.n_routes || flat.tenants.empty()) return false;
+        size_t lo = 0, hi = flat.tenants.size();
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) / 2;
+            if (flat.tenants[mid].lo <= rank) lo = mid;
+            else hi = mid;
+        }
+        *ti = lo;
+        *local = rank - flat.tenants[lo].lo;
+        return *local < flat.tenants[lo].n_routes;
+    }
     int64_t device_bytes() const {
         return (int64_t) (d_slots.bytes() + d_tags.bytes() + d_roots.bytes() + d_segs.bytes() + d_rkind.bytes() + d_pfxP.bytes() + d_pfxG.bytes());
     }
@@ -213,6 +234,7 @@ struct bfq_index {
     bool dedup = true;                   // BFQ_DEDUP=0: match duplicates of a (tenant, topic) pair separately
     double last_kernel_ms = 0;
     int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0, duplicate_topics = 0;
+    int64_t full_commits = 0, delta_commits = 0;
 
     ~bfq_index() {
         cudaSetDevice(device);
@@ -761,8 +783,11 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
         if (!decode_route_key(sv((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i])), &d))
             return fail(BFQ_E_INVALID, "undecodable route key in add set (nothing was staged)");
     }
-    for (int64_t i = 0; i < n_del; i++)
+    for (int64_t i = 0; i < n_del; i++) {
         if (del_key_off[i + 1] < del_key_off[i]) return fail(BFQ_E_INVALID, "offsets not ascending");
+        if (tenant_prefix_of(sv((const char*) del_keys + del_key_off[i], (size_t) (del_key_off[i + 1] - del_key_off[i]))).empty())
+            return fail(BFQ_E_INVALID, "undecodable route key in delete set (nothing was staged)");
+    }
     std::lock_guard<std::mutex> g(h->stage_mu);
     for (int64_t i = 0; i < n_add; i++)
         h->staging.upsert(sv((const char*) add_keys + add_key_off[i], (size_t) (add_key_off[i + 1] - add_key_off[i])),
@@ -772,13 +797,36 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
     return BFQ_OK;
 }
 
-int32_t bfq_index_commit(bfq_index* h) {
-    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
-    // The rebuild runs under the staging lock only: matches keep running on the previous snapshot meanwhile; the new one
-    // is published by swapping one shared pointer. Matches and results in flight keep the old snapshot alive.
-    std::lock_guard<std::mutex> gs(h->stage_mu);
-    CUDA_TRY(cudaSetDevice(h->device));
-    const KVBlob& kv = h->staging.materialize();
+namespace {
+
+void set_l2_window(bfq_index* h, Snapshot* sn) {
+    // Keep the tag array of the (rare) global tag table resident in L2 (persisting access window). BFQ_L2PERSIST=0 disables.
+    const char* e = getenv("BFQ_L2PERSIST");
+    if (e && atoi(e) == 0) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    size_t want = std::min<size_t>(sn->d_tags.bytes(), std::min<size_t>((size_t) max_persist, (size_t) max_window));
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) sn->l2_window_bytes = want;
+    cudaGetLastError();
+}
+
+void publish(bfq_index* h, std::shared_ptr<Snapshot> sn) {
+    std::shared_ptr<Snapshot> old;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        sn->generation = h->next_generation++;
+        old = std::move(h->snap);
+        h->snap = std::move(sn);
+    }
+    old.reset();   // freed here unless a match or a result still pins it
+}
+
+// every tenant rebuilt on all host cores, everything uploaded: bfq_index_load, the first commit, and whenever the delta
+// path cannot be used
+int32_t commit_full(bfq_index* h) {
+    h->staging.merge_all();
+    const KVBlob kv = h->staging.concat();
     auto sn = std::make_shared<Snapshot>();
     sn->device = h->device;
     FlatIndex& flat = sn->flat;
@@ -800,38 +848,316 @@ int32_t bfq_index_commit(bfq_index* h) {
         CUDA_TRY(cudaMemcpy(sn->d_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(sn->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(sn->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // per-tenant host side: the staged blobs are shared (no second copy of the KV), the route kinds are sliced
+    sn->th.resize(flat.tenants.size());
+    {
+        size_t i = 0;
+        for (auto& kvp : h->staging.tenants()) {
+            if (i >= flat.tenants.size() || kvp.second.base->n() != flat.tenants[i].n_routes)
+                return fail(BFQ_E_STATE, "internal error: staged tenants and built tenants disagree");
+            sn->th[i].kv = kvp.second.base;
+            sn->th[i].rkind = std::make_shared<const std::vector<uint8_t>>(flat.rkind.begin() + flat.tenants[i].lo,
+                                                                            flat.rkind.begin() + flat.tenants[i].lo + flat.tenants[i].n_routes);
+            i++;
+        }
+        if (i != flat.tenants.size()) return fail(BFQ_E_STATE, "internal error: staged tenants and built tenants disagree");
+    }
     // the host keeps only what it needs after the upload
     flat.slots.clear();
     flat.slots.shrink_to_fit();
     flat.tags.clear();
     flat.tags.shrink_to_fit();
     flat.roots.clear();
+    flat.rkind.clear();
+    flat.rkind.shrink_to_fit();
     flat.pfx_persistent.clear();
     flat.pfx_persistent.shrink_to_fit();
     flat.pfx_group.clear();
     flat.pfx_group.shrink_to_fit();
-    sn->committed = kv;   // snapshot of the raw KV for route lookups
-    // Keep the tag array of the (rare) global tag table resident in L2 (persisting access window). BFQ_L2PERSIST=0 disables.
+    set_l2_window(h, sn.get());
+    h->staging.clear_bulk_changed();
+    publish(h, std::move(sn));
+    return BFQ_OK;
+}
+
+constexpr int32_t BFQ_NEED_FULL = -101;   // internal: the delta path does not apply, do a full build
+
+// walks one tenant's slice of the segment table (a sequence of {n_segments, total, (first, count) x n_segments}) and moves
+// the ranks in it by `d`
+void shift_seg_slice(std::vector<uint32_t>& segs, uint64_t base, uint64_t words, int64_t d) {
+    uint64_t w = base;
+    while (w + 2 <= base + words) {
+        const uint32_t nseg = segs[w];
+        for (uint32_t k = 0; k < nseg && w + 2 + 2 * k + 1 < base + words + 1; k++) segs[w + 2 + 2 * k] = (uint32_t) ((int64_t) segs[w + 2 + 2 * k] + d);
+        w += 2 + 2 * (uint64_t) nseg;
+    }
+}
+
+// The delta path (DW/DistWorkerCoProc.java:304-513 applies one SUB / UNSUB at a time): only the touched
+// tenants are merged, rebuilt and uploaded. The new snapshot is a device-side copy of the previous one (a few milliseconds
+// for gigabytes at HBM speed; the previous snapshot stays untouched for the matches and results that pin it) in which
+//   * every rebuilt tenant gets a fresh slot region appended behind the existing ones (its old region becomes garbage until
+//     the next full build) and a patched root record;
+//   * ranks stay dense positions in KV order, so the tenants behind a tenant that grew or shrank have the ranks in their
+//     records moved by the difference (one streaming kernel over their regions) and their per-rank arrays copied to the
+//     shifted position.
+// The kernels see exactly the layout a full build would have produced, up to the placement of the regions.
+int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const std::vector<std::string>& dirty) {
+    const FlatIndex& of = old->flat;
+    if (of.n_big_edges > 0) return BFQ_NEED_FULL;   // the shared tag table cannot be patched per tenant
+    if (old->garbage_slots > (uint64_t) of.n_slots / 4 + 4096) return BFQ_NEED_FULL;   // reclaim the replaced regions
+    // ---- merge the touched tenants' KV (copy-on-write: the old blobs stay with the old snapshot)
+    for (auto& p : dirty) h->staging.merge_tenant(p);
+    struct Plan {
+        std::string prefix;            // key prefix
+        int old_index = -1;            // position in of.tenants, or -1 for a new tenant
+        std::shared_ptr<const KVBlob> kv;   // null: the tenant is gone
+        TenantImage img;
+    };
+    std::vector<Plan> plans;
+    std::unordered_map<std::string, int> old_pos;   // tenant id -> index in of.tenants
+    for (size_t i = 0; i < of.tenants.size(); i++) old_pos.emplace(of.tenants[i].tenant, (int) i);
+    for (auto& p : dirty) {
+        Plan pl;
+        pl.prefix = p;
+        const std::string id = p.substr(3);
+        auto it = old_pos.find(id);
+        pl.old_index = it == old_pos.end() ? -1 : it->second;
+        auto st = h->staging.tenants().find(p);
+        if (st != h->staging.tenants().end()) pl.kv = st->second.base;
+        if (pl.old_index < 0 && !pl.kv) continue;   // created and deleted between two commits
+        plans.push_back(std::move(pl));
+    }
+    if (plans.empty()) return BFQ_OK;   // nothing changed
+    // ---- the new tenant list in key order: old tenants (untouched or replaced) merged with the new ones
+    struct Entry {
+        int old_index;   // -1: new tenant
+        int plan;        // -1: untouched
+    };
+    std::vector<Entry> entries;
     {
-        const char* e = getenv("BFQ_L2PERSIST");
-        if (!e || atoi(e) != 0) {
-            int max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
-            size_t want = std::min<size_t>(sn->d_tags.bytes(), std::min<size_t>((size_t) max_persist, (size_t) max_window));
-            if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) sn->l2_window_bytes = want;
-            cudaGetLastError();
+        std::vector<int> plan_of_old(of.tenants.size(), -1);
+        std::vector<std::pair<std::string, int>> fresh;   // (prefix, plan) of new tenants, in key order (dirty is in key order)
+        for (size_t k = 0; k < plans.size(); k++) {
+            if (plans[k].old_index >= 0) plan_of_old[(size_t) plans[k].old_index] = (int) k;
+            else fresh.emplace_back(plans[k].prefix, (int) k);
+        }
+        size_t f = 0;
+        auto prefix_of_old = [&](size_t i) { return make_tenant_begin_key(of.tenants[i].tenant); };
+        for (size_t i = 0; i <= of.tenants.size(); i++) {
+            const std::string bound = i < of.tenants.size() ? prefix_of_old(i) : std::string();
+            while (f < fresh.size() && (i == of.tenants.size() || fresh[f].first < bound)) entries.push_back({-1, fresh[f++].second});
+            if (i == of.tenants.size()) break;
+            const int pk = plan_of_old[i];
+            if (pk >= 0 && !plans[(size_t) pk].kv) continue;   // tenant removed
+            entries.push_back({(int) i, pk});
         }
     }
+    // ---- bases: dense ranks, appended slot regions / segment slices, running prefix-count bases
+    auto sn = std::make_shared<Snapshot>();
+    sn->device = h->device;
+    FlatIndex& nf = sn->flat;
+    nf.tenant_ordinal = of.tenant_ordinal;
+    nf.host_roots = of.host_roots;
+    nf.segs = of.segs;
+    nf.n_blocks = of.n_blocks;
+    nf.n_big_edges = 0;
+    nf.overflowed_blocks = of.overflowed_blocks;
+    nf.max_nodes_per_depth = of.max_nodes_per_depth;
+    nf.max_tenant_nodes = of.max_tenant_nodes;
+    for (int k = 0; k < 5; k++) nf.child_hist[k] = of.child_hist[k];
+    uint64_t slot_cursor = of.n_slots, seg_cursor = of.segs.size();
+    int64_t rank = 0;
+    uint32_t ppb = 0, pgb = 0;
+    std::string err;
+    nf.tenants.reserve(entries.size());
+    sn->th.reserve(entries.size());
+    for (auto& e : entries) {
+        if (e.plan < 0) {   // untouched: same region, ranks moved by the growth of the tenants before it
+            TenantMeta m = of.tenants[(size_t) e.old_index];
+            m.lo = rank;
+            m.pp_base = ppb;
+            m.pg_base = pgb;
+            rank += m.n_routes;
+            ppb += m.pp;
+            pgb += m.pg;
+            nf.tenants.push_back(std::move(m));
+            sn->th.push_back(old->th[(size_t) e.old_index]);
+            continue;
+        }
+        Plan& pl = plans[(size_t) e.plan];
+        uint32_t ordinal;
+        const std::string id = pl.prefix.substr(3);
+        if (pl.old_index >= 0) {
+            ordinal = of.tenants[(size_t) pl.old_index].ordinal;
+        } else {
+            ordinal = (uint32_t) nf.host_roots.size();
+            nf.host_roots.emplace_back();
+            nf.tenant_ordinal[id] = ordinal;
+        }
+        if (!build_tenant_image(*pl.kv, sv(id), ordinal, rank, slot_cursor, seg_cursor, ppb, pgb, &pl.img, &err)) return fail(BFQ_E_INVALID, err);
+        if (pl.img.meta.big_edges > 0) return BFQ_NEED_FULL;
+        slot_cursor += pl.img.meta.csr_slots;
+        seg_cursor += pl.img.meta.seg_words;
+        rank += pl.img.meta.n_routes;
+        ppb += pl.img.meta.pp;
+        pgb += pl.img.meta.pg;
+        nf.host_roots[ordinal] = pl.img.root;
+        nf.segs.insert(nf.segs.end(), pl.img.segs.begin(), pl.img.segs.end());
+        nf.max_nodes_per_depth = std::max(nf.max_nodes_per_depth, pl.img.meta.max_depth_nodes);
+        nf.max_tenant_nodes = std::max(nf.max_tenant_nodes, pl.img.meta.walk_nodes);
+        nf.tenants.push_back(pl.img.meta);
+        Snapshot::TenantHost thh;
+        thh.kv = pl.kv;
+        thh.rkind = std::make_shared<const std::vector<uint8_t>>(pl.img.rkind);
+        sn->th.push_back(std::move(thh));
+    }
+    for (auto& pl : plans)
+        if (!pl.kv) nf.tenant_ordinal.erase(pl.prefix.substr(3));   // its root record stays behind, unreachable
+    if (slot_cursor >= 0x7FFFFFF0ull || rank >= (int64_t) 0x7FFFFFFF) return BFQ_NEED_FULL;
+    nf.n_routes = rank;
+    nf.n_slots = (uint32_t) slot_cursor;
+    nf.n_nodes = 0;
+    nf.n_multi = 0;
+    nf.n_cont_chunks = 0;
+    for (auto& m : nf.tenants) {
+        nf.n_nodes += m.tenant_nodes;
+        nf.n_multi += m.n_multi;
+        nf.n_cont_chunks += m.n_cont;
+    }
+    sn->garbage_slots = old->garbage_slots;
+    for (auto& pl : plans)
+        if (pl.old_index >= 0) sn->garbage_slots += of.tenants[(size_t) pl.old_index].csr_slots;
+    sn->delta_commits = old->delta_commits + 1;
+    // ---- device: copy, patch, shift
+    cudaStream_t st = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    } guard{st};
+    const size_t n_new = (size_t) rank, n_old = (size_t) of.n_routes;
+    CUDA_TRY(sn->d_slots.reserve((size_t) slot_cursor));
+    CUDA_TRY(sn->d_tags.reserve(std::max<size_t>(old->d_tags.cap, 1)));
+    CUDA_TRY(sn->d_roots.reserve(std::max<size_t>(nf.host_roots.size(), 1)));
+    CUDA_TRY(sn->d_segs.reserve(std::max<size_t>(nf.segs.size(), 2)));
+    CUDA_TRY(sn->d_rkind.reserve(std::max<size_t>(n_new, 1)));
+    CUDA_TRY(sn->d_pfxP.reserve(n_new + 1));
+    CUDA_TRY(sn->d_pfxG.reserve(n_new + 1));
+    CUDA_TRY(cudaMemcpyAsync(sn->d_slots.p, old->d_slots.p, (size_t) of.n_slots * sizeof(Slot), cudaMemcpyDeviceToDevice, st));
+    if (old->d_tags.cap) CUDA_TRY(cudaMemcpyAsync(sn->d_tags.p, old->d_tags.p, old->d_tags.cap, cudaMemcpyDeviceToDevice, st));
+    // untouched tenants: slot regions whose ranks move, and the pieces of the per-rank arrays
+    std::vector<RankShiftRegion> regions;
+    for (size_t i = 0; i < nf.tenants.size(); i++) {
+        const Entry& e = entries[i];
+        const TenantMeta& m = nf.tenants[i];
+        if (e.plan >= 0) {
+            const TenantImage& img = plans[(size_t) e.plan].img;
+            if (m.csr_slots) CUDA_TRY(cudaMemcpyAsync(sn->d_slots.p + m.region_base, img.slots.data(), (size_t) m.csr_slots * sizeof(Slot), cudaMemcpyHostToDevice, st));
+            if (m.n_routes) {
+                CUDA_TRY(cudaMemcpyAsync(sn->d_rkind.p + m.lo, img.rkind.data(), (size_t) m.n_routes, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(sn->d_pfxP.p + m.lo, img.pfxP.data(), (size_t) m.n_routes * 4, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(sn->d_pfxG.p + m.lo, img.pfxG.data(), (size_t) m.n_routes * 4, cudaMemcpyHostToDevice, st));
+            }
+            continue;
+        }
+        const TenantMeta& om = of.tenants[(size_t) e.old_index];
+        const int64_t d = m.lo - om.lo;
+        if (d != 0) {
+            if (m.csr_slots) regions.push_back(RankShiftRegion{m.region_base, m.csr_slots, (int32_t) d});
+            Slot& r = nf.host_roots[m.ordinal];
+            if (r.w[W_OWN_COUNT] > 0 && !(r.w[W_META] & FLAG_OWN_MULTI)) r.w[W_OWN_FIRST] = (uint32_t) ((int64_t) r.w[W_OWN_FIRST] + d);
+            if (r.w[W_HASH_COUNT] > 0 && !(r.w[W_META] & FLAG_HASH_MULTI)) r.w[W_HASH_FIRST] = (uint32_t) ((int64_t) r.w[W_HASH_FIRST] + d);
+            if (m.seg_words) shift_seg_slice(nf.segs, m.seg_base, m.seg_words, d);
+        }
+    }
+    // per-rank arrays of the untouched tenants: maximal runs with one rank shift and one pair of prefix-count shifts
+    for (size_t i = 0; i < nf.tenants.size();) {
+        if (entries[i].plan >= 0) {
+            i++;
+            continue;
+        }
+        const TenantMeta& m0 = nf.tenants[i];
+        const TenantMeta& o0 = of.tenants[(size_t) entries[i].old_index];
+        const int64_t d = m0.lo - o0.lo;
+        const uint32_t dP = m0.pp_base - o0.pp_base, dG = m0.pg_base - o0.pg_base;
+        size_t j = i;
+        int64_t len = 0;
+        while (j < nf.tenants.size() && entries[j].plan < 0) {
+            const TenantMeta& m = nf.tenants[j];
+            const TenantMeta& om = of.tenants[(size_t) entries[j].old_index];
+            if (m.lo - om.lo != d || m.pp_base - om.pp_base != dP || m.pg_base - om.pg_base != dG || om.lo != o0.lo + len) break;
+            len += m.n_routes;
+            j++;
+        }
+        if (len > 0) {
+            CUDA_TRY(cudaMemcpyAsync(sn->d_rkind.p + m0.lo, old->d_rkind.p + o0.lo, (size_t) len, cudaMemcpyDeviceToDevice, st));
+            launch_copy_add(sn->d_pfxP.p + m0.lo, old->d_pfxP.p + o0.lo, len, dP, st);
+            launch_copy_add(sn->d_pfxG.p + m0.lo, old->d_pfxG.p + o0.lo, len, dG, st);
+        }
+        i = j;
+    }
+    {
+        const uint32_t tail[2] = {ppb, pgb};
+        CUDA_TRY(cudaMemcpyAsync(sn->d_pfxP.p + n_new, &tail[0], 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(sn->d_pfxG.p + n_new, &tail[1], 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // `tail` is on the stack
+    }
+    (void) n_old;
+    if (!regions.empty()) {
+        DevBuf<RankShiftRegion> d_regions;
+        CUDA_TRY(d_regions.reserve(regions.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_regions.p, regions.data(), regions.size() * sizeof(RankShiftRegion), cudaMemcpyHostToDevice, st));
+        launch_rank_shift(sn->d_slots.p, d_regions.p, (int) regions.size(), st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        d_regions.release();
+    }
+    CUDA_TRY(cudaMemcpyAsync(sn->d_roots.p, nf.host_roots.data(), nf.host_roots.size() * sizeof(Slot), cudaMemcpyHostToDevice, st));
+    if (!nf.segs.empty()) CUDA_TRY(cudaMemcpyAsync(sn->d_segs.p, nf.segs.data(), nf.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    sn->l2_window_bytes = 0;
+    publish(h, std::move(sn));
+    return BFQ_OK;
+}
+
+}  // namespace
+
+int32_t bfq_index_commit(bfq_index* h) {
+    if (!h) return fail(BFQ_E_INVALID, "handle is NULL");
+    // The rebuild runs under the staging lock only: matches keep running on the previous snapshot meanwhile; the new one
+    // is published by swapping one shared pointer. Matches and results in flight keep the old snapshot alive.
+    std::lock_guard<std::mutex> gs(h->stage_mu);
+    CUDA_TRY(cudaSetDevice(h->device));
     std::shared_ptr<Snapshot> old;
     {
         std::lock_guard<std::mutex> g(h->mu);
-        sn->generation = h->next_generation++;
-        old = std::move(h->snap);
-        h->snap = std::move(sn);
+        old = h->snap;
     }
-    old.reset();   // freed here unless a match or a result still pins it
-    return BFQ_OK;
+    static const bool delta_enabled = [] {
+        const char* e = getenv("BFQ_DELTA_COMMIT");   // experiment switch: 0 = every commit is a full build
+        return !e || atoi(e) != 0;
+    }();
+    if (old && delta_enabled && !h->staging.bulk_changed()) {
+        const std::vector<std::string> dirty = h->staging.dirty_tenants();
+        if (dirty.empty()) return BFQ_OK;   // nothing staged since the last commit
+        if (dirty.size() <= 64) {
+            const int32_t rc = commit_delta(h, old, dirty);
+            if (rc != BFQ_NEED_FULL) {
+                if (rc == BFQ_OK) {
+                    std::lock_guard<std::mutex> g(h->mu);
+                    h->delta_commits++;
+                }
+                return rc;
+            }
+        }
+    }
+    const int32_t rc = commit_full(h);
+    if (rc == BFQ_OK) {
+        std::lock_guard<std::mutex> g(h->mu);
+        h->full_commits++;
+    }
+    return rc;
 }
 
 int32_t bfq_index_generation(bfq_index* h, uint64_t* generation) {
@@ -846,10 +1172,11 @@ int32_t bfq_index_stats(bfq_index* h, int64_t* stats, int32_t n) {
     std::lock_guard<std::mutex> g(h->mu);
     static const FlatIndex empty;
     const FlatIndex& f = h->snap ? h->snap->flat : empty;
-    const int64_t v[13] = {f.n_routes, (int64_t) f.tenant_ordinal.size(), f.n_nodes, (int64_t) f.n_slots,
+    const int64_t v[16] = {f.n_routes, (int64_t) f.tenant_ordinal.size(), f.n_nodes, (int64_t) f.n_slots,
                            h->snap ? h->snap->device_bytes() : 0, f.max_nodes_per_depth, h->launches, h->overflow_topics,
-                           h->flagged_topics, f.n_multi, f.n_cont_chunks, h->deferred_topics, h->duplicate_topics};
-    for (int32_t i = 0; i < n && i < 13; i++) stats[i] = v[i];
+                           h->flagged_topics, f.n_multi, f.n_cont_chunks, h->deferred_topics, h->duplicate_topics,
+                           h->full_commits, h->delta_commits, h->snap ? (int64_t) h->snap->garbage_slots : 0};
+    for (int32_t i = 0; i < n && i < 16; i++) stats[i] = v[i];
     return BFQ_OK;
 }
 
@@ -860,7 +1187,7 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
     if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
-    const KVBlob& snapshot = st.materialize();
+    const KVBlob snapshot = st.concat();
     const auto t1 = std::chrono::steady_clock::now();
     FlatIndex flat;
     if (!build_flat_index(snapshot, &flat, &err)) return fail(BFQ_E_INVALID, err);
@@ -916,8 +1243,10 @@ int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms) {
 namespace {
 int32_t lookup_in(const Snapshot* s, int64_t rank, uint8_t* key_out, int64_t key_cap, int64_t* key_len, uint8_t* val_out,
                   int64_t val_cap, int64_t* val_len) {
-    if (rank < 0 || rank >= s->committed.n()) return fail(BFQ_E_RANGE, "rank out of range");
-    sv k = s->committed.key(rank), v = s->committed.val(rank);
+    size_t ti = 0;
+    int64_t local = 0;
+    if (!s->locate(rank, &ti, &local)) return fail(BFQ_E_RANGE, "rank out of range");
+    sv k = s->th[ti].kv->key(local), v = s->th[ti].kv->val(local);
     if (key_len) *key_len = (int64_t) k.size();
     if (val_len) *val_len = (int64_t) v.size();
     if (key_out && (int64_t) k.size() <= key_cap) memcpy(key_out, k.data(), k.size());
@@ -926,8 +1255,10 @@ int32_t lookup_in(const Snapshot* s, int64_t rank, uint8_t* key_out, int64_t key
 }
 int32_t kinds_in(const Snapshot* s, const int64_t* ranks, int64_t n, uint8_t* kinds_out) {
     for (int64_t i = 0; i < n; i++) {
-        if (ranks[i] < 0 || ranks[i] >= (int64_t) s->flat.rkind.size()) return fail(BFQ_E_RANGE, "rank out of range");
-        kinds_out[i] = s->flat.rkind[(size_t) ranks[i]];
+        size_t ti = 0;
+        int64_t local = 0;
+        if (!s->locate(ranks[i], &ti, &local)) return fail(BFQ_E_RANGE, "rank out of range");
+        kinds_out[i] = (*s->th[ti].rkind)[(size_t) local];
     }
     return BFQ_OK;
 }

@@ -13,81 +13,146 @@ namespace bfq {
 
 // ------------------------------------------------------------------------------------------------ staging
 void Staging::reset() {
-    base_.clear();
-    delta_.clear();
-    dirty_ = true;
+    tenants_.clear();
+    last_loaded_.clear();
+    bulk_changed_ = true;
 }
 
 bool Staging::load(const uint8_t* keys, const int64_t* koff, const uint8_t* vals, const int64_t* voff, int64_t n,
                    std::string* err) {
     if (n <= 0) return true;
-    // fast path: appending a sorted run after the current base
-    bool sorted_append = delta_.empty();
-    if (sorted_append) {
-        sv prev = base_.n() ? base_.key(base_.n() - 1) : sv();
-        bool have_prev = base_.n() > 0;
-        for (int64_t i = 0; i < n && sorted_append; i++) {
-            sv k((const char*) keys + koff[i], (size_t) (koff[i + 1] - koff[i]));
-            if (have_prev && !(prev < k)) sorted_append = false;
+    auto key_at = [&](int64_t i) { return sv((const char*) keys + koff[i], (size_t) (koff[i + 1] - koff[i])); };
+    // validate first (nothing is staged on failure): strictly ascending, after everything loaded before, tenant prefix present
+    {
+        sv prev = sv(last_loaded_);
+        bool have_prev = !last_loaded_.empty();
+        for (int64_t i = 0; i < n; i++) {
+            const sv k = key_at(i);
+            if (koff[i + 1] < koff[i] || voff[i + 1] < voff[i] || (have_prev && !(prev < k))) {
+                if (err) *err = "bfq_index_load: keys must be strictly ascending (and follow the keys already staged)";
+                return false;
+            }
+            if (tenant_prefix_of(k).empty()) {
+                if (err) *err = "undecodable route key at position " + std::to_string(i);
+                return false;
+            }
             prev = k;
             have_prev = true;
         }
     }
-    if (sorted_append) {
-        const int64_t kb = koff[0], vb = voff[0];
-        const size_t k0 = base_.keys.size(), v0 = base_.vals.size();
-        base_.keys.insert(base_.keys.end(), keys + kb, keys + koff[n]);
-        base_.vals.insert(base_.vals.end(), vals + vb, vals + voff[n]);
-        base_.koff.reserve(base_.koff.size() + n);
-        base_.voff.reserve(base_.voff.size() + n);
-        for (int64_t i = 1; i <= n; i++) {
-            base_.koff.push_back((int64_t) k0 + koff[i] - kb);
-            base_.voff.push_back((int64_t) v0 + voff[i] - vb);
+    // append tenant by tenant (a run of keys with one prefix is one bulk copy)
+    int64_t i = 0;
+    while (i < n) {
+        const sv pfx = tenant_prefix_of(key_at(i));
+        int64_t j = i + 1;
+        while (j < n) {
+            const sv k = key_at(j);
+            if (k.size() < pfx.size() || memcmp(k.data(), pfx.data(), pfx.size()) != 0) break;
+            j++;
         }
-    } else {
-        if (err) *err = "bfq_index_load: keys must be strictly ascending (and follow the keys already staged)";
-        return false;
+        TenantStage& ts = tenants_[std::string(pfx)];
+        auto nb = std::make_shared<KVBlob>(*ts.base);   // copy-on-write: the old blob may be pinned by a snapshot
+        const size_t k0 = nb->keys.size(), v0 = nb->vals.size();
+        nb->keys.insert(nb->keys.end(), keys + koff[i], keys + koff[j]);
+        nb->vals.insert(nb->vals.end(), vals + voff[i], vals + voff[j]);
+        for (int64_t r = i + 1; r <= j; r++) {
+            nb->koff.push_back((int64_t) k0 + koff[r] - koff[i]);
+            nb->voff.push_back((int64_t) v0 + voff[r] - voff[i]);
+        }
+        ts.base = std::move(nb);
+        i = j;
     }
-    dirty_ = true;
+    last_loaded_ = std::string(key_at(n - 1));
+    bulk_changed_ = true;
     return true;
 }
 
-void Staging::upsert(sv k, sv v) {
-    delta_[std::string(k)] = {true, std::string(v)};
-    dirty_ = true;
+bool Staging::upsert(sv k, sv v) {
+    const sv pfx = tenant_prefix_of(k);
+    if (pfx.empty()) return false;
+    tenants_[std::string(pfx)].delta[std::string(k)] = {true, std::string(v)};
+    return true;
 }
-void Staging::erase(sv k) {
-    delta_[std::string(k)] = {false, std::string()};
-    dirty_ = true;
+bool Staging::erase(sv k) {
+    const sv pfx = tenant_prefix_of(k);
+    if (pfx.empty()) return false;
+    auto it = tenants_.find(std::string(pfx));
+    if (it == tenants_.end()) return true;   // nothing of this tenant is staged: nothing to delete
+    it->second.delta[std::string(k)] = {false, std::string()};
+    return true;
+}
+bool Staging::has_delta() const {
+    for (auto& kv : tenants_)
+        if (!kv.second.delta.empty()) return true;
+    return false;
+}
+std::vector<std::string> Staging::dirty_tenants() const {
+    std::vector<std::string> out;
+    for (auto& kv : tenants_)
+        if (!kv.second.delta.empty()) out.push_back(kv.first);
+    return out;
 }
 
-const KVBlob& Staging::materialize() {
-    if (!delta_.empty()) {
-        KVBlob merged;
-        merged.keys.reserve(base_.keys.size());
-        merged.vals.reserve(base_.vals.size());
+void Staging::merge_tenant(const std::string& prefix) {
+    auto it = tenants_.find(prefix);
+    if (it == tenants_.end()) return;
+    TenantStage& ts = it->second;
+    if (!ts.delta.empty()) {
+        const KVBlob& base = *ts.base;
+        auto merged = std::make_shared<KVBlob>();
+        merged->keys.reserve(base.keys.size() + 256);
+        merged->vals.reserve(base.vals.size() + 64);
         int64_t i = 0;
-        const int64_t n = base_.n();
-        auto d = delta_.begin();
-        while (i < n || d != delta_.end()) {
+        const int64_t n = base.n();
+        auto d = ts.delta.begin();
+        while (i < n || d != ts.delta.end()) {
             int c;
             if (i >= n) c = 1;
-            else if (d == delta_.end()) c = -1;
-            else c = base_.key(i).compare(sv(d->first));
+            else if (d == ts.delta.end()) c = -1;
+            else c = base.key(i).compare(sv(d->first));
             if (c < 0) {
-                merged.push(base_.key(i), base_.val(i));
+                merged->push(base.key(i), base.val(i));
                 i++;
             } else {
-                if (d->second.first) merged.push(d->first, d->second.second);
+                if (d->second.first) merged->push(d->first, d->second.second);
                 if (c == 0) i++;
                 ++d;
             }
         }
-        base_ = std::move(merged);
-        delta_.clear();
+        ts.base = std::move(merged);
+        ts.delta.clear();
     }
-    dirty_ = false;
-    return base_;
+    if (ts.base->n() == 0) tenants_.erase(it);
+}
+void Staging::merge_all() {
+    std::vector<std::string> names;
+    for (auto& kv : tenants_) names.push_back(kv.first);
+    for (auto& nme : names) merge_tenant(nme);
+}
+
+KVBlob Staging::concat() const {
+    KVBlob out;
+    size_t kb = 0, vb = 0, nn = 0;
+    for (auto& kv : tenants_) {
+        kb += kv.second.base->keys.size();
+        vb += kv.second.base->vals.size();
+        nn += (size_t) kv.second.base->n();
+    }
+    out.keys.reserve(kb);
+    out.vals.reserve(vb);
+    out.koff.reserve(nn + 1);
+    out.voff.reserve(nn + 1);
+    for (auto& kv : tenants_) {
+        const KVBlob& b = *kv.second.base;
+        const int64_t k0 = (int64_t) out.keys.size(), v0 = (int64_t) out.vals.size();
+        out.keys.insert(out.keys.end(), b.keys.begin(), b.keys.end());
+        out.vals.insert(out.vals.end(), b.vals.begin(), b.vals.end());
+        for (int64_t r = 1; r <= b.n(); r++) {
+            out.koff.push_back(k0 + b.koff[(size_t) r]);
+            out.voff.push_back(v0 + b.voff[(size_t) r]);
+        }
+    }
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------ builder
@@ -242,10 +307,20 @@ struct TenantBuild {
     uint64_t region_base = 0, seg_base = 0;
     uint32_t pp_base = 0, pg_base = 0;
     int64_t n_multi = 0;
+    // where the phases write (the whole-index arrays of a full build, or one tenant's private buffers of a delta build):
+    // rank r of `kv` is stored in the records as r + rank_off and indexes the per-rank arrays at r + index_off
+    int64_t rank_off = 0, index_off = 0;
+    uint8_t* rkind = nullptr;
+    uint32_t *pfxP = nullptr, *pfxG = nullptr;
+    Slot* slots = nullptr;        // slot s of the device array lives at slots[s - slot_origin]
+    uint64_t slot_origin = 0;
+    Slot* root_rec = nullptr;
+    uint32_t* segs = nullptr;     // word w of the segment table lives at segs[w - seg_origin]
+    uint64_t seg_origin = 0;
 };
 
 // phase B: decode the tenant's keys, build its trie, plan the child arrays
-void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
+void build_tenant(const KVBlob& kv, TenantBuild& tb) {
     Builder& b = tb.b;
     const uint32_t root = b.new_root(0);
     std::vector<sv> path_levels, levels;
@@ -257,9 +332,9 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
             tb.err = "undecodable route key at rank " + std::to_string(r);
             return;
         }
-        out->rkind[(size_t) r] = (uint8_t) d.kind;
-        out->pfx_persistent[(size_t) r] = pp;   // tenant-local for now, rebased in phase D
-        out->pfx_group[(size_t) r] = pg;
+        tb.rkind[(size_t) (r + tb.index_off)] = (uint8_t) d.kind;
+        tb.pfxP[(size_t) (r + tb.index_off)] = pp;   // tenant-local for now, rebased in phase D
+        tb.pfxG[(size_t) (r + tb.index_off)] = pg;
         if (d.kind == KIND_PERSISTENT) pp++;
         else if (d.kind == KIND_GROUP) pg++;
         levels.clear();
@@ -282,7 +357,7 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
             path_levels.push_back(levels[k]);
             path_nodes.push_back(node);
         }
-        b.add_route(multi_wild ? b.nodes[node].hash : b.nodes[node].own, (uint32_t) r, d.kind);
+        b.add_route(multi_wild ? b.nodes[node].hash : b.nodes[node].own, (uint32_t) (r + tb.rank_off), d.kind);
     }
     tb.pp = pp;
     tb.pg = pg;
@@ -380,7 +455,7 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb, FlatIndex* out) {
 inline uint32_t sat8(uint32_t v) { return v > 255u ? 255u : v; }
 
 // phase D: place the tenant's nodes (BFS inside its private region; big fan-outs into the shared tag table) and emit records
-void place_tenant(TenantBuild& tb, EdgeTable& table, FlatIndex* out) {
+void place_tenant(TenantBuild& tb, EdgeTable& table) {
     Builder& b = tb.b;
     const size_t N = b.nodes.size();
     std::vector<uint32_t> id_of(N, NONE), child_base(N, 0), order;
@@ -427,11 +502,12 @@ void place_tenant(TenantBuild& tb, EdgeTable& table, FlatIndex* out) {
             *first = (uint32_t) (seg_cursor / 2);
             *count = t.total;
             *flags |= multi_flag;
-            out->segs[seg_cursor++] = (uint32_t) lst.size();
-            out->segs[seg_cursor++] = t.total;
+            uint32_t* sg = tb.segs - tb.seg_origin;
+            sg[seg_cursor++] = (uint32_t) lst.size();
+            sg[seg_cursor++] = t.total;
             for (auto& p : lst) {
-                out->segs[seg_cursor++] = p.first;
-                out->segs[seg_cursor++] = p.second;
+                sg[seg_cursor++] = p.first;
+                sg[seg_cursor++] = p.second;
             }
             tb.n_multi++;
         } else {
@@ -443,11 +519,11 @@ void place_tenant(TenantBuild& tb, EdgeTable& table, FlatIndex* out) {
         BNode& nd = b.nodes[i];
         Slot* rec;
         if (nd.parent == NONE) {
-            rec = &out->roots[tb.ordinal];
+            rec = tb.root_rec;
             memset(rec->w, 0, sizeof(rec->w));
             rec->w[W_PARENT] = NONE;
         } else {
-            rec = &table.slots[id_of[i]];
+            rec = &tb.slots[id_of[i] - tb.slot_origin];
             rec->w[W_PARENT] = id_of[nd.parent];
             rec->w[W_LEN] = nd.lenw;
             for (uint32_t k = 0; k < TOKEN_WORDS; k++) rec->w[W_TOK + k] = nd.tok[k];
@@ -463,8 +539,8 @@ void place_tenant(TenantBuild& tb, EdgeTable& table, FlatIndex* out) {
     }
     // rebase the tenant-local prefix counts
     for (int64_t r = tb.lo; r < tb.hi; r++) {
-        out->pfx_persistent[(size_t) r] += tb.pp_base;
-        out->pfx_group[(size_t) r] += tb.pg_base;
+        tb.pfxP[(size_t) (r + tb.index_off)] += tb.pp_base;
+        tb.pfxG[(size_t) (r + tb.index_off)] += tb.pg_base;
     }
 }
 
@@ -549,7 +625,12 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     for (size_t i = 0; i < tenants.size(); i++) by_size[i] = (uint32_t) i;
     std::sort(by_size.begin(), by_size.end(), [&](uint32_t a, uint32_t b) { return tenants[a].hi - tenants[a].lo > tenants[b].hi - tenants[b].lo; });
     // ---- phase B (parallel): per-tenant trie + child-array plans
-    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { build_tenant(kv, tb, out); });
+    for (auto& tb : tenants) {
+        tb.rkind = out->rkind.data();
+        tb.pfxP = out->pfx_persistent.data();
+        tb.pfxG = out->pfx_group.data();
+    }
+    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { build_tenant(kv, tb); });
     lap("B tries + plans (parallel)");
     if (trace) {
         uint64_t big_nodes = 0, big_edges = 0, hist[6] = {0, 0, 0, 0, 0, 0};
@@ -622,20 +703,114 @@ bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err) {
     out->segs.assign((size_t) std::max<uint64_t>(seg_total, 2), 0);
     lap("C regions + allocation");
     // ---- phase D (parallel): placement + record emission (tag-table claims are atomic)
-    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { place_tenant(tb, table, out); });
+    for (auto& tb : tenants) {
+        tb.slots = table.slots.data();
+        tb.root_rec = &out->roots[tb.ordinal];
+        tb.segs = out->segs.data();
+    }
+    parallel_for_tenants(tenants, by_size, [&](TenantBuild& tb) { place_tenant(tb, table); });
+    out->tenants.clear();
+    out->tenants.reserve(tenants.size());
     for (auto& tb : tenants) {
         if (!tb.err.empty()) {
             if (err) *err = tb.err;
             return false;
         }
         out->n_multi += tb.n_multi;
+        TenantMeta m;
+        m.tenant = std::string(tb.tenant);
+        m.ordinal = tb.ordinal;
+        m.lo = tb.lo;
+        m.n_routes = tb.hi - tb.lo;
+        m.region_base = tb.region_base;
+        m.csr_slots = tb.csr_slots;
+        m.seg_base = tb.seg_base;
+        m.seg_words = tb.seg_words;
+        m.pp = tb.pp;
+        m.pg = tb.pg;
+        m.pp_base = tb.pp_base;
+        m.pg_base = tb.pg_base;
+        m.tenant_nodes = (int64_t) tb.b.nodes.size();
+        m.max_depth_nodes = tb.max_depth_nodes;
+        m.walk_nodes = tb.tenant_nodes;
+        m.n_multi = tb.n_multi;
+        m.n_cont = tb.b.n_cont;
+        m.big_edges = tb.big_edges;
+        out->tenants.push_back(std::move(m));
     }
+    out->n_big_edges = n_big_edges;
+    out->host_roots = out->roots;
     lap("D placement (parallel)");
     out->n_blocks = table.n_blocks;
     out->n_slots = (uint32_t) table.slots.size();
     out->overflowed_blocks = table.overflowed_blocks;
     out->slots = std::move(table.slots);
     out->tags = std::move(table.tags);
+    return true;
+}
+
+bool build_tenant_image(const KVBlob& tkv, sv tenant, uint32_t ordinal, int64_t rank_lo, uint64_t region_base, uint64_t seg_base,
+                        uint32_t pp_base, uint32_t pg_base, TenantImage* out, std::string* err) {
+    *out = TenantImage();
+    const int64_t n = tkv.n();
+    TenantBuild tb;
+    tb.tenant = tenant;
+    tb.lo = 0;
+    tb.hi = n;
+    tb.ordinal = ordinal;
+    tb.rank_off = rank_lo;
+    tb.index_off = 0;
+    out->rkind.assign((size_t) n, 0);
+    out->pfxP.assign((size_t) n + 1, 0);
+    out->pfxG.assign((size_t) n + 1, 0);
+    tb.rkind = out->rkind.data();
+    tb.pfxP = out->pfxP.data();
+    tb.pfxG = out->pfxG.data();
+    build_tenant(tkv, tb);
+    if (!tb.err.empty()) {
+        if (err) *err = tb.err;
+        return false;
+    }
+    TenantMeta& m = out->meta;
+    m.tenant = std::string(tenant);
+    m.ordinal = ordinal;
+    m.lo = rank_lo;
+    m.n_routes = n;
+    m.region_base = region_base;
+    m.csr_slots = tb.csr_slots;
+    m.seg_base = seg_base;
+    m.seg_words = tb.seg_words;
+    m.pp = tb.pp;
+    m.pg = tb.pg;
+    m.pp_base = pp_base;
+    m.pg_base = pg_base;
+    m.tenant_nodes = (int64_t) tb.b.nodes.size();
+    m.max_depth_nodes = tb.max_depth_nodes;
+    m.walk_nodes = tb.tenant_nodes;
+    m.n_cont = tb.b.n_cont;
+    m.big_edges = tb.big_edges;
+    if (tb.big_edges > 0) return true;   // needs the shared tag table: the caller falls back to a full rebuild
+    tb.region_base = region_base;
+    tb.seg_base = seg_base;
+    tb.pp_base = pp_base;
+    tb.pg_base = pg_base;
+    out->slots.resize((size_t) tb.csr_slots);
+    fill_empty_slots(out->slots.data(), out->slots.size());
+    out->segs.assign((size_t) tb.seg_words, 0);
+    tb.slots = out->slots.data();
+    tb.slot_origin = region_base;
+    tb.root_rec = &out->root;
+    tb.segs = out->segs.data();
+    tb.seg_origin = seg_base;
+    EdgeTable unused;
+    place_tenant(tb, unused);
+    if (!tb.err.empty()) {
+        if (err) *err = tb.err;
+        return false;
+    }
+    out->pfxP[(size_t) n] = pp_base + tb.pp;
+    out->pfxG[(size_t) n] = pg_base + tb.pg;
+    m.n_multi = tb.n_multi;
     return true;
 }
 

@@ -1009,6 +1009,36 @@ __global__ void __launch_bounds__(CAPS_THREADS) expand_flagged_kernel(const Expa
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) rank_shift_kernel(Slot* slots, const RankShiftRegion* regions, int n_regions) {
+    // a CTA takes a region at a time; regions differ in size by orders of magnitude, so big ones are cut into pieces of 8192
+    // slots that all CTAs pick up (piece index = blockIdx, striding)
+    for (int r = 0; r < n_regions; r++) {
+        const RankShiftRegion rg = regions[r];
+        const uint32_t d = (uint32_t) rg.delta;
+        for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < rg.len; s += (uint64_t) gridDim.x * blockDim.x) {
+            uint32_t* w = slots[rg.base + s].w;
+            if (w[W_PARENT] == EMPTY_PARENT) continue;
+            const uint32_t meta = w[W_META];
+            if (w[W_OWN_COUNT] > 0 && !(meta & FLAG_OWN_MULTI)) w[W_OWN_FIRST] += d;
+            if (w[W_HASH_COUNT] > 0 && !(meta & FLAG_HASH_MULTI)) w[W_HASH_FIRST] += d;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) copy_add_kernel(uint32_t* dst, const uint32_t* src, int64_t n, uint32_t add) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) dst[i] = src[i] + add;
+}
+}  // namespace
+
+void launch_rank_shift(Slot* slots, const RankShiftRegion* d_regions, int n_regions, cudaStream_t stream) {
+    if (n_regions <= 0) return;
+    rank_shift_kernel<<<148 * 8, 256, 0, stream>>>(slots, d_regions, n_regions);
+}
+void launch_copy_add(uint32_t* dst, const uint32_t* src, int64_t n, uint32_t add, cudaStream_t stream) {
+    if (n <= 0) return;
+    copy_add_kernel<<<(unsigned) std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(dst, src, n, add);
+}
+
 int match_kernel_smem_bytes() { return (int) sizeof(WarpSmem) * WARPS_PER_CTA; }
 
 void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStream_t stream) {

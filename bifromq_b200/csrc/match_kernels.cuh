@@ -186,4 +186,14 @@ struct CompactParams {
 cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp_bytes, cudaStream_t stream, int phase);
 int match_kernel_smem_bytes();
 
+// bfq_index_commit's delta path: the records of the tenants BEHIND a tenant that grew or shrank carry dense KV ranks, so
+// their own / '#' first-rank words move by the difference. One streaming pass over the listed slot regions.
+struct RankShiftRegion {
+    uint64_t base, len;     // slots [base, base + len)
+    int32_t delta;
+};
+void launch_rank_shift(Slot* slots, const RankShiftRegion* d_regions, int n_regions, cudaStream_t stream);
+// dst[i] = src[i] + add (the prefix-count arrays of those tenants, copied to their shifted position)
+void launch_copy_add(uint32_t* dst, const uint32_t* src, int64_t n, uint32_t add, cudaStream_t stream);
+
 }  // namespace bfq

@@ -170,11 +170,11 @@ class GpuRouteIndex:
         N.check(N.lib.bfq_index_commit(self._h))
 
     def stats(self):
-        s = np.zeros(13, np.int64)
-        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 13))
+        s = np.zeros(16, np.int64)
+        N.check(N.lib.bfq_index_stats(self._h, s.ctypes.data, 16))
         names = ["routes", "tenants", "nodes", "slots", "device_bytes", "max_nodes_per_depth", "launches",
                  "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks", "deferred_topics",
-                 "duplicate_topics"]
+                 "duplicate_topics", "full_commits", "delta_commits", "garbage_slots"]
         return dict(zip(names, s.tolist()))
 
     def generation(self):
