@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -904,6 +905,14 @@ void shift_seg_slice(std::vector<uint32_t>& segs, uint64_t base, uint64_t words,
 // The kernels see exactly the layout a full build would have produced, up to the placement of the regions.
 int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const std::vector<std::string>& dirty) {
     const FlatIndex& of = old->flat;
+    const bool trace = getenv("BFQ_COMMIT_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bfq delta commit] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     if (of.n_big_edges > 0) return BFQ_NEED_FULL;   // the shared tag table cannot be patched per tenant
     if (old->garbage_slots > (uint64_t) of.n_slots / 4 + 4096) return BFQ_NEED_FULL;   // reclaim the replaced regions
     // ---- merge the touched tenants' KV (copy-on-write: the old blobs stay with the old snapshot)
@@ -929,6 +938,7 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
         plans.push_back(std::move(pl));
     }
     if (plans.empty()) return BFQ_OK;   // nothing changed
+    lap("merge touched tenants' KV");
     // ---- the new tenant list in key order: old tenants (untouched or replaced) merged with the new ones
     struct Entry {
         int old_index;   // -1: new tenant
@@ -1029,6 +1039,7 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
     for (auto& pl : plans)
         if (pl.old_index >= 0) sn->garbage_slots += of.tenants[(size_t) pl.old_index].csr_slots;
     sn->delta_commits = old->delta_commits + 1;
+    lap("rebuild touched tenants (host)");
     // ---- device: copy, patch, shift
     cudaStream_t st = nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1044,6 +1055,7 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
     CUDA_TRY(sn->d_rkind.reserve(std::max<size_t>(n_new, 1)));
     CUDA_TRY(sn->d_pfxP.reserve(n_new + 1));
     CUDA_TRY(sn->d_pfxG.reserve(n_new + 1));
+    lap("device allocations");
     CUDA_TRY(cudaMemcpyAsync(sn->d_slots.p, old->d_slots.p, (size_t) of.n_slots * sizeof(Slot), cudaMemcpyDeviceToDevice, st));
     if (old->d_tags.cap) CUDA_TRY(cudaMemcpyAsync(sn->d_tags.p, old->d_tags.p, old->d_tags.cap, cudaMemcpyDeviceToDevice, st));
     // untouched tenants: slot regions whose ranks move, and the pieces of the per-rank arrays
@@ -1116,8 +1128,10 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
     if (!nf.segs.empty()) CUDA_TRY(cudaMemcpyAsync(sn->d_segs.p, nf.segs.data(), nf.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    lap("device copy + patch + rank shift");
     sn->l2_window_bytes = 0;
     publish(h, std::move(sn));
+    lap("publish (drops the old snapshot)");
     return BFQ_OK;
 }
 
