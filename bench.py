@@ -44,9 +44,10 @@ def parse_args():
     ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"],
                     help="C4 is the headline (and the default); C5 = the inverse path (retained topics matched BY wildcard filters)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a bench number)")
-    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
-                    help="N > 1 only. strong (default): ONE filter set tenant-sharded over the ranks, the same batch split by owner, the "
-                         "results all-gathered inside the timed step; weak: every rank hosts its own full-size set")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1 only; either way ONE filter set is tenant-sharded over the ranks and the results are all-gathered inside the "
+                         "timed step. weak (default): the publish batch grows with N (N x the config's batch, about one config batch per "
+                         "rank); strong: the config's batch itself is split N ways")
     ap.add_argument("--no-replicate-hot", action="store_true", help="strong scaling: pure hash placement, no replicas of hot tenants")
     ap.add_argument("--retain-limit", type=int, default=10, help="C5: ids returned per filter (RetainMessageMatchLimit default 10; -1 = unlimited)")
     ap.add_argument("--exchange", default="ranges", choices=["ranges", "counts", "none"], help="N > 1: what the timed step all-gathers")
@@ -197,12 +198,16 @@ def make_roofline(sample_topic_bytes, st, ns, n_topics_per_launch, kernel_ms, gp
 
 
 def make_workload(args, rank, world):
+    """N = 1: the BASELINE config as written. N > 1: ONE filter set of that config, tenant-sharded over the ranks (tenant ->
+    rank by fnv1a64(tenantId) mod N; hot tenants replicated, see workload.py), and a publish batch split by owner:
+      weak   (default)  the batch is N times the config's (N GPUs serving N times the publish traffic of the same filter set):
+                        about the config's batch per rank, whatever N
+      strong            the config's batch itself, split N ways"""
     from bifromq_b200.workload import Workload
-    if world > 1 and args.scaling == "strong":
-        return Workload(args.config, scale=args.scale, shard_index=rank, shard_count=world, replicate_hot=not args.no_replicate_hot)
-    # weak scaling: every rank hosts a full-size shard with its own tenant namespace
-    prefix = "" if world == 1 else "g%d-" % rank
-    return Workload(args.config, seed=Workload.SEED + rank, scale=args.scale, tenant_prefix=prefix)
+    if world > 1:
+        return Workload(args.config, scale=args.scale, shard_index=rank, shard_count=world, replicate_hot=not args.no_replicate_hot,
+                        topic_mult=world if args.scaling == "weak" else 1)
+    return Workload(args.config, scale=args.scale)
 
 
 def cpu_sample_indices(w, want):
@@ -440,11 +445,6 @@ def main():
         return main_inverse(args, rank, world, local)
     if world != args.gpus and world > 1:
         args.gpus = world
-    if args.scaling is None:
-        # BASELINE C4 / C3 as written: one filter set sharded by tenant over the GPUs. C2 is ONE tenant: it cannot shard by
-        # tenant, every rank then hosts the whole set ("replicas") and the ranks' batches are independent -> weak.
-        args.scaling = "strong" if (world > 1 and args.config in ("C3", "C4")) else "weak"
-
     if args.impl == "reference":
         # the reference's own algorithm (restated in C++, oracle/) on the host cores; rank 0 only
         if rank != 0:
@@ -526,7 +526,8 @@ def main():
     xch = None
     if world > 1 and args.exchange != "none":
         xch = D.Exchange(local)   # NCCL communicator inside the library; the id travels over torch.distributed
-    DEPTH = 3 if xch is None else 1   # matches in flight (each on its own leased workspace); the exchange synchronises every step
+        idx.set_option("tier0_ctas_per_sm", 6)   # one CTA slot per SM stays free for the exchange kernels of the previous step
+    DEPTH = 3   # matches in flight (each on its own leased workspace)
     sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
     if rank == 0:
         sampler.start()
@@ -547,57 +548,77 @@ def main():
         else:
             res.release()
 
-    def step_sharded(record):
-        """N > 1: match this rank's topics, then the one exchange step — every rank ends with every rank's
-        per-topic counts (and ranges): bfq_exchange_gather, NCCL inside the library, on the same stream"""
-        res = enqueue_device()
-        res.wait()
-        g = xch.gather(res, ranges=args.exchange == "ranges", stream=stream.cuda_stream)
-        gathered_info.update(topics=g.n_topics_total, ranges=g.n_ranges_total, bytes_received=g.bytes_received)
-        if last[0] is not None:
-            last[0].release()      # the previous step's buffers: everything that read them finished before this step's sync
-        last[0] = res
-        if record:
-            kernel_ms.append(res.tier0_ms)
-            return res.n_launches + 4
-        return 0
+    xs = torch.cuda.Stream(dev) if xch is not None else None   # the exchange runs on its own stream, one step behind the matching
+    pipe = {"pending": None, "gathered": None}
+
+    def pump(res_new, record):
+        """N > 1, software-pipelined: the match of step i is enqueued (no host sync) BEFORE the exchange of step i - 1 is issued,
+        so the exchange's one host synchronisation and its NCCL traffic overlap the next step's kernels. The exchange
+        (SURVEY.md 8e): every rank ends with every rank's per-topic counts (and ranges) — bfq_exchange_gather, NCCL inside
+        the library."""
+        pend = pipe["pending"]
+        if pend is not None:
+            pend.wait()                      # waits for THAT match only (an event behind it), then reads its counters
+            g = xch.gather(pend, ranges=args.exchange == "ranges", stream=xs.cuda_stream)
+            gathered_info.update(topics=g.n_topics_total, ranges=g.n_ranges_total, bytes_received=g.bytes_received)
+            if pipe["gathered"] is not None:
+                pipe["gathered"].release()   # its gather finished before the synchronisation inside the gather just issued
+            pipe["gathered"] = pend
+            if record:
+                kernel_ms.append(pend.tier0_ms)
+        pipe["pending"] = res_new
+        return (res_new.n_launches + 4) if (res_new is not None and record) else 0
 
     inflight = []
     for _ in range(max(args.warmup, 3) + DEPTH):   # warm-up (also creates the workspaces the timed loop will reuse)
         if xch is not None:
-            step_sharded(False)
+            pump(enqueue_device(), False)
             continue
         inflight.append(enqueue_device())
         if len(inflight) >= DEPTH:
             retire(inflight.pop(0), record=False)
     while inflight:
         retire(inflight.pop(0), record=False)
+    if xch is not None:
+        pump(None, False)
+        xs.synchronize()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(dev)
-    for i in range(args.steps):
-        flush.zero_()                     # L2 flush between timed iterations (untimed: outside the event pair)
-        ev[i][0].record(stream)
-        if xch is not None:
-            launches += step_sharded(True)
-        else:
+    if xch is not None:
+        # K steps back to back; timed as a whole (first match enqueued -> last exchange complete): the steps overlap by design.
+        # No L2 flush here: every rank's index is far larger than L2 and each step streams new result buffers.
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin.record(stream)
+        for i in range(args.steps):
+            launches += pump(enqueue_device(), True)
+        pump(None, True)
+        t_end.record(xs)
+        xs.synchronize()
+        torch.cuda.synchronize(dev)
+        step_total = t_begin.elapsed_time(t_end)
+        ev = None
+    else:
+        for i in range(args.steps):
+            flush.zero_()                     # L2 flush between timed iterations (untimed: outside the event pair)
+            ev[i][0].record(stream)
             inflight.append(enqueue_device())
-        ev[i][1].record(stream)
-        if len(inflight) >= DEPTH:
-            retire(inflight.pop(0))
-    while inflight:
-        r_ = inflight.pop(0)
-        retire(r_, keep=not inflight)
+            ev[i][1].record(stream)
+            if len(inflight) >= DEPTH:
+                retire(inflight.pop(0))
+        while inflight:
+            r_ = inflight.pop(0)
+            retire(r_, keep=not inflight)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    out = last[0]
+    out = last[0] if xch is None else pipe["gathered"]
     if xch is not None:
         n_ranges, n_overflow, n_distinct = out.n_ranges, out.n_overflow_topics, out.n_distinct_topics
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = [a.elapsed_time(b) for a, b in ev] if ev is not None else [step_total / args.steps] * args.steps
     total_ms = float(sum(step_ms))
     # per-rank view (rank 0 prints it): where the max over ranks comes from
     per_rank, imbalance = None, None
@@ -655,12 +676,14 @@ def main():
                 "config": {"workload": workload_name(args, w), "routes_per_gpu": w.n_routes, "filters_per_gpu": w.n_filters,
                            "tenants_per_gpu": w.n_tenants, "topics_per_step_per_gpu": n, "topics_per_step_all_gpus": int(topics_all),
                            "parallelism": "tenant-sharded x%d" % world,
-                           "l2": "flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" % (stats["device_bytes"] / 1e9),
+                           "l2": ("flushed between timed steps (256 MiB memset, untimed); index %.2f GB >> L2" if xch is None else
+                                  "not flushed (the pipelined steps overlap); inputs larger than L2: index %.2f GB per rank") % (stats["device_bytes"] / 1e9),
                            "caps": "MaxPersistentFanout=%s, MaxGroupFanout=%s (reference defaults: INT_MAX, 100)" % (
                                "INT_MAX" if args.max_pfanout == 2 ** 31 - 1 else args.max_pfanout, "INT_MAX" if args.max_gfanout == 2 ** 31 - 1 else args.max_gfanout),
                            "order": "inside the timed region: duplicate (tenant, topic) pairs are found with a device hash table and answered from their "
                                     "first occurrence (%d of %d topics distinct), the distinct ones are matched in locality order (own counting sort)" % (n_distinct, n),
-                           "pipelining": "steps are enqueued without host synchronisation (bfq_match_device_async), %d in flight; timed per step with CUDA events on the launching stream" % DEPTH,
+                           "pipelining": ("steps are enqueued without host synchronisation (bfq_match_device_async), %d in flight; timed per step with CUDA events on the launching stream" % DEPTH) if xch is None else
+                                         "software pipeline of depth 2: the match of step i is enqueued before the exchange of step i-1 (own stream) is issued; the K steps are timed as a whole with CUDA events (first match -> last exchange complete); no L2 flush (index >> L2)",
                            "host": ("rank pinned to NUMA node %d of its GPU (%d cpus) for the GPU legs" % (numa["node"], numa["cpus"])) if numa
                                    else "no NUMA pinning (topology not exposed or single node)",
                            "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
@@ -677,10 +700,9 @@ def main():
                                  "topics_gathered": gathered_info.get("topics"), "ranges_gathered": gathered_info.get("ranges"),
                                  "bytes_received_per_rank": gathered_info.get("bytes_received")} if xch is not None else
                                 {"what": "none (--exchange none)"})
-            if args.scaling == "strong":
-                line["config"]["sharding"] = ("one %s filter set: tenant -> rank by fnv1a64(tenantId) mod %d%s; the SAME %d-topic batch split by owner" % (
-                    args.config, world, "" if args.no_replicate_hot else "; tenants above 1/(4 x ranks) of the batch are hosted by every rank, their topics dealt round-robin",
-                    int(topics_all)))
+            line["config"]["sharding"] = ("ONE %s filter set: tenant -> rank by fnv1a64(tenantId) mod %d%s; a %d-topic batch (%s) split by owner" % (
+                args.config, world, "" if args.no_replicate_hot else "; tenants above 1/(4 x ranks) of the batch are hosted by every rank, their topics dealt round-robin",
+                int(topics_all), "%d x the config's batch: weak scaling" % world if args.scaling == "weak" else "the config's batch: strong scaling"))
         if roof:
             line["roofline"] = roof
         if cpu_base:

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "bfq_index_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]),
     "bfq_index_commit": (_i32, [_vp]),
     "bfq_index_generation": (_i32, [_vp, C.POINTER(C.c_uint64)]),
+    "bfq_index_set_option": (_i32, [_vp, C.c_char_p, _i64]),
     "bfq_index_stats": (_i32, [_vp, _vp, _i32]),
     "bfq_host_build_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32]),
     "bfq_index_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_double)]),

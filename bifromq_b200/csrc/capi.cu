@@ -134,6 +134,7 @@ struct Workspace {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[MAX_CHUNKS] = {};
     cudaEvent_t evk[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done = nullptr;   // device path: recorded behind the last thing a match enqueued (what wait() waits for)
     // resolved tenant table of the previous call on this workspace (reused when the same list comes again)
     uint64_t tab_generation = ~0ull;
     std::vector<uint8_t> tab_blob;
@@ -177,6 +178,7 @@ struct Workspace {
             if (e == cudaSuccess) e = cudaEventCreate(&x);
         for (auto& x : ev_h2d)
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
         return e;
     }
     ~Workspace() {
@@ -192,6 +194,7 @@ struct Workspace {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : evk) if (e) cudaEventDestroy(e);
         for (auto& e : ev_h2d) if (e) cudaEventDestroy(e);
+        if (ev_done) cudaEventDestroy(ev_done);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto& w : work_stream) if (w) cudaStreamDestroy(w);
         if (stream) cudaStreamDestroy(stream);
@@ -233,6 +236,7 @@ struct bfq_index {
     std::shared_ptr<Pool> pool = std::make_shared<Pool>();   // idle workspaces
     int64_t order_min = 32768;           // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
     bool dedup = true;                   // BFQ_DEDUP=0: match duplicates of a (tenant, topic) pair separately
+    int32_t tier0_ctas_per_sm = 0;       // bfq_index_set_option("tier0_ctas_per_sm"): 0 = as many as fit
     double last_kernel_ms = 0;
     int64_t launches = 0, overflow_topics = 0, flagged_topics = 0, deferred_topics = 0, duplicate_topics = 0;
     int64_t full_commits = 0, delta_commits = 0;
@@ -441,6 +445,7 @@ MatchParams core_params(const CoreCtx& c, const SubBatch& sb) {
     p.ranges = w->d_ranges.p + (uint64_t) b * INLINE_RANGES;
     p.dyn_base = (uint64_t) (sb.n_total - b) * INLINE_RANGES + sb.dyn_off;
     p.ranges_cap = p.dyn_base + sb.dyn_cap;
+    p.max_ctas_per_sm = c.h->tier0_ctas_per_sm;
     return p;
 }
 
@@ -565,12 +570,14 @@ int32_t copy_counters(const CoreCtx& c, const SubBatch& sb) {
 // Waits for the sub-batch and handles what the optimistic enqueue could not: topics that need tier 2 (frontier / range
 // overflow of tier 1: scratch sized from the index statistics, then the followers and caps passes once more for what
 // tier 2 added) and slices that turned out too small (BFQ_RETRY_GROW). *reran = tier 2 changed the spans.
-int32_t finish_core(const CoreCtx& c, const SubBatch& sb, CoreOut* out, bool* reran) {
+int32_t finish_core(const CoreCtx& c, const SubBatch& sb, CoreOut* out, bool* reran, cudaEvent_t done = nullptr) {
     Workspace* w = c.w;
     cudaStream_t stream = c.stream;
     unsigned long long* hc = w->h_counters.p + (size_t) sb.chunk * CTR_COUNT;
     if (reran) *reran = false;
-    CUDA_TRY(cudaStreamSynchronize(stream));
+    // the device path waits for ITS match only (an event behind it): later matches may already be queued on the same stream
+    if (done) CUDA_TRY(cudaEventSynchronize(done));
+    else CUDA_TRY(cudaStreamSynchronize(stream));
     out->n_overflow += (int64_t) hc[CTR_OVERFLOW];
     out->n_deferred += (int64_t) hc[CTR_DEFER];
     if (hc[CTR_OVERFLOW] > 0) {
@@ -695,7 +702,10 @@ int32_t device_enqueue(DeviceLease* L) {
     const SubBatch sb = whole_batch(L->ws, L->n);
     rc = enqueue_core(L->ctx, sb, &L->co);
     if (rc != BFQ_OK) return rc;
-    return copy_counters(L->ctx, sb);
+    rc = copy_counters(L->ctx, sb);
+    if (rc != BFQ_OK) return rc;
+    CUDA_TRY(cudaEventRecord(L->ws->ev_done, L->ctx.stream));
+    return BFQ_OK;
 }
 
 int32_t device_wait(DeviceLease* L) {
@@ -703,7 +713,7 @@ int32_t device_wait(DeviceLease* L) {
     L->done = true;
     for (int attempt = 0;; attempt++) {
         if (attempt == 8) return L->rc = fail(BFQ_E_STATE, "buffer sizing did not converge");
-        int32_t rc = finish_core(L->ctx, whole_batch(L->ws, L->n), &L->co, nullptr);
+        int32_t rc = finish_core(L->ctx, whole_batch(L->ws, L->n), &L->co, nullptr, L->ws->ev_done);
         if (rc == BFQ_OK) break;
         if (rc != BFQ_RETRY_GROW) return L->rc = rc;
         if (cudaDeviceSynchronize() != cudaSuccess) return L->rc = fail(BFQ_E_CUDA, "cudaDeviceSynchronize");
@@ -1172,6 +1182,17 @@ int32_t bfq_index_commit(bfq_index* h) {
         h->full_commits++;
     }
     return rc;
+}
+
+int32_t bfq_index_set_option(bfq_index* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    const std::string n(name);
+    if (n == "tier0_ctas_per_sm") h->tier0_ctas_per_sm = (int32_t) std::max<int64_t>(0, std::min<int64_t>(value, 32));
+    else if (n == "order_min_topics") h->order_min = value <= 0 ? (int64_t) 1 << 62 : value;
+    else if (n == "dedup") h->dedup = value != 0;
+    else return fail(BFQ_E_INVALID, "unknown option: " + n);
+    return BFQ_OK;
 }
 
 int32_t bfq_index_generation(bfq_index* h, uint64_t* generation) {
@@ -1643,7 +1664,7 @@ void bfq_device_result_release(bfq_device_result* out) {
     if (!out || !out->lease) return;
     auto* L = static_cast<DeviceLease*>(out->lease);
     cudaSetDevice(L->pool->device);
-    if (!L->done) cudaStreamSynchronize(L->ctx.stream);   // never hand a busy workspace back
+    if (!L->done) cudaEventSynchronize(L->ws->ev_done);   // never hand a busy workspace back
     give_back(L->pool, L->ws);
     delete L;
     out->lease = nullptr;

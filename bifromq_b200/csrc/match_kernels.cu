@@ -1152,6 +1152,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
         ctas_per_sm = ctas_of[variant];
     }
     // persistent grid (SM count x resident CTAs); warps claim 32-topic chunks with one atomicAdd each
+    if (p.max_ctas_per_sm > 0) ctas_per_sm = std::min(ctas_per_sm, (int) p.max_ctas_per_sm);
     int64_t ctas = (int64_t) sms * ctas_per_sm;
     const int64_t need = ((p.n_topics + L_CHUNK - 1) / L_CHUNK + L_WARPS - 1) / L_WARPS;
     if (need < ctas) ctas = need < 1 ? 1 : need;

@@ -45,6 +45,8 @@ struct MatchParams {
     // 0..n_topics. Only the order in which lanes pick topics changes; every output stays indexed by topic.
     const uint32_t* order;
     const unsigned long long* order_count;   // device scalar: entries of `order` (the batch's distinct topics); with order only
+    int32_t max_ctas_per_sm;        // tier 0: cap of resident CTAs per SM (0 = as many as fit); one slot less leaves room for a
+                                    // concurrently running exchange (NCCL) kernel
     // tiers 1/2: list of topic indices to process (nullptr => all topics 0..n_topics)
     const uint32_t* work_list;
     int64_t n_work;

@@ -214,14 +214,16 @@ extern "C" {
 // replicate_hot != 0: a tenant that carries more than 1 / (4 shard_count) of the batch is hosted by EVERY shard and its
 // topics are dealt round-robin by batch position (SURVEY.md 8e "replicas" mode, applied per hot tenant): with Zipf tenant
 // sizes the largest tenant alone is 13 % of C4's batch, so pure hash placement caps 8 GPUs at ~4x.
+// topic_mult > 1: the publish batch is topic_mult times the config's size (same distributions): N GPUs serving N times the
+// publish traffic of ONE filter set.
 bfqw* bfqw_generate2(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
-                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot);
+                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot, int32_t topic_mult);
 bfqw* bfqw_generate(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
                     const char* tenant_prefix, int32_t nthreads) {
-    return bfqw_generate2(config, seed, scale, shard_index, shard_count, tenant_prefix, nthreads, 0);
+    return bfqw_generate2(config, seed, scale, shard_index, shard_count, tenant_prefix, nthreads, 0, 1);
 }
 bfqw* bfqw_generate2(const char* config, uint64_t seed, double scale, int32_t shard_index, int32_t shard_count,
-                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot) {
+                     const char* tenant_prefix, int32_t nthreads, int32_t replicate_hot, int32_t topic_mult) {
     Cfg cfg = (Cfg) (config && config[0] == 'C' ? config[1] - '0' : 0);
     if (cfg < C1 || cfg > C5) return nullptr;
     if (shard_count < 1) shard_count = 1;
@@ -329,7 +331,8 @@ bfqw* bfqw_generate2(const char* config, uint64_t seed, double scale, int32_t sh
         return (int64_t) (std::lower_bound(cum.begin(), cum.end(), u) - cum.begin());
     };
     if (cfg != C5) {
-        for (int64_t i = 0; i < pl.n_topics; i++) {
+        const int64_t n_batch = pl.n_topics * (int64_t) std::max(1, topic_mult);
+        for (int64_t i = 0; i < n_batch; i++) {
             const int64_t t = std::min<int64_t>(pick_tenant(), pl.n_tenants - 1);
             // draw the random numbers regardless of ownership so every shard sees the same batch
             const double hit = r.uniform(), pop = r.uniform();

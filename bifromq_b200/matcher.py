@@ -177,6 +177,9 @@ class GpuRouteIndex:
                  "duplicate_topics", "full_commits", "delta_commits", "garbage_slots"]
         return dict(zip(names, s.tolist()))
 
+    def set_option(self, name, value):
+        N.check(N.lib.bfq_index_set_option(self._h, name.encode(), int(value)))
+
     def generation(self):
         g = C.c_uint64(0)
         N.check(N.lib.bfq_index_generation(self._h, C.byref(g)))

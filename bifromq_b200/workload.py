@@ -26,7 +26,7 @@ def _load():
         lib.bfqw_generate.restype = C.c_void_p
         lib.bfqw_generate.argtypes = [C.c_char_p, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
         lib.bfqw_generate2.restype = C.c_void_p
-        lib.bfqw_generate2.argtypes = [C.c_char_p, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+        lib.bfqw_generate2.argtypes = [C.c_char_p, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
         lib.bfqw_free.argtypes = [C.c_void_p]
         lib.bfqw_info.argtypes = [C.c_void_p, C.c_void_p]
         for name in ["keys", "key_off", "vals", "val_off", "tenants", "tenant_off", "topics", "topic_off", "topic_tenant",
@@ -48,15 +48,17 @@ def _view(p, count, dtype):
 class Workload:
     SEED = 0xB1F20
 
-    def __init__(self, config, seed=SEED, scale=1.0, shard_index=0, shard_count=1, tenant_prefix="", nthreads=None, replicate_hot=False):
+    def __init__(self, config, seed=SEED, scale=1.0, shard_index=0, shard_count=1, tenant_prefix="", nthreads=None, replicate_hot=False,
+                 topic_mult=1):
         """shard_index / shard_count: keep the tenants this shard owns (fnv1a64(tenant) % shard_count) and their topics;
-        replicate_hot: tenants above 1 / (4 shard_count) of the batch live on every shard, topics dealt round-robin"""
+        replicate_hot: tenants above 1 / (4 shard_count) of the batch live on every shard, topics dealt round-robin;
+        topic_mult: the publish batch is topic_mult times the config's size (N GPUs serving N times the traffic of one filter set)"""
         lib = _load()
         if nthreads is None:
             nthreads = max(1, min(32, os.cpu_count() or 1))
         self.config, self.seed, self.scale = config, seed, scale
         self._h = lib.bfqw_generate2(config.encode(), seed, float(scale), shard_index, shard_count, tenant_prefix.encode(), nthreads,
-                                     1 if replicate_hot else 0)
+                                     1 if replicate_hot else 0, int(topic_mult))
         if not self._h:
             raise ValueError("unknown workload config %r" % config)
         info = np.zeros(8, np.int64)

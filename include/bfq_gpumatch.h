@@ -83,6 +83,13 @@ int32_t bfq_index_apply(bfq_index* h, const uint8_t* add_keys, const int64_t* ad
  * undecodable key leaves the staging area untouched. */
 int32_t bfq_index_commit(bfq_index* h);
 int32_t bfq_index_generation(bfq_index* h, uint64_t* generation);   /* 0 before the first commit */
+/* Tuning knobs (defaults are the measured best for a handle that has the GPU to itself):
+ *   "tier0_ctas_per_sm"  cap of the lane-per-topic kernel's resident CTAs per SM (0 = as many as fit, 7 on a B200). One slot
+ *                        less leaves room for kernels that must run BESIDE the matching: the exchange of the previous batch
+ *                        (bfq_exchange_gather on another stream) in a multi-GPU pipeline;
+ *   "order_min_topics"   batches of at least this many topics are de-duplicated and matched in locality order (default 32768);
+ *   "dedup"              0: match repeated (tenant, topic) pairs separately. */
+int32_t bfq_index_set_option(bfq_index* h, const char* name, int64_t value);
 
 /* stats[k], k < n: 0 routes, 1 tenants, 2 trie nodes, 3 hash-table slots, 4 device bytes, 5 max nodes per
  * depth, 6 kernel launches so far, 7 overflow (tier-2) topics so far, 8 cap-flagged topics so far,
