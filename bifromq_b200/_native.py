@@ -34,7 +34,8 @@ class BfqDeviceResult(C.Structure):
 
 class BfqGathered(C.Structure):
     _fields_ = [("d_route_count", C.c_void_p), ("d_span_count", C.c_void_p), ("d_ranges", C.c_void_p),
-                ("topic_base", C.POINTER(C.c_int64)), ("range_base", C.POINTER(C.c_int64)), ("n_topics_total", C.c_int64),
+                ("topic_base", C.POINTER(C.c_int64)), ("range_base", C.POINTER(C.c_int64)), ("topic_count", C.POINTER(C.c_int64)),
+                ("range_count", C.POINTER(C.c_int64)), ("n_topics_total", C.c_int64),
                 ("n_ranges_total", C.c_int64), ("bytes_received", C.c_int64), ("world", C.c_int32)]
 
 

@@ -136,18 +136,27 @@ class Gathered:
         self.world = raw.world
         self.topic_base = [raw.topic_base[i] for i in range(raw.world + 1)]
         self.range_base = [raw.range_base[i] for i in range(raw.world + 1)]
+        self.topic_count = [raw.topic_count[i] for i in range(raw.world)]
+        self.range_count = [raw.range_count[i] for i in range(raw.world)]
         self.n_topics_total, self.n_ranges_total, self.bytes_received = raw.n_topics_total, raw.n_ranges_total, raw.bytes_received
         self._device = device
 
+    def _slices(self, ptr, base, count, width):
+        import torch
+        whole = device_view(ptr, max(width * base[-1], width), "<u4", self._device)
+        parts = [whole[width * base[r]:width * (base[r] + count[r])] for r in range(self.world)]
+        return torch.cat(parts) if self.world > 1 else parts[0]
+
     def route_count(self):
-        return device_view(self.raw.d_route_count, max(self.n_topics_total, 1), "<u4", self._device)[:self.n_topics_total]
+        """matched routes per topic, the ranks' slices concatenated in rank order (padding removed)"""
+        return self._slices(self.raw.d_route_count, self.topic_base, self.topic_count, 1)
 
     def span_count(self):
-        return device_view(self.raw.d_span_count, max(self.n_topics_total, 1), "<u4", self._device)[:self.n_topics_total]
+        return self._slices(self.raw.d_span_count, self.topic_base, self.topic_count, 1)
 
     def ranges(self):
-        """[n_ranges_total, 2] uint32: first rank, count (| 0x80000000 for a multi-segment filter)"""
-        return device_view(self.raw.d_ranges, max(2 * self.n_ranges_total, 2), "<u4", self._device)[:2 * self.n_ranges_total].view(-1, 2)
+        """[n_ranges_total, 2] uint32: first rank, count (| 0x80000000 for a multi-segment filter), slices concatenated"""
+        return self._slices(self.raw.d_ranges, self.range_base, self.range_count, 2).view(-1, 2)
 
 
 class Exchange:

@@ -228,12 +228,14 @@ int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int6
 #define BFQ_EXCHANGE_RANGES 2
 typedef struct bfq_exchange bfq_exchange;
 typedef struct {
-    const uint32_t* d_route_count;   /* [n_topics_total] matched routes per topic, ranks concatenated in rank order */
-    const uint32_t* d_span_count;    /* [n_topics_total] matched ranges per topic (NULL with BFQ_EXCHANGE_COUNTS) */
-    const bfq_range* d_ranges;       /* [n_ranges_total] dense: a topic's ranges follow those of the topic before it
-                                        (NULL with BFQ_EXCHANGE_COUNTS) */
-    const int64_t* topic_base;       /* host [world + 1]: rank r's topics are [topic_base[r], topic_base[r + 1]) */
-    const int64_t* range_base;       /* host [world + 1] */
+    const uint32_t* d_route_count;   /* matched routes per topic; rank r's slice starts at topic_base[r] */
+    const uint32_t* d_span_count;    /* matched ranges per topic, same slices (NULL with BFQ_EXCHANGE_COUNTS) */
+    const bfq_range* d_ranges;       /* rank r's slice starts at range_base[r]; dense inside a slice: a topic's ranges follow
+                                        those of the topic before it (NULL with BFQ_EXCHANGE_COUNTS) */
+    const int64_t* topic_base;       /* host [world + 1]: rank r's topics are [topic_base[r], topic_base[r] + topic_count[r]) — the  */
+    const int64_t* range_base;       /* host [world + 1]   slices have one padded stride (the payload travels as ncclAllGather)    */
+    const int64_t* topic_count;      /* host [world] */
+    const int64_t* range_count;      /* host [world] */
     int64_t n_topics_total, n_ranges_total;
     int64_t bytes_received;          /* payload bytes this rank received from its peers */
     int32_t world;

@@ -683,10 +683,10 @@ def test_exchange_gather_single_rank(B):
         g = x.gather(out, ranges=ranges, stream=stream)
         torch.cuda.synchronize()
         res = idx.match(tenants, w.topics, w.topic_off, w.topic_tenant[:n])
-        assert g.world == 1 and g.topic_base == [0, n] and g.n_topics_total == n
+        assert g.world == 1 and g.topic_base[0] == 0 and g.topic_count == [n] and g.n_topics_total == n
         assert g.route_count().cpu().numpy().tolist() == res.route_count.tolist()
         if ranges:
-            assert g.range_base == [0, len(res.ranges)]
+            assert g.range_base[0] == 0 and g.range_count == [len(res.ranges)]
             assert g.span_count().cpu().numpy().tolist() == res.span_count.tolist()
             got = g.ranges().cpu().numpy()
             want = np.stack([res.ranges["first"], res.ranges["count"]], axis=1)
