@@ -151,7 +151,7 @@ struct Workspace {
     DevBuf<uint32_t> d_span_begin, d_span_count, d_route_count, d_overflow, d_flagged, d_kept, d_defer;
     DevBuf<uint2> d_ranges, d_scratch, d_ranges_c;
     DevBuf<uint8_t> d_scan_tmp;
-    DevBuf<uint32_t> d_cnt, d_new_begin;
+    DevBuf<uint32_t> d_cnt, d_new_begin, d_final_begin, d_final_count;
     // locality order + dedup (launch_order): per compute-stream slot (two sub-batches can be in flight)
     DevBuf<uint32_t> d_ord_keys, d_leader, d_order;
     DevBuf<unsigned long long> d_hash_tab;   // 2 x hash_stride
@@ -187,7 +187,8 @@ struct Workspace {
         d_topics.release(); d_topic_off.release(); d_topic_tenant.release();
         d_span_begin.release(); d_span_count.release(); d_route_count.release(); d_overflow.release();
         d_flagged.release(); d_kept.release(); d_defer.release(); d_exp_counts.release(); d_ranges_c.release();
-        d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_ranges.release(); d_scratch.release();
+        d_scan_tmp.release(); d_cnt.release(); d_new_begin.release(); d_final_begin.release(); d_final_count.release();
+        d_ranges.release(); d_scratch.release();
         d_throttled.release(); d_counters.release(); h_counters.release();
         d_ord_keys.release(); d_leader.release(); d_order.release(); d_hash_tab.release(); d_hist.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
@@ -1365,6 +1366,8 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     CUDA_TRY(w->d_topic_tenant.reserve(nn));
     CUDA_TRY(w->d_cnt.reserve(nn));
     CUDA_TRY(w->d_new_begin.reserve(nn));
+    CUDA_TRY(w->d_final_begin.reserve(nn));
+    CUDA_TRY(w->d_final_count.reserve(nn));
     CUDA_TRY(w->h_span_begin.reserve(nn));
     CUDA_TRY(w->h_span_count.reserve(nn));
     CUDA_TRY(w->h_route_count.reserve(nn));
@@ -1372,7 +1375,7 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     // Large batches are cut into sub-batches that flow through three streams: all H2D copies on one, the kernels +
     // compaction + D2H of consecutive sub-batches alternating on two others, so the copy of sub-batch c+1 and the
     // result read-back of c-1 overlap the kernels of c (PCIe is full duplex; the copies dominate the host path).
-    int C = n >= (1 << 17) ? 4 : 1;
+    int C = n >= (1 << 19) ? 8 : n >= (1 << 17) ? 4 : 1;   // more, smaller sub-batches shorten the un-overlapped tail (the last sub-batch's kernels + read-back)
     CoreOut co;
     int64_t rbase = 0, tbase = 0;
     double kernel_ms = -1;
@@ -1435,8 +1438,11 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
             cp.span_begin = w->d_span_begin.p + sb.begin;
             cp.span_count = w->d_span_count.p + sb.begin;
             cp.ranges = w->d_ranges.p + (uint64_t) sb.begin * INLINE_RANGES;
+            cp.leader = (wants_order(ctx, sb) && h->dedup) ? w->d_leader.p + sb.begin : nullptr;   // repeats share their leader's dense span
             cp.counts = w->d_cnt.p + sb.begin;
             cp.new_begin = w->d_new_begin.p + sb.begin;
+            cp.final_begin = w->d_final_begin.p + sb.begin;
+            cp.final_count = w->d_final_count.p + sb.begin;
             cp.ranges_out = w->d_ranges_c.p + region;
             cp.ranges_out_cap = (uint64_t) sb.n * INLINE_RANGES + sb.dyn_cap;
             cp.total_out = w->d_counters.p + (size_t) c * CTR_COUNT + CTR_ROUTES;
@@ -1485,8 +1491,8 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
             cp.out_base = (uint32_t) rbase;
             CUDA_TRY(launch_compact(cp, scan_tmp, &tmp_bytes, st, 2));
             co.n_launches += 4;
-            CUDA_TRY(cudaMemcpyAsync(w->h_span_begin.p + sb.begin, w->d_new_begin.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(w->h_span_count.p + sb.begin, w->d_cnt.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(w->h_span_begin.p + sb.begin, w->d_final_begin.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(w->h_span_count.p + sb.begin, w->d_final_count.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(w->h_route_count.p + sb.begin, w->d_route_count.p + sb.begin, (size_t) sb.n * 4, cudaMemcpyDeviceToHost, st));
             if (total_c > 0)
                 CUDA_TRY(cudaMemcpyAsync(w->h_ranges.p + rbase, w->d_ranges_c.p + region, (size_t) total_c * sizeof(uint2), cudaMemcpyDeviceToHost, st));

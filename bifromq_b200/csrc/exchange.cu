@@ -123,7 +123,7 @@ __global__ void exchange_meta_kernel(long long* meta, long long n_topics, const 
 struct bfq_exchange {
     int device = 0, rank = 0, world = 1;
     ncclComm_t comm = nullptr;
-    XBuf<uint32_t> d_cnt, d_begin;          // local compaction scratch
+    XBuf<uint32_t> d_cnt, d_begin, d_final_begin, d_final_count;   // local compaction scratch
     XBuf<uint8_t> d_scan_tmp;
     XBuf<long long> d_meta;                 // {n_topics, n_ranges} x world
     long long* h_meta = nullptr;            // pinned copy
@@ -133,7 +133,7 @@ struct bfq_exchange {
     ~bfq_exchange() {
         cudaSetDevice(device);
         if (comm && nccl().ok) nccl().CommDestroy(comm);
-        d_cnt.release(); d_begin.release(); d_scan_tmp.release(); d_meta.release();
+        d_cnt.release(); d_begin.release(); d_final_begin.release(); d_final_count.release(); d_scan_tmp.release(); d_meta.release();
         g_route_count.release(); g_span_count.release(); g_ranges.release();
         if (h_meta) cudaFreeHost(h_meta);
     }
@@ -193,13 +193,18 @@ int32_t bfq_exchange_gather(bfq_exchange* x, const bfq_device_result* res, int32
     // ---- 1. local compaction, phase 1 (counts, exclusive scan); the total goes into this rank's meta slot on the device
     X_CUDA(x->d_cnt.reserve((size_t) std::max<int64_t>(n, 1)));
     X_CUDA(x->d_begin.reserve((size_t) std::max<int64_t>(n, 1)));
+    X_CUDA(x->d_final_begin.reserve((size_t) std::max<int64_t>(n, 1)));
+    X_CUDA(x->d_final_count.reserve((size_t) std::max<int64_t>(n, 1)));
     CompactParams cp{};
     cp.n_topics = n;
     cp.span_begin = res->d_span_begin;
     cp.span_count = res->d_span_count;
     cp.ranges = reinterpret_cast<const uint2*>(res->d_ranges);
+    cp.leader = nullptr;            // peers get every topic's ranges in full: a slice must be self-contained
     cp.counts = x->d_cnt.p;
     cp.new_begin = x->d_begin.p;
+    cp.final_begin = x->d_final_begin.p;
+    cp.final_count = x->d_final_count.p;
     cp.total_out = reinterpret_cast<unsigned long long*>(x->d_meta.p + 2 * x->rank + 1);
     size_t tmp_bytes = 0;
     {

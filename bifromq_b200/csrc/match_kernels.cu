@@ -854,9 +854,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ compaction
-__global__ void compact_counts_kernel(int64_t n, const uint32_t* span_count, uint32_t* counts) {
+// counts[i] = ranges topic i contributes to the dense array: its own, or none if it repeats an earlier (tenant, topic) pair —
+// a repeat shares its leader's dense span instead of copying it (a third of BASELINE C4's batch: 13 MB less D2H per 1M topics)
+__global__ void compact_counts_kernel(const CompactParams p) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counts[i] = span_count[i] & SPAN_COUNT_MASK;
+    if (i < p.n_topics) p.counts[i] = (p.leader && p.leader[i] != (uint32_t) i) ? 0u : (p.span_count[i] & SPAN_COUNT_MASK);
 }
 __global__ void compact_total_kernel(const CompactParams p) {
     *p.total_out = (unsigned long long) p.new_begin[p.n_topics - 1] + p.counts[p.n_topics - 1];
@@ -864,10 +866,16 @@ __global__ void compact_total_kernel(const CompactParams p) {
 __global__ void compact_gather_kernel(const CompactParams p) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_topics) return;
-    const uint32_t c = p.counts[i], nb = p.new_begin[i], ob = p.span_begin[i];
-    if ((uint64_t) nb + c <= p.ranges_out_cap)
-        for (uint32_t j = 0; j < c; j++) p.ranges_out[nb + j] = p.ranges[ob + j];
-    p.new_begin[i] = nb + p.out_base;   // final position in the concatenated result
+    const uint32_t l = p.leader ? p.leader[i] : (uint32_t) i;
+    const uint32_t c = p.span_count[i] & SPAN_COUNT_MASK;     // a repeat carries its leader's span (finalize_kernel)
+    const uint32_t nb = p.new_begin[l];                       // the scan's output is not modified here: no race with the leader's thread
+    if (l == (uint32_t) i) {
+        const uint32_t ob = p.span_begin[i];
+        if ((uint64_t) nb + c <= p.ranges_out_cap)
+            for (uint32_t j = 0; j < c; j++) p.ranges_out[nb + j] = p.ranges[ob + j];
+    }
+    p.final_begin[i] = nb + p.out_base;   // position in the concatenated result
+    p.final_count[i] = c;
 }
 
 // ------------------------------------------------------------------------------------------------ caps
@@ -1164,7 +1172,7 @@ cudaError_t launch_compact(const CompactParams& p, void* d_scan_tmp, size_t* tmp
     if (p.n_topics <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned) ((p.n_topics + 255) / 256);
     if (phase == 1) {   // clean counts, exclusive scan, total
-        compact_counts_kernel<<<blocks, 256, 0, stream>>>(p.n_topics, p.span_count, p.counts);
+        compact_counts_kernel<<<blocks, 256, 0, stream>>>(p);
         cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, *tmp_bytes, p.counts, p.new_begin, (int) p.n_topics, stream);
         if (e != cudaSuccess) return e;
         compact_total_kernel<<<1, 1, 0, stream>>>(p);

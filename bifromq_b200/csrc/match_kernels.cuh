@@ -177,8 +177,11 @@ struct CompactParams {
     const uint32_t* span_begin;     // in
     const uint32_t* span_count;     // in (flag bits allowed)
     const uint2* ranges;            // in
+    const uint32_t* leader;         // optional [n]: leader[i] != i marks a repeat of topic leader[i] (shares its dense span)
     uint32_t* counts;               // scratch [n]
-    uint32_t* new_begin;            // out [n]
+    uint32_t* new_begin;            // scratch [n]: exclusive scan of counts
+    uint32_t* final_begin;          // out [n] (phase 2): first range of topic i in the concatenated result
+    uint32_t* final_count;          // out [n] (phase 2): its number of ranges
     uint2* ranges_out;              // out [total]
     uint64_t ranges_out_cap;
     uint32_t out_base;              // index of ranges_out[0] in the concatenated result (added to new_begin in phase 2)
