@@ -39,6 +39,11 @@ class BfqGathered(C.Structure):
                 ("n_ranges_total", C.c_int64), ("bytes_received", C.c_int64), ("world", C.c_int32)]
 
 
+class BfqFanoutResult(C.Structure):
+    _fields_ = [("d_pack_offsets", C.c_void_p), ("d_pack_topic", C.c_void_p), ("d_pack_rank", C.c_void_p), ("d_pack_member", C.c_void_p),
+                ("n_pairs", C.c_int64), ("n_deliverers", C.c_int32), ("ordered_share_id", C.c_int32), ("generation", C.c_uint64)]
+
+
 EXCHANGE_ID_BYTES, EXCHANGE_COUNTS, EXCHANGE_RANGES = 128, 1, 2
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 _SIGNATURES = {
@@ -75,6 +80,8 @@ _SIGNATURES = {
     "bfq_device_result_wait": (_i32, [C.POINTER(BfqDeviceResult)]),
     "bfq_device_result_release": (None, [C.POINTER(BfqDeviceResult)]),
     "bfq_expand_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "bfq_fanout_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(BfqFanoutResult)]),
+    "bfq_fanout_deliverer": (_i32, [_vp, _i32, C.POINTER(_i32), _vp, _i64, C.POINTER(_i64)]),
     "bfq_exchange_unique_id": (_i32, [_vp, _i32]),
     "bfq_exchange_create": (_i32, [_i32, _i32, _i32, _vp, C.POINTER(_vp)]),
     "bfq_exchange_destroy": (None, [_vp]),

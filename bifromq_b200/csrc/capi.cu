@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include "../../include/bfq_gpumatch.h"
 #include "codec.h"
 #include "index_builder.h"
+#include "fanout.h"
 #include "match_kernels.cuh"
 
 using namespace bfq;
@@ -96,7 +98,17 @@ struct Snapshot {
     struct TenantHost {
         std::shared_ptr<const KVBlob> kv;
         std::shared_ptr<const std::vector<uint8_t>> rkind;
+        std::shared_ptr<const TenantFan> fan;   // routes -> deliverer ids, built on the first fan-out that sees this blob
     };
+    // fan-out tables of the whole snapshot (device), assembled from the tenants' on first use
+    struct FanTable {
+        DevBuf<uint32_t> d_rdeliv, d_gmem_off, d_gmem_deliv;
+        DevBuf<uint8_t> d_gordered;
+        uint32_t n_deliverers = 0;   // incl. the reserved last id (ordered shared subscriptions)
+        ~FanTable() { d_rdeliv.release(); d_gmem_off.release(); d_gmem_deliv.release(); d_gordered.release(); }
+    };
+    std::mutex fan_mu;
+    std::shared_ptr<FanTable> fan;
     std::vector<TenantHost> th;
     uint64_t garbage_slots = 0;   // slots of regions that delta commits replaced (reclaimed by the next full build)
     int64_t delta_commits = 0;    // delta commits since the last full build
@@ -161,6 +173,10 @@ struct Workspace {
     DevBuf<unsigned long long> d_counters;
     PinBuf<unsigned long long> h_counters;
     DevBuf<unsigned long long> d_exp_counts;
+    // fan-out expansion (fanout.cu)
+    DevBuf<uint32_t> d_fo_counts, d_fo_base, d_pack_topic, d_pack_rank, d_pack_member;
+    DevBuf<long long> d_pack_offsets;
+    DevBuf<uint8_t> d_fo_tmp;
     // pinned result buffers
     PinBuf<uint32_t> h_span_begin, h_span_count, h_route_count;
     PinBuf<uint2> h_ranges;
@@ -191,6 +207,8 @@ struct Workspace {
         d_ranges.release(); d_scratch.release();
         d_throttled.release(); d_counters.release(); h_counters.release();
         d_ord_keys.release(); d_leader.release(); d_order.release(); d_hash_tab.release(); d_hist.release();
+        d_fo_counts.release(); d_fo_base.release(); d_pack_topic.release(); d_pack_rank.release(); d_pack_member.release();
+        d_pack_offsets.release(); d_fo_tmp.release();
         h_span_begin.release(); h_span_count.release(); h_route_count.release(); h_ranges.release(); h_throttled.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : evk) if (e) cudaEventDestroy(e);
@@ -235,6 +253,7 @@ struct bfq_index {
     std::shared_ptr<Snapshot> snap;
     uint64_t next_generation = 1;
     std::shared_ptr<Pool> pool = std::make_shared<Pool>();   // idle workspaces
+    std::shared_ptr<DelivererTable> deliverers = std::make_shared<DelivererTable>();   // (subBrokerId, delivererKey) -> id, append-only
     int64_t order_min = 32768;           // batches smaller than this are matched in arrival order (BFQ_ORDER=0: never order)
     bool dedup = true;                   // BFQ_DEDUP=0: match duplicates of a (tenant, topic) pair separately
     int32_t tier0_ctas_per_sm = 0;       // bfq_index_set_option("tier0_ctas_per_sm"): 0 = as many as fit
@@ -1735,6 +1754,136 @@ int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int6
     }
     std::lock_guard<std::mutex> g(h->mu);
     h->launches += launches;
+    return BFQ_OK;
+}
+
+// ---------------------------------------------------------------- fan-out expansion (fanout.cu)
+namespace {
+// the snapshot's fan-out tables: every tenant's routes resolved to deliverer ids (cached per tenant blob: a delta commit
+// re-resolves only the tenants it rebuilt), concatenated in rank order and uploaded once per snapshot
+int32_t ensure_fan_table(bfq_index* h, Snapshot* s, std::shared_ptr<Snapshot::FanTable>* out) {
+    std::lock_guard<std::mutex> g(s->fan_mu);
+    if (s->fan) {
+        *out = s->fan;
+        return BFQ_OK;
+    }
+    const size_t T = s->th.size();
+    std::vector<std::string> errs(T);
+    {
+        std::atomic<size_t> cursor{0};
+        auto worker = [&]() {
+            while (true) {
+                const size_t i = cursor.fetch_add(1);
+                if (i >= T) break;
+                if (s->th[i].fan) continue;
+                auto tf = std::make_shared<TenantFan>();
+                if (build_tenant_fan(*s->th[i].kv, h->deliverers.get(), tf.get(), &errs[i])) s->th[i].fan = std::move(tf);
+            }
+        };
+        const unsigned nt = (unsigned) std::max<size_t>(1, std::min<size_t>(std::min<size_t>(std::thread::hardware_concurrency(), 64), T));
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto& x : th) x.join();
+    }
+    for (size_t i = 0; i < T; i++)
+        if (!s->th[i].fan) return fail(BFQ_E_INVALID, "fan-out tables: " + errs[i]);
+    std::vector<uint32_t> rdeliv((size_t) std::max<int64_t>(s->flat.n_routes, 1), 0), gmem_off(1, 0), gmem_deliv;
+    std::vector<uint8_t> gordered;
+    for (size_t i = 0; i < T; i++) {
+        const TenantFan& tf = *s->th[i].fan;
+        const uint32_t gbase = (uint32_t) gordered.size(), mbase = (uint32_t) gmem_deliv.size();
+        const int64_t lo = s->flat.tenants[i].lo;
+        for (size_t r = 0; r < tf.rdeliv.size(); r++)
+            rdeliv[(size_t) lo + r] = (tf.rdeliv[r] & FO_GROUP_BIT) ? (FO_GROUP_BIT | ((tf.rdeliv[r] & ~FO_GROUP_BIT) + gbase)) : tf.rdeliv[r];
+        for (size_t k = 1; k < tf.gmem_off.size(); k++) gmem_off.push_back(tf.gmem_off[k] + mbase);
+        gmem_deliv.insert(gmem_deliv.end(), tf.gmem_deliv.begin(), tf.gmem_deliv.end());
+        gordered.insert(gordered.end(), tf.gordered.begin(), tf.gordered.end());
+    }
+    auto ft = std::make_shared<Snapshot::FanTable>();
+    {
+        std::lock_guard<std::mutex> gd(h->deliverers->mu);
+        ft->n_deliverers = (uint32_t) h->deliverers->list.size() + 1;
+    }
+    if (ft->n_deliverers > fanout_max_deliverers()) return fail(BFQ_E_RANGE, "more distinct (subBrokerId, delivererKey) pairs than the fan-out pass counts per tile");
+    CUDA_TRY(ft->d_rdeliv.reserve(rdeliv.size()));
+    CUDA_TRY(ft->d_gmem_off.reserve(gmem_off.size()));
+    CUDA_TRY(ft->d_gmem_deliv.reserve(std::max<size_t>(gmem_deliv.size(), 1)));
+    CUDA_TRY(ft->d_gordered.reserve(std::max<size_t>(gordered.size(), 1)));
+    CUDA_TRY(cudaMemcpy(ft->d_rdeliv.p, rdeliv.data(), rdeliv.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ft->d_gmem_off.p, gmem_off.data(), gmem_off.size() * 4, cudaMemcpyHostToDevice));
+    if (!gmem_deliv.empty()) CUDA_TRY(cudaMemcpy(ft->d_gmem_deliv.p, gmem_deliv.data(), gmem_deliv.size() * 4, cudaMemcpyHostToDevice));
+    if (!gordered.empty()) CUDA_TRY(cudaMemcpy(ft->d_gordered.p, gordered.data(), gordered.size(), cudaMemcpyHostToDevice));
+    s->fan = ft;
+    *out = ft;
+    return BFQ_OK;
+}
+}  // namespace
+
+int32_t bfq_fanout_device(const bfq_device_result* res, const int64_t* d_offsets, const int64_t* d_ranks, int64_t n_pairs, void* stream,
+                          bfq_fanout_result* out) {
+    if (!res || !res->lease || !out || !d_offsets || n_pairs < 0 || (n_pairs > 0 && !d_ranks)) return fail(BFQ_E_INVALID, "bad argument");
+    auto* L = static_cast<DeviceLease*>(res->lease);
+    if (!L->done || L->rc != BFQ_OK) return fail(BFQ_E_STATE, "bfq_fanout_device needs a completed match (bfq_device_result_wait)");
+    if (n_pairs >= (int64_t) 0xFFFFFFF0ll) return fail(BFQ_E_RANGE, "more than 2^32 (topic, route) pairs in one batch; split the batch");
+    bfq_index* h = L->h;
+    Workspace* w = L->ws;
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::shared_ptr<Snapshot::FanTable> ft;
+    int32_t rc = ensure_fan_table(h, L->snap.get(), &ft);
+    if (rc != BFQ_OK) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    const int64_t tile = fanout_tile();
+    const size_t n_tiles = (size_t) std::max<int64_t>(1, (n_pairs + tile - 1) / tile);
+    const size_t cells = (size_t) ft->n_deliverers * n_tiles;
+    if (cells >= 0x7FFFFFF0ull) return fail(BFQ_E_RANGE, "fan-out count matrix too large (deliverers x tiles); split the batch");
+    CUDA_TRY(w->d_fo_counts.reserve(cells));
+    CUDA_TRY(w->d_fo_base.reserve(cells));
+    CUDA_TRY(w->d_pack_offsets.reserve((size_t) ft->n_deliverers + 1));
+    CUDA_TRY(w->d_pack_topic.reserve((size_t) std::max<int64_t>(n_pairs, 1)));
+    CUDA_TRY(w->d_pack_rank.reserve((size_t) std::max<int64_t>(n_pairs, 1)));
+    CUDA_TRY(w->d_pack_member.reserve((size_t) std::max<int64_t>(n_pairs, 1)));
+    FanoutParams p{};
+    p.n_topics = L->n;
+    p.offsets = d_offsets;
+    p.n_pairs = n_pairs;
+    p.ranks = d_ranks;
+    p.rdeliv = ft->d_rdeliv.p;
+    p.gmem_off = ft->d_gmem_off.p;
+    p.gmem_deliv = ft->d_gmem_deliv.p;
+    p.gordered = ft->d_gordered.p;
+    p.n_deliverers = ft->n_deliverers;
+    p.tile_counts = w->d_fo_counts.p;
+    p.tile_base = w->d_fo_base.p;
+    p.pack_offsets = w->d_pack_offsets.p;
+    p.pack_topic = w->d_pack_topic.p;
+    p.pack_rank = w->d_pack_rank.p;
+    p.pack_member = w->d_pack_member.p;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(launch_fanout(p, nullptr, &tmp_bytes, st));
+    CUDA_TRY(w->d_fo_tmp.reserve(tmp_bytes + 256));
+    CUDA_TRY(launch_fanout(p, w->d_fo_tmp.p, &tmp_bytes, st));
+    out->d_pack_offsets = (const int64_t*) w->d_pack_offsets.p;
+    out->d_pack_topic = w->d_pack_topic.p;
+    out->d_pack_rank = w->d_pack_rank.p;
+    out->d_pack_member = w->d_pack_member.p;
+    out->n_pairs = n_pairs;
+    out->n_deliverers = (int32_t) ft->n_deliverers;
+    out->ordered_share_id = (int32_t) ft->n_deliverers - 1;
+    out->generation = L->snap->generation;
+    std::lock_guard<std::mutex> g(h->mu);
+    h->launches += 5;
+    return BFQ_OK;
+}
+
+int32_t bfq_fanout_deliverer(bfq_index* h, int32_t id, int32_t* sub_broker_id, uint8_t* key_out, int64_t key_cap, int64_t* key_len) {
+    if (!h || id < 0) return fail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->deliverers->mu);
+    if ((size_t) id >= h->deliverers->list.size()) return fail(BFQ_E_RANGE, "deliverer id out of range (the last id of a fan-out result is the ordered-share marker)");
+    const auto& e = h->deliverers->list[(size_t) id];
+    if (sub_broker_id) *sub_broker_id = e.first;
+    if (key_len) *key_len = (int64_t) e.second.size();
+    if (key_out && (int64_t) e.second.size() <= key_cap) memcpy(key_out, e.second.data(), e.second.size());
     return BFQ_OK;
 }
 

@@ -113,6 +113,13 @@ class DeviceResult:
         N.check(N.lib.bfq_expand_device(C.byref(self.raw), d_offsets_ptr, d_ranks_ptr, rank_cap, stream, C.byref(total)))
         return total.value
 
+    def fanout(self, d_offsets_ptr, d_ranks_ptr, n_pairs, stream=0):
+        """bfq_fanout_device: the (topic, route) pairs of this result's device CSR grouped by deliverer id -> BfqFanoutResult
+        (device pointers into this result's workspace)"""
+        out = N.BfqFanoutResult()
+        N.check(N.lib.bfq_fanout_device(C.byref(self.raw), d_offsets_ptr, d_ranks_ptr, n_pairs, stream, C.byref(out)))
+        return out
+
     def release(self):
         if getattr(self, "raw", None) is not None and self.raw.lease:
             N.lib.bfq_device_result_release(C.byref(self.raw))
@@ -176,6 +183,14 @@ class GpuRouteIndex:
                  "overflow_topics", "flagged_topics", "multi_segment_filters", "long_token_chunks", "deferred_topics",
                  "duplicate_topics", "full_commits", "delta_commits", "garbage_slots"]
         return dict(zip(names, s.tolist()))
+
+    def deliverer(self, deliverer_id):
+        """(subBrokerId, delivererKey bytes) of a fan-out deliverer id"""
+        broker, kl = C.c_int32(0), C.c_int64(0)
+        N.check(N.lib.bfq_fanout_deliverer(self._h, int(deliverer_id), C.byref(broker), None, 0, C.byref(kl)))
+        kb = C.create_string_buffer(max(kl.value, 1))
+        N.check(N.lib.bfq_fanout_deliverer(self._h, int(deliverer_id), C.byref(broker), C.addressof(kb), kl.value, C.byref(kl)))
+        return broker.value, kb.raw[:kl.value]
 
     def set_option(self, name, value):
         N.check(N.lib.bfq_index_set_option(self._h, name.encode(), int(value)))

@@ -208,6 +208,34 @@ int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int6
                           void* stream, int64_t* n_ranks);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fan-out expansion on the device: the step right behind the match. DeliverExecutorGroup.submit
+ * (DW/DeliverExecutorGroup.java:112-231) walks every matched route of a message, resolves a shared subscription to one
+ * member (:242-278) and hands each route to the deliverer of its (subBrokerId, delivererKey) (DW/DeliverExecutor.java:89-93),
+ * which batches per deliverer. bfq_fanout_device does that grouping for a whole batch: it takes the device CSR of a completed
+ * match (bfq_expand_device: surviving ranks per topic, caps applied) and returns every (topic, route) pair grouped by
+ * deliverer id: pairs [d_pack_offsets[d], d_pack_offsets[d + 1]) belong to deliverer d; d_pack_topic / d_pack_rank give the
+ * pair, d_pack_member the member index a $share subscription was resolved to (0xFFFFFFFF for ordinary routes; members in the
+ * order of the stored RouteGroup). An unordered share picks member hash(topic position, rank) mod n (the reference picks
+ * uniformly at random: any member is valid); ORDERED shares need each message's publisher (rendezvous hash of ClientInfo) and
+ * are grouped, unresolved, under the last id (ordered_share_id) for the host. Ids are dense over the distinct
+ * (subBrokerId, delivererKey) pairs of the index, stable across commits; bfq_fanout_deliverer gives the pair back.
+ * The arrays live in the result's leased workspace: valid until bfq_device_result_release.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const int64_t* d_pack_offsets;   /* [n_deliverers + 1] */
+    const uint32_t* d_pack_topic;    /* [n_pairs] topic position in the batch */
+    const uint32_t* d_pack_rank;     /* [n_pairs] route rank (of the result's snapshot) */
+    const uint32_t* d_pack_member;   /* [n_pairs] */
+    int64_t n_pairs;
+    int32_t n_deliverers;            /* ids [0, n_deliverers); the last one is ordered_share_id */
+    int32_t ordered_share_id;
+    uint64_t generation;
+} bfq_fanout_result;
+int32_t bfq_fanout_device(const bfq_device_result* res, const int64_t* d_offsets, const int64_t* d_ranks, int64_t n_pairs,
+                          void* stream, bfq_fanout_result* out);
+int32_t bfq_fanout_deliverer(bfq_index* h, int32_t id, int32_t* sub_broker_id, uint8_t* key_out, int64_t key_cap, int64_t* key_len);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU: the one exchange step of the tenant-sharded path. Tenants are independent key ranges, so
  * every GPU (one process each) matches the topics of the tenants it hosts with NO data-path collective; what travels is
  * the reply, reassembled on every rank the way the dist-server reassembles the per-worker BatchDistReply messages

@@ -428,3 +428,44 @@ class TopicLevelIndex:
             if n <= cap:
                 return out[:n].tolist()
             cap = n
+
+
+# ------------------------------------------------------------------ fan-out grouping
+def deliverer_of_receiver_url(receiver_url):
+    """(subBrokerId, delivererKey) a NormalMatching is delivered through: DeliverExecutor.send
+    (bifromq-dist/bifromq-dist-worker/src/main/java/org/apache/bifromq/dist/worker/DeliverExecutor.java:89-93) keys its DeliveryCall
+    by matched.subBrokerId() and matched.delivererKey(), both cut out of the receiver url
+    "<subBrokerId>\\0<receiverId>\\0<delivererKey>" (KVSchemaUtil.java:56-58, cache/ReceiverCache.java:32-36)."""
+    broker, _receiver, deliverer_key = bytes(receiver_url).split(b"\0", 2)
+    return int(broker), deliverer_key
+
+
+def route_group_members_in_wire_order(value):
+    """receiver urls of a RouteGroup value in the order the proto carries them — GroupMatching.receiverList keeps the map's
+    iteration order (cache/GroupMatching.java:44-46), which for a parsed protobuf map is the wire order."""
+    b, i, out = bytes(value), 0, []
+
+    def varint():
+        nonlocal i
+        v, shift = 0, 0
+        while True:
+            c = b[i]
+            i += 1
+            v |= (c & 0x7F) << shift
+            if not c & 0x80:
+                return v
+            shift += 7
+    while i < len(b):
+        assert varint() == (1 << 3) | 2
+        end = varint() + i
+        key = None
+        while i < end:
+            tag = varint()
+            if tag == (1 << 3) | 2:
+                n = varint()
+                key = b[i:i + n]
+                i += n
+            else:
+                varint()
+        out.append(key)
+    return out

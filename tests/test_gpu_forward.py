@@ -664,6 +664,72 @@ def test_async_device_matches_in_flight_together(B):
         out.release()
 
 
+@pytest.mark.parametrize("caps", [(2 ** 31 - 1, 100), (3, 1)])
+def test_fanout_groups_routes_by_deliverer(B, caps):
+    """bfq_fanout_device: the surviving (topic, route) pairs of a batch grouped by (subBrokerId, delivererKey) — what
+    DeliverExecutorGroup.submit + DeliverExecutor.send do one route at a time (DW/DeliverExecutorGroup.java:112-231,
+    DW/DeliverExecutor.java:89-93). Every pair of the device CSR appears exactly once, under the deliverer its route is
+    delivered through (restated in oracle_lib.deliverer_of_receiver_url); a $share route is resolved to one member of its
+    stored group (any member is a valid outcome of the reference's random pick), an $oshare route is left to the host under
+    the reserved id."""
+    import torch
+    w = B.workload.Workload("C3", scale=0.02)
+    idx = B.pkg.GpuRouteIndex(0)
+    idx.load(w.keys, w.key_off, w.vals, w.val_off)
+    idx.commit()
+    tenants, n = w.tenants, w.n_topics
+    nt = len(tenants)
+    dev = torch.device("cuda", 0)
+    d_topics = torch.from_numpy(np.ascontiguousarray(w.topics)).to(dev)
+    d_off = torch.from_numpy(np.ascontiguousarray(w.topic_off)).to(dev)
+    d_tt = torch.from_numpy(np.ascontiguousarray(w.topic_tenant[:n])).to(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = idx.match_device(tenants, d_topics.data_ptr(), d_off.data_ptr(), d_tt.data_ptr(), n, [caps[0]] * nt, [caps[1]] * nt, stream)
+    d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    total = out.expand(d_offsets.data_ptr(), None, 0, stream)
+    d_ranks = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+    out.expand(d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream)
+    fo = out.fanout(d_offsets.data_ptr(), d_ranks.data_ptr(), total, stream)
+    torch.cuda.synchronize()
+    from bifromq_b200 import dist as D
+    D_ = fo.n_deliverers
+    pack_off = D.device_view(fo.d_pack_offsets, D_ + 1, "<i8", dev).cpu().numpy()
+    pt = D.device_view(fo.d_pack_topic, max(total, 1), "<u4", dev).cpu().numpy()[:total]
+    pr = D.device_view(fo.d_pack_rank, max(total, 1), "<u4", dev).cpu().numpy()[:total]
+    pm = D.device_view(fo.d_pack_member, max(total, 1), "<u4", dev).cpu().numpy()[:total]
+    assert fo.n_pairs == total and pack_off[0] == 0 and pack_off[-1] == total and (np.diff(pack_off) >= 0).all()
+    assert fo.ordered_share_id == D_ - 1
+    # every pair of the CSR exactly once
+    offsets = d_offsets.cpu().numpy()
+    ranks = d_ranks.cpu().numpy()[:total]
+    want_pairs = np.stack([np.repeat(np.arange(n), np.diff(offsets)), ranks], axis=1)
+    got_pairs = np.stack([pt.astype(np.int64), pr.astype(np.int64)], axis=1)
+    assert sorted(map(tuple, want_pairs.tolist())) == sorted(map(tuple, got_pairs.tolist()))
+    # every pair under the right deliverer
+    deliverers = [idx.deliverer(d) for d in range(D_ - 1)]
+    assert len(set(deliverers)) == len(deliverers)
+    route_cache = {}
+    n_group = n_ordered = 0
+    for d in range(D_):
+        for j in range(int(pack_off[d]), int(pack_off[d + 1])):
+            r = int(pr[j])
+            if r not in route_cache:
+                k, v = idx.route(r)
+                route_cache[r] = (O.build_match_route(k, v), v)
+            m, v = route_cache[r]
+            if m["type"] == "Normal":
+                assert pm[j] == 0xFFFFFFFF and deliverers[d] == O.deliverer_of_receiver_url(m["receiverUrl"])
+            elif m["mqttTopicFilter"].startswith("$oshare/"):
+                assert d == fo.ordered_share_id
+                n_ordered += 1
+            else:
+                members = O.route_group_members_in_wire_order(v)
+                assert pm[j] < len(members) and deliverers[d] == O.deliverer_of_receiver_url(members[pm[j]])
+                n_group += 1
+    assert n_group > 0 and n_ordered > 0 and total > n
+    out.release()
+
+
 def test_exchange_gather_single_rank(B):
     """bfq_exchange_gather with a world of one (NCCL communicator of size 1): the reassembled arrays are the dense,
     topic-ordered form of the device result — equal to what the host path returns for the same batch"""
