@@ -1418,6 +1418,8 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
         rbase = tbase = 0;
         // ---- H2D of every sub-batch, back to back on the copy stream
         CUDA_TRY(cudaEventRecord(w->ev[0], w->copy_stream));
+        // the kernels read whole aligned 16-byte granules: define the bytes behind the blob's end (masked out, but read)
+        CUDA_TRY(cudaMemsetAsync(w->d_topics.p + blob_e, 0, 64, w->copy_stream));
         rc = resolve_tenants(w, snap.get(), tenants, tenant_off, n_tenants, max_pfanout, max_gfanout, w->copy_stream);
         if (rc != BFQ_OK) return rc;
         int64_t bounds[MAX_CHUNKS + 1];
