@@ -89,12 +89,16 @@ _SIGNATURES = {
     "bfq_receiver_url": (_i64, [_i32, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_route_key": (_i64, [C.c_char_p, _i64, C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_tenant_begin_key": (_i64, [C.c_char_p, _i64, _vp, _i64]),
+    "bfq_retain_key": (_i64, [C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
+    "bfq_retain_key_prefix": (_i64, [C.c_char_p, _i64, C.c_char_p, _i64, _vp, _i64]),
     "bfq_is_valid_topic": (_i32, [C.c_char_p, _i64, _i32, _i32, _i32]),
     "bfq_is_valid_topic_filter": (_i32, [C.c_char_p, _i64, _i32, _i32, _i32]),
     "bfq_rindex_create": (_i32, [_i32, C.POINTER(_vp)]),
     "bfq_rindex_destroy": (None, [_vp]),
     "bfq_rindex_reset": (_i32, [_vp]),
     "bfq_rindex_add": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "bfq_rindex_load_keys": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "bfq_rresult_retain_keys": (_i64, [_vp, _vp, _vp, _i64, _vp]),
     "bfq_rindex_remove": (_i32, [_vp, C.c_char_p, _i64, C.c_char_p, _i64]),
     "bfq_rindex_commit": (_i32, [_vp]),
     "bfq_rindex_lookup": (_i32, [_vp, _i64, _vp, _i64, C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]),

@@ -1898,6 +1898,12 @@ int64_t bfq_route_key(const uint8_t* tenant, int64_t tn, const uint8_t* tf, int6
                       uint8_t* out, int64_t cap) {
     return emit_bytes(make_route_key(sv((const char*) tenant, (size_t) tn), sv((const char*) tf, (size_t) fn), sv((const char*) url, (size_t) un)), out, cap);
 }
+int64_t bfq_retain_key(const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t n, uint8_t* out, int64_t cap) {
+    return emit_bytes(make_retain_key(sv((const char*) tenant, (size_t) tn), sv((const char*) topic, (size_t) n)), out, cap);
+}
+int64_t bfq_retain_key_prefix(const uint8_t* tenant, int64_t tn, const uint8_t* tf, int64_t fn, uint8_t* out, int64_t cap) {
+    return emit_bytes(make_retain_key_prefix(sv((const char*) tenant, (size_t) tn), sv((const char*) tf, (size_t) fn)), out, cap);
+}
 int64_t bfq_tenant_begin_key(const uint8_t* tenant, int64_t tn, uint8_t* out, int64_t cap) {
     return emit_bytes(make_tenant_begin_key(sv((const char*) tenant, (size_t) tn)), out, cap);
 }

@@ -82,6 +82,89 @@ int32_t java_string_hash(sv s) {
     return (int32_t) h;
 }
 
+uint8_t level_hash_byte(sv s) {
+    uint32_t h = 0x811c9dc5u;
+    const size_t n = s.size();
+    auto step = [&](uint32_t unit) {
+        h ^= unit;
+        h *= 0x01000193u;
+    };
+    for (size_t i = 0; i < n;) {   // UTF-8 -> UTF-16 code units, as String.charAt sees them
+        uint8_t c = (uint8_t) s[i];
+        uint32_t cp;
+        int len;
+        if (c < 0x80) { cp = c; len = 1; }
+        else if (c < 0xE0) { cp = c & 0x1F; len = 2; }
+        else if (c < 0xF0) { cp = c & 0x0F; len = 3; }
+        else { cp = c & 0x07; len = 4; }
+        for (int j = 1; j < len && i + j < n; j++) cp = (cp << 6) | ((uint8_t) s[i + j] & 0x3F);
+        i += len;
+        if (cp >= 0x10000) {
+            cp -= 0x10000;
+            step(0xD800u + (cp >> 10));
+            step(0xDC00u + (cp & 0x3FF));
+        } else {
+            step(cp);
+        }
+    }
+    return (uint8_t) (h & 0xFF);
+}
+
+std::string make_retain_key(sv tenant, sv topic) {
+    std::string k = make_tenant_begin_key(tenant);
+    size_t levels = 0;
+    std::string hashes;
+    for_each_level(topic, '/', [&](sv l) {
+        levels++;
+        hashes.push_back((char) level_hash_byte(l));
+    });
+    put_be16(k, levels);
+    k.append(hashes);
+    for (char c : topic) k.push_back(c == '/' ? '\0' : c);
+    return k;
+}
+
+std::string make_retain_key_prefix(sv tenant, sv tf) {
+    std::vector<sv> lv;
+    for_each_level(tf, '/', [&](sv l) { lv.push_back(l); });
+    const bool multi = !lv.empty() && lv.back().size() == 1 && lv.back()[0] == '#';
+    const size_t levels = multi ? lv.size() - 1 : lv.size();
+    size_t cut = lv.size();   // filterPrefix: up to the first '+', else without a final '#'
+    for (size_t i = 0; i < lv.size(); i++)
+        if (lv[i].size() == 1 && lv[i][0] == '+') {
+            cut = i;
+            break;
+        }
+    if (cut == lv.size() && multi) cut = lv.size() - 1;
+    std::string k = make_tenant_begin_key(tenant);
+    put_be16(k, levels);
+    for (size_t i = 0; i < cut; i++) k.push_back((char) level_hash_byte(lv[i]));
+    return k;
+}
+
+bool decode_retain_key(sv key, sv* tenant, std::string* topic) {
+    if (key.size() < 5 || key[0] != 0) return false;
+    const size_t tl = ((size_t) (uint8_t) key[1] << 8) | (uint8_t) key[2];
+    if (key.size() < 3 + tl + 2) return false;
+    *tenant = key.substr(3, tl);
+    const size_t levels = ((size_t) (uint8_t) key[3 + tl] << 8) | (uint8_t) key[4 + tl];
+    const size_t at = 5 + tl + levels;
+    if (levels == 0 || key.size() < at) return false;
+    const sv esc = key.substr(at);
+    // the escaped topic must have exactly `levels` levels and the stored hash bytes must be theirs
+    size_t n = 0;
+    bool ok = true;
+    for_each_level(esc, '\0', [&](sv l) {
+        if (n < levels && (uint8_t) key[5 + tl + n] != level_hash_byte(l)) ok = false;
+        n++;
+    });
+    if (!ok || n != levels) return false;
+    topic->assign(esc);
+    for (char& c : *topic)
+        if (c == '\0') c = '/';
+    return true;
+}
+
 uint8_t receiver_bucket(sv receiver) {
     uint32_t h = (uint32_t) java_string_hash(receiver);
     return (uint8_t) ((h ^ (h >> 16)) & 0xFF);

@@ -54,6 +54,16 @@ std::string prefix_upper_bound(sv key, bool* open_end);
 // thread-local error text behind bfq_last_error() (defined in capi.cu)
 int32_t set_error(int32_t code, const std::string& msg);
 
+// ---- retain store key layout (bifromq-retain/bifromq-retain-store-schema/.../schema/KVSchemaUtil.java:44-73, LevelHash.java:31-49):
+//   key = <0x00> <u16 BE len> tenantId <u16 BE number of topic levels> <one FNV-1a byte per level> escape(topic)
+// with escape = '/' -> NUL (U/TopicUtil.java:189-192). The topic is recoverable from the key, so the index is fed from a plain
+// key scan (RetainStoreCoProc.load, RS/RetainStoreCoProc.java:279-296, parses every VALUE for it).
+uint8_t level_hash_byte(sv level_utf8);                          // LevelHash.hashToByte :41-48 (FNV-1a over UTF-16 code units, low byte)
+std::string make_retain_key(sv tenant, sv topic);                // retainMessageKey :44-50
+// retainKeyPrefix(tenant, levels, filterPrefix(filter)) :52-72 with levels = the filter's level count (one less under a final '#')
+std::string make_retain_key_prefix(sv tenant, sv topic_filter);
+bool decode_retain_key(sv key, sv* tenant, std::string* topic);  // false if the bytes cannot be a retain key
+
 bool is_valid_topic(sv topic, int max_level_length, int max_level, int max_length);
 bool is_valid_topic_filter(sv tf, int max_level_length, int max_level, int max_length);
 

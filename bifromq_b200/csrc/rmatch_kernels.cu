@@ -731,6 +731,55 @@ int32_t bfq_rindex_add(bfq_rindex* h, const uint8_t* tenants, const int64_t* ten
     return BFQ_OK;
 }
 
+// The feed of RetainStoreCoProc.load() (RS/RetainStoreCoProc.java:279-296): raw retain-store KV keys from a range scan. The
+// reference parses every VALUE (a TopicMessage proto) for the topic; the key carries it too (escaped, behind the level-hash bytes),
+// so the index is fed from the keys alone. ids_out[i] < 0 marks a key that is not a retain key (skipped, as the reference logs
+// and skips an unparsable entry).
+int32_t bfq_rindex_load_keys(bfq_rindex* h, const uint8_t* keys, const int64_t* key_off, int64_t n, int64_t* ids_out) {
+    if (!h || n < 0 || (n > 0 && (!keys || !key_off))) return rfail(BFQ_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    for (int64_t i = 0; i < n; i++) {
+        sv tenant;
+        std::string topic;
+        if (key_off[i + 1] < key_off[i] || !decode_retain_key(sv((const char*) keys + key_off[i], (size_t) (key_off[i + 1] - key_off[i])), &tenant, &topic)) {
+            if (ids_out) ids_out[i] = -1;
+            continue;
+        }
+        std::pair<std::string, std::string> key(std::string(tenant), std::move(topic));
+        auto it = h->staged.find(key);
+        int64_t id;
+        if (it == h->staged.end()) {
+            id = (int64_t) h->by_id.size();
+            h->by_id.push_back(key);
+            h->alive.push_back(1);
+            h->staged.emplace(std::move(key), id);
+        } else {
+            id = it->second;
+        }
+        if (ids_out) ids_out[i] = id;
+    }
+    return BFQ_OK;
+}
+
+// retainMessageKey(tenant, topic) of every id in a match result, in result order: the keys of the follow-up reader.get calls of
+// RetainStoreCoProc.match (RS/RetainStoreCoProc.java:177-188), as one batch. Returns the blob length; copies if it fits.
+int64_t bfq_rresult_retain_keys(bfq_rindex* h, const bfq_rresult* r, uint8_t* blob_out, int64_t blob_cap, int64_t* key_off_out) {
+    if (!h || !r) return BFQ_E_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int64_t at = 0;
+    const int64_t n = (int64_t) r->ids.size();
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t id = r->ids[(size_t) i];
+        if (id < 0 || id >= (int64_t) h->by_id.size()) return BFQ_E_RANGE;
+        const std::string k = make_retain_key(h->by_id[(size_t) id].first, h->by_id[(size_t) id].second);
+        if (key_off_out) key_off_out[i] = at;
+        if (blob_out && at + (int64_t) k.size() <= blob_cap) memcpy(blob_out + at, k.data(), k.size());
+        at += (int64_t) k.size();
+    }
+    if (key_off_out) key_off_out[n] = at;
+    return at;
+}
+
 int32_t bfq_rindex_remove(bfq_rindex* h, const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t n) {
     if (!h) return rfail(BFQ_E_INVALID, "handle is NULL");
     std::lock_guard<std::mutex> g(h->mu);

@@ -15,7 +15,7 @@ from . import _native as N
 
 
 class RMatchResult:
-    def __init__(self, handle):
+    def __init__(self, handle, index_handle=None, with_retain_keys=False):
         lib = N.lib
         n = lib.bfq_rresult_num_filters(handle)
         self.n_filters = n
@@ -33,6 +33,17 @@ class RMatchResult:
         lib.bfq_rresult_timings(handle, ms.ctypes.data, 8)
         self.timings_ms = dict(zip(["h2d", "kernels", "d2h", "total", "device_all_kernels", "device_rmatch_kernel"], ms[:6].tolist()))
         self.n_ranges, self.n_overflow_filters = int(ms[6]), int(ms[7])
+        self.retain_keys = None
+        if with_retain_keys and index_handle is not None:
+            # the keys of RetainStoreCoProc.match's follow-up reader.get calls, as one batch (bfq_rresult_retain_keys)
+            koff = np.zeros(len(self.ids) + 1, np.int64)
+            total = lib.bfq_rresult_retain_keys(index_handle, handle, None, 0, koff.ctypes.data)
+            if total < 0:
+                lib.bfq_rresult_free(handle)
+                raise N.NativeError("bfq_rresult_retain_keys: %d" % total)
+            blob = np.zeros(max(total, 1), np.uint8)
+            lib.bfq_rresult_retain_keys(index_handle, handle, blob.ctypes.data, total, koff.ctypes.data)
+            self.retain_keys = (blob[:total], koff)
         lib.bfq_rresult_free(handle)
 
     def matches(self, i):
@@ -85,7 +96,15 @@ class GpuTopicMatchIndex:
         N.check(N.lib.bfq_rindex_lookup(self._h, int(topic_id), C.addressof(tb), tl.value, C.byref(tl), C.addressof(pb), pl.value, C.byref(pl)))
         return tb.raw[:tl.value].decode(), pb.raw[:pl.value].decode()
 
-    def match_blobs(self, tenants, filters_blob, filter_off, filter_tenant, limit=None):
+    def load_keys(self, keys_blob, key_off):
+        """bfq_rindex_load_keys: the feed of RetainStoreCoProc.load() — raw retain-store KV keys of a range scan -> topic ids
+        (-1 for bytes that are not a retain key)"""
+        n = len(key_off) - 1
+        ids = np.zeros(max(n, 1), np.int64)
+        N.check(N.lib.bfq_rindex_load_keys(self._h, N.ptr(keys_blob), N.ptr(np.ascontiguousarray(key_off, dtype=np.int64)), n, ids.ctypes.data))
+        return ids[:n]
+
+    def match_blobs(self, tenants, filters_blob, filter_off, filter_tenant, limit=None, with_retain_keys=False):
         tb, toff = N.as_blob(tenants)
         n = len(filter_off) - 1
         ft = np.ascontiguousarray(filter_tenant, dtype=np.int32)
@@ -93,7 +112,7 @@ class GpuTopicMatchIndex:
         r = C.c_void_p()
         N.check(N.lib.bfq_rmatch(self._h, N.ptr(tb), N.ptr(toff), len(tenants), N.ptr(filters_blob), N.ptr(filter_off), N.ptr(ft), n,
                                  N.ptr(lim) if lim is not None else None, C.byref(r)))
-        return RMatchResult(r)
+        return RMatchResult(r, self._h, with_retain_keys)
 
     def match(self, tenant, filters, limit=None):
         blob, off = N.as_blob(filters)

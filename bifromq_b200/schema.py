@@ -98,6 +98,18 @@ def route_key(tenant, mqtt_topic_filter, receiver_url_=b""):
     return _bytes_call(N.lib.bfq_route_key, t, len(t), f, len(f), u, len(u))
 
 
+def retain_key(tenant, topic):
+    """retainMessageKey (retain-store-schema KVSchemaUtil.java:44-50)"""
+    t, p = _b(tenant), _b(topic)
+    return _bytes_call(N.lib.bfq_retain_key, t, len(t), p, len(p))
+
+
+def retain_key_prefix(tenant, topic_filter):
+    """retainKeyPrefix of a topic filter (KVSchemaUtil.java:52-72)"""
+    t, f = _b(tenant), _b(topic_filter)
+    return _bytes_call(N.lib.bfq_retain_key_prefix, t, len(t), f, len(f))
+
+
 def tenant_begin_key(tenant):
     t = _b(tenant)
     return _bytes_call(N.lib.bfq_tenant_begin_key, t, len(t))

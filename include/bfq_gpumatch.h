@@ -284,6 +284,10 @@ int64_t bfq_receiver_url(int32_t sub_broker_id, const uint8_t* receiver_id, int6
 int64_t bfq_route_key(const uint8_t* tenant, int64_t tn, const uint8_t* mqtt_topic_filter, int64_t fn,
                       const uint8_t* receiver_url, int64_t un, uint8_t* out, int64_t cap);
 int64_t bfq_tenant_begin_key(const uint8_t* tenant, int64_t tn, uint8_t* out, int64_t cap);
+/* retain store key layout (bifromq-retain/bifromq-retain-store-schema/src/main/java/org/apache/bifromq/retain/store/schema/
+ * KVSchemaUtil.java:44-73, LevelHash.java:31-49): retainMessageKey(tenant, topic) and retainKeyPrefix of a topic filter */
+int64_t bfq_retain_key(const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t n, uint8_t* out, int64_t cap);
+int64_t bfq_retain_key_prefix(const uint8_t* tenant, int64_t tn, const uint8_t* topic_filter, int64_t fn, uint8_t* out, int64_t cap);
 int32_t bfq_is_valid_topic(const uint8_t* topic, int64_t n, int32_t max_level_length, int32_t max_level, int32_t max_length);
 int32_t bfq_is_valid_topic_filter(const uint8_t* tf, int64_t n, int32_t max_level_length, int32_t max_level, int32_t max_length);
 
@@ -301,6 +305,10 @@ int32_t bfq_rindex_reset(bfq_rindex* h);
 int32_t bfq_rindex_add(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
                        const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n,
                        int64_t* ids_out);
+/* The feed of RetainStoreCoProc.load() (RS/RetainStoreCoProc.java:279-296): raw retain-store KV KEYS of a range scan. The
+ * reference parses every value (a TopicMessage proto) for the topic; the key carries it too, so the index is fed from the keys
+ * alone. ids_out[i] = the topic's id, or -1 for bytes that are not a retain key (skipped). */
+int32_t bfq_rindex_load_keys(bfq_rindex* h, const uint8_t* keys, const int64_t* key_off, int64_t n, int64_t* ids_out);
 int32_t bfq_rindex_remove(bfq_rindex* h, const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t n);
 int32_t bfq_rindex_commit(bfq_rindex* h);
 /* topic id -> (tenant, topic) strings */
@@ -324,6 +332,10 @@ const int64_t* bfq_rresult_total_matches(const bfq_rresult* r);      /* [n_filte
  * "inputs resident" to "ids expanded" (CUDA events on the call's stream); ms[5]: device time of rmatch_kernel alone;
  * ms[6]: rank ranges the kernel emitted (8 bytes each); ms[7]: filters that needed the global-scratch tier */
 int32_t bfq_rresult_timings(const bfq_rresult* r, double* ms, int32_t n);
+/* retainMessageKey of every id of the result, in result order, as one (blob, key_off[n_ids + 1]) batch: the keys of the
+ * follow-up reader.get calls of RetainStoreCoProc.match (RS/RetainStoreCoProc.java:177-188). Returns the blob length (or a
+ * negative BFQ_E_*); copies only if it fits blob_cap; key_off_out may be NULL. */
+int64_t bfq_rresult_retain_keys(bfq_rindex* h, const bfq_rresult* r, uint8_t* blob_out, int64_t blob_cap, int64_t* key_off_out);
 void bfq_rresult_free(bfq_rresult* r);
 
 #ifdef __cplusplus

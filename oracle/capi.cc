@@ -72,6 +72,17 @@ int64_t orc_receiver_url(int32_t subBrokerId, const uint8_t* rid, int64_t rn, co
 int64_t orc_tenant_begin_key(const uint8_t* t, int64_t tn, uint8_t* out, int64_t cap) {
     return emit(tenant_begin_key(S(t, tn)), out, cap);
 }
+// retain store schema
+int64_t orc_retain_key(const uint8_t* t, int64_t tn, const uint8_t* topic, int64_t n, uint8_t* out, int64_t cap) {
+    return emit(retain_message_key(S(t, tn), S(topic, n)), out, cap);
+}
+// KVSchemaUtilTest.toRetainMessageKeyPrefix (test helper, :88-94): levels = the filter's level count, one less under a final '#'
+int64_t orc_retain_key_prefix(const uint8_t* t, int64_t tn, const uint8_t* tf, int64_t fn, uint8_t* out, int64_t cap) {
+    const std::vector<std::string> lv = parse(S(tf, fn), false);
+    const bool multi = !lv.empty() && lv.back() == "#";
+    return emit(retain_key_prefix(S(t, tn), (int) (multi ? lv.size() - 1 : lv.size()), retain_filter_prefix(lv)), out, cap);
+}
+int32_t orc_level_hash_byte(const uint8_t* l, int64_t n) { return (int32_t) level_hash_byte(S(l, n)); }
 int64_t orc_tenant_route_start_key(const uint8_t* t, int64_t tn, const uint8_t* filter, int64_t fn, uint8_t* out, int64_t cap) {
     return emit(tenant_route_start_key(S(t, tn), parse(S(filter, fn), false)), out, cap);
 }

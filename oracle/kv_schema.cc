@@ -246,3 +246,58 @@ Matching build_match_route(const std::string& key, const std::string& value) {
 }
 
 }  // namespace orc
+
+// ------------------------------------------------------------------ retain store schema
+namespace orc {
+// LevelHash.hashToByte (bifromq-retain/bifromq-retain-store-schema/.../schema/LevelHash.java:41-48): FNV-1a over data.charAt(i),
+// int arithmetic, low byte
+uint8_t level_hash_byte(const std::string& level) {
+    const std::u16string u = to_utf16(level);
+    uint32_t hash = 0x811c9dc5u;
+    for (char16_t c : u) {
+        hash ^= (uint32_t) c;
+        hash *= 0x01000193u;
+    }
+    return (uint8_t) (hash & 0xff);
+}
+// LevelHash.hash :33-39
+std::string level_hash(const std::vector<std::string>& levels) {
+    std::string out;
+    for (const auto& l : levels) out.push_back((char) level_hash_byte(l));
+    return out;
+}
+// KVSchemaUtil.retainMessageKey :44-50: tenantBeginKey ++ toByteString((short) levels) ++ LevelHash.hash(levels) ++ escape(topic)
+std::string retain_message_key(const std::string& tenantId, const std::string& topic) {
+    const std::vector<std::string> levels = parse(topic, false);
+    std::string k = tenant_begin_key(tenantId);
+    k.push_back((char) ((levels.size() >> 8) & 0xff));
+    k.push_back((char) (levels.size() & 0xff));
+    k += level_hash(levels);
+    std::string esc = topic;   // TopicUtil.escape :189-192
+    for (char& c : esc)
+        if (c == '/') c = '\0';
+    return k + esc;
+}
+// KVSchemaUtil.filterPrefix :52-62
+std::vector<std::string> retain_filter_prefix(const std::vector<std::string>& filterLevels) {
+    int firstWildcard = -1;
+    for (size_t i = 0; i < filterLevels.size(); i++)
+        if (filterLevels[i] == "+") {
+            firstWildcard = (int) i;
+            break;
+        }
+    if (firstWildcard == -1) {
+        if (!filterLevels.empty() && filterLevels.back() == "#")
+            return std::vector<std::string>(filterLevels.begin(), filterLevels.end() - 1);
+        return filterLevels;
+    }
+    return std::vector<std::string>(filterLevels.begin(), filterLevels.begin() + firstWildcard);
+}
+// KVSchemaUtil.retainKeyPrefix :64-68
+std::string retain_key_prefix(const std::string& tenantId, int levels, const std::vector<std::string>& filterPrefix) {
+    std::string k = tenant_begin_key(tenantId);
+    k.push_back((char) ((levels >> 8) & 0xff));
+    k.push_back((char) (levels & 0xff));
+    return k + level_hash(filterPrefix);
+}
+}  // namespace orc

@@ -67,6 +67,12 @@ RouteMatcher route_matcher_from(const std::string& topicFilter);                
 // ---------------------------------------------------------------- DWS/KVSchemaUtil.java
 std::string to_receiver_url(int subBrokerId, const std::string& receiverId, const std::string& delivererKey);  // :56-58
 std::string tenant_begin_key(const std::string& tenantId);                              // :91-94
+// retain store schema (bifromq-retain/bifromq-retain-store-schema/src/main/java/org/apache/bifromq/retain/store/schema/):
+uint8_t level_hash_byte(const std::string& level);                                      // LevelHash.java:41-48
+std::string level_hash(const std::vector<std::string>& levels);                         // LevelHash.java:33-39
+std::string retain_message_key(const std::string& tenantId, const std::string& topic);  // KVSchemaUtil.java:44-50
+std::vector<std::string> retain_filter_prefix(const std::vector<std::string>& filterLevels);   // KVSchemaUtil.java:52-62
+std::string retain_key_prefix(const std::string& tenantId, int levels, const std::vector<std::string>& filterPrefix);   // :64-68
 std::string tenant_route_start_key(const std::string& tenantId, const Levels& filterLevels);  // :96-102
 std::string to_normal_route_key(const std::string& tenantId, const RouteMatcher& m, const std::string& receiverUrl);  // :108-113
 std::string to_group_route_key(const std::string& tenantId, const RouteMatcher& m);     // :115-120

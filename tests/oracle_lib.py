@@ -40,6 +40,9 @@ def _load():
         "orc_route_matcher_from": (i64, [u8p, i64, u8p, i64]),
         "orc_receiver_url": (i64, [i32, u8p, i64, u8p, i64, u8p, i64]),
         "orc_tenant_begin_key": (i64, [u8p, i64, u8p, i64]),
+        "orc_retain_key": (i64, [u8p, i64, u8p, i64, u8p, i64]),
+        "orc_retain_key_prefix": (i64, [u8p, i64, u8p, i64, u8p, i64]),
+        "orc_level_hash_byte": (i32, [u8p, i64]),
         "orc_tenant_route_start_key": (i64, [u8p, i64, u8p, i64, u8p, i64]),
         "orc_route_key": (i64, [u8p, i64, u8p, i64, u8p, i64, u8p, i64]),
         "orc_upper_bound": (i64, [u8p, i64, u8p, i64]),
@@ -194,6 +197,21 @@ def receiver_url(sub_broker_id, receiver_id, deliverer_key):
 def tenant_begin_key(tenant):
     t = _b(tenant)
     return _bytes_call(lib.orc_tenant_begin_key, t, len(t))
+
+
+def retain_key(tenant, topic):
+    t, p = _b(tenant), _b(topic)
+    return _bytes_call(lib.orc_retain_key, t, len(t), p, len(p))
+
+
+def retain_key_prefix(tenant, topic_filter):
+    t, f = _b(tenant), _b(topic_filter)
+    return _bytes_call(lib.orc_retain_key_prefix, t, len(t), f, len(f))
+
+
+def level_hash_byte(level):
+    l = _b(level)
+    return lib.orc_level_hash_byte(l, len(l))
 
 
 def tenant_route_start_key(tenant, topic_filter):

@@ -197,3 +197,41 @@ def test_c5_config_scaled_vs_oracle(R):
     lim = np.full(w.n_query_filters, 10, np.int64)
     res10 = idx.match_blobs(tenants, w.filters, w.filter_off, w.filter_tenant, lim)
     assert (np.diff(res10.offsets) == np.minimum(res.totals, 10)).all()
+
+
+def test_retain_store_feed_from_raw_keys_and_batched_get_keys(R):
+    """RetainStoreCoProc.load() (RS/RetainStoreCoProc.java:279-296) rebuilds the index from a range scan; bfq_rindex_load_keys takes
+    the scan's raw KEYS (the topic is in the key, no value parsing), and bfq_rresult_retain_keys returns the retainMessageKey of
+    every matched topic as one batch — the keys of RetainStoreCoProc.match's follow-up reader.get calls (:177-188). Same
+    answers as feeding (tenant, topic) strings; junk keys are skipped; the keys equal the oracle's retainMessageKey."""
+    w = R.workload.Workload("C5", scale=0.01)
+    tenants = w.tenants
+    tl = w.topic_list()
+    keys = [O.retain_key(tenants[w.topic_tenant[i]], tl[i]) for i in range(w.n_topics)]
+    keys_sorted = sorted(keys)                       # a range scan delivers them in key order
+    junk = [b"\x00\x00\x01t", b"garbage", keys_sorted[0][:-1] + b"\x00extra-level"]
+    from bifromq_b200 import _native as N
+    kb, ko = N.as_blob(keys_sorted + junk)
+    a = R.retain.GpuTopicMatchIndex(0)
+    ids = a.load_keys(kb, ko)
+    assert (ids[:len(keys_sorted)] >= 0).all() and (ids[len(keys_sorted):] == -1).all()
+    a.commit()
+    b = R.retain.GpuTopicMatchIndex(0)
+    b.add_blobs(tenants, w.topics, w.topic_off, w.topic_tenant[:w.n_topics])
+    b.commit()
+    ra = a.match_blobs(tenants, w.filters, w.filter_off, w.filter_tenant[:w.n_query_filters], with_retain_keys=True)
+    rb = b.match_blobs(tenants, w.filters, w.filter_off, w.filter_tenant[:w.n_query_filters])
+    assert ra.offsets.tolist() == rb.offsets.tolist() and int(ra.totals.sum()) > w.n_query_filters
+    blob, koff = ra.retain_keys
+    assert len(koff) == len(ra.ids) + 1
+
+    def topic_of(idx, i):
+        t, p = idx.lookup(int(i))
+        return t, p
+    for f in range(0, w.n_query_filters, 23):
+        sa = sorted(topic_of(a, i) for i in ra.matches(f))
+        sb = sorted(topic_of(b, i) for i in rb.matches(f))
+        assert sa == sb
+        for j in range(int(ra.offsets[f]), int(ra.offsets[f + 1])):
+            t, p = topic_of(a, ra.ids[j])
+            assert bytes(blob[koff[j]:koff[j + 1]]) == O.retain_key(t, p)

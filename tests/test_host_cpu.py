@@ -264,3 +264,25 @@ def test_jni_shim_covers_every_native_method_and_type_checks():
     assert called <= declared, called - declared
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-DBFQ_JNI_STUB",
                            os.path.join(root, "jni", "bfq_gpumatch_jni.c")])
+
+
+def test_retain_key_codec_matches_the_oracle():
+    """bfq_retain_key / bfq_retain_key_prefix (csrc/codec.cc) against the oracle's restatement of the retain store schema, on
+    random topics and filters incl. empty levels and non-ASCII text (UTF-16 code units drive LevelHash)"""
+    import random
+    from bifromq_b200 import schema
+    rng = random.Random(3)
+    vocab = ["a", "b", "", "dd", "é", "温度", "x" * 30, "$sys", "😀"]
+    for _ in range(1500):
+        tenant = rng.choice(["t", "tenantA", "租户"])
+        lv = [rng.choice(vocab) for _ in range(rng.randint(1, 7))]
+        topic = "/".join(lv)
+        assert schema.retain_key(tenant, topic) == O.retain_key(tenant, topic), topic
+        f = list(lv)
+        for i in range(len(f)):
+            if rng.random() < 0.25:
+                f[i] = "+"
+        if rng.random() < 0.3:
+            f[-1] = "#"
+        tf = "/".join(f)
+        assert schema.retain_key_prefix(tenant, tf) == O.retain_key_prefix(tenant, tf), tf

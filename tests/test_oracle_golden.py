@@ -780,3 +780,42 @@ def test_reference_backward_seek_with_trailing_empty_topic_level():
     trie = kv.match_batch(["t"], ["dd/"], None, mode=O.MODE_TRIE)
     assert brute.route_sets() == trie.route_sets() == ref.route_sets()
     assert len(brute.routes(0)) == 1
+
+
+# ------------------------------------------------------------------ retain store schema
+# bifromq-retain/bifromq-retain-store-schema/src/test/java/org/apache/bifromq/retain/store/schema/KVSchemaUtilTest.java:43-74,
+# LevelHashTest.java:30-41. The reference's vectors are structural (prefix = tenantNS ++ levels ++ LevelHash.hash(prefix levels));
+# LevelHash itself is FNV-1a 32 (offset 0x811c9dc5, prime 0x01000193) over UTF-16 code units, low byte: the published FNV-1a test
+# vectors "" -> 0x811c9dc5 and "a" -> 0xe40c292c pin its two constants.
+def _levels_u16(n):
+    return bytes([(n >> 8) & 0xFF, n & 0xFF])
+
+
+def test_level_hash_known_answers():
+    assert O.level_hash_byte("") == 0xC5 and O.level_hash_byte("a") == 0x2C
+    assert O.level_hash_byte("foobar") == 0xBF9CF968 & 0xFF          # FNV-1a 32 published vector
+    assert len({O.level_hash_byte(x) for x in ["a", "b", "c"]}) == 3
+
+
+def test_retain_message_key_prefix_vectors():   # KVSchemaUtilTest.java:43-74
+    tenant = "tenantA"
+    ns = O.tenant_begin_key(tenant)
+
+    def H(*levels):
+        return bytes(O.level_hash_byte(l) for l in levels)
+    cases = [("#", 0, H()), ("/#", 1, H("")), ("+", 1, H()), ("+/#", 1, H()), ("a/#", 1, H("a")), ("/a", 2, H("", "a")),
+             ("a/+", 2, H("a")), ("a/b", 2, H("a", "b")), ("/a/#", 2, H("", "a")), ("/a/+", 3, H("", "a")),
+             ("/a/+/+", 4, H("", "a")), ("/+/b/", 4, H("")), ("/+/b/+/", 5, H(""))]
+    for tf, levels, hashes in cases:
+        assert O.retain_key_prefix(tenant, tf) == ns + _levels_u16(levels) + hashes, tf
+
+
+def test_retain_message_key_layout_and_tenant_parse():   # KVSchemaUtilTest.java:96-104 + KVSchemaUtil.java:44-50
+    k = O.retain_key("tenantA", "/a/b/c")
+    ns = O.tenant_begin_key("tenantA")
+    assert k.startswith(ns) and k[len(ns):len(ns) + 2] == _levels_u16(4)
+    assert k[len(ns) + 2:len(ns) + 6] == bytes(O.level_hash_byte(l) for l in ["", "a", "b", "c"])
+    assert k[len(ns) + 6:] == b"\x00a\x00b\x00c"               # escape(topic): '/' -> NUL
+    # a retain key starts with the prefix of every filter that can match its topic by a plain prefix scan
+    for tf in ["/a/b/c", "/a/b/+", "/a/+/+", "/+/b/c"]:
+        assert k.startswith(O.retain_key_prefix("tenantA", tf))
