@@ -80,6 +80,7 @@ _SIGNATURES = {
     "bfq_device_result_wait": (_i32, [C.POINTER(BfqDeviceResult)]),
     "bfq_device_result_release": (None, [C.POINTER(BfqDeviceResult)]),
     "bfq_expand_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "bfq_range_lookup": (_i32, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bfq_fanout_device": (_i32, [C.POINTER(BfqDeviceResult), _vp, _vp, _i64, _vp, C.POINTER(BfqFanoutResult)]),
     "bfq_fanout_deliverer": (_i32, [_vp, _i32, C.POINTER(_i32), _vp, _i64, C.POINTER(_i64)]),
     "bfq_exchange_unique_id": (_i32, [_vp, _i32]),

@@ -204,3 +204,39 @@ class Exchange:
             self.close()
         except Exception:
             pass
+
+
+def range_lookup(tenants, topics, topic_tenant, candidates, device=0):
+    """TenantRangeLookupCache.lookup for a batch (bfq_range_lookup). candidates[t] = the ordered candidate ranges of tenant t,
+    each None (no Fact) or a pair (first, last) of global filter level lists (either may be None: empty range); level 0 of
+    first / last is the tenant id. Returns, per topic, the list of kept candidate indices."""
+    import numpy as np
+
+    from . import _native as N
+    tb, toff = N.as_blob(tenants)
+    pb, poff = N.as_blob(topics)
+    tt = np.ascontiguousarray(topic_tenant, dtype=np.int32)
+    cand_off = np.zeros(len(tenants) + 1, np.int64)
+    flags, firsts, lasts = [], [], []
+    for t, cl in enumerate(candidates):
+        cand_off[t + 1] = cand_off[t] + len(cl)
+        for c in cl:
+            if c is None:
+                flags.append(0)
+                firsts.append(b"")
+                lasts.append(b"")
+                continue
+            first, last = c
+            enc = lambda lv: b"\0".join(x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in lv)
+            flags.append(1 | (2 if first is not None else 0) | (4 if last is not None else 0))
+            firsts.append(enc(first) if first is not None else b"")
+            lasts.append(enc(last) if last is not None else b"")
+    fl = np.asarray(flags + [0], np.uint8)
+    fb, foff = N.as_blob(firsts)
+    lb, loff = N.as_blob(lasts)
+    keep_off = np.zeros(len(topics) + 1, np.int64)
+    total = int(sum(cand_off[t + 1] - cand_off[t] for t in tt.tolist())) if len(topics) else 0
+    keep = np.zeros(max(total, 1), np.uint8)
+    N.check(N.lib.bfq_range_lookup(device, N.ptr(tb), N.ptr(toff), len(tenants), N.ptr(pb), N.ptr(poff), N.ptr(tt), len(topics),
+                                   N.ptr(cand_off), N.ptr(fl), N.ptr(fb), N.ptr(foff), N.ptr(lb), N.ptr(loff), N.ptr(keep_off), N.ptr(keep)))
+    return [np.nonzero(keep[keep_off[i]:keep_off[i + 1]])[0].tolist() for i in range(len(topics))]

@@ -208,6 +208,27 @@ int32_t bfq_expand_device(const bfq_device_result* res, int64_t* d_offsets, int6
                           void* stream, int64_t* n_ranks);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched range pruning on the dist-server side: TenantRangeLookupCache.lookup
+ * (bifromq-dist/bifromq-dist-server/src/main/java/org/apache/bifromq/dist/server/scheduler/TenantRangeLookupCache.java:70-106)
+ * decides, per publish topic, which of the tenant's KV ranges can hold a matching route: a range with a Fact
+ * {firstGlobalFilterLevels, lastGlobalFilterLevels} stays a candidate iff the topic's expansion set (every filter that matches
+ * it) has a member in [first, last]; the reference runs its expansion iterator per topic and candidate behind a cache. Here one
+ * kernel answers a whole batch (one thread per (topic, candidate): a lower-bound walk of the implicit expansion trie).
+ *   tenants / topics / topic_tenant   as for bfq_match
+ *   cand_off[n_tenants + 1]           tenant t's candidate ranges are [cand_off[t], cand_off[t + 1]), in boundary order
+ *   cand_flags[c]                     bit 0: the range has a Fact, bit 1: it has first, bit 2: it has last
+ *   first / last (blob, off[n_cand + 1])   the global filter levels joined by NUL bytes, level 0 = the tenant id
+ *   keep_off_out[n_topics + 1], keep_out[keep_off_out[n_topics]]   topic i's row = one byte per candidate of its tenant:
+ *                                     1 = the range is returned by the reference's lookup, 0 = it is not
+ * Semantics are the reference's loop, literally: no Fact -> kept; a Fact without first or last -> empty range, skipped; the
+ * first range whose seek runs past the end of the expansion set ends the scan. Stateless; needs a CUDA device.
+ * ---------------------------------------------------------------------------------------------- */
+int32_t bfq_range_lookup(int32_t device_ordinal, const uint8_t* tenants, const int64_t* tenant_off, int32_t n_tenants,
+                         const uint8_t* topics, const int64_t* topic_off, const int32_t* topic_tenant, int64_t n_topics,
+                         const int64_t* cand_off, const uint8_t* cand_flags, const uint8_t* first_blob, const int64_t* first_off,
+                         const uint8_t* last_blob, const int64_t* last_off, int64_t* keep_off_out, uint8_t* keep_out);
+
+/* ------------------------------------------------------------------------------------------------
  * Fan-out expansion on the device: the step right behind the match. DeliverExecutorGroup.submit
  * (DW/DeliverExecutorGroup.java:112-231) walks every matched route of a message, resolves a shared subscription to one
  * member (:242-278) and hands each route to the deliverer of its (subBrokerId, delivererKey) (DW/DeliverExecutor.java:89-93),

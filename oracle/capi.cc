@@ -299,6 +299,44 @@ int64_t orc_expansion_list(const uint8_t* topics, const int64_t* topic_off, int6
     o += body;
     return emit(o, out, cap);
 }
+// TenantRangeLookupCache.lookup(CacheKey) literally (bifromq-dist/bifromq-dist-server/src/main/java/org/apache/bifromq/dist/server/
+// scheduler/TenantRangeLookupCache.java:70-106) for ONE topic of a tenant over its ordered candidate ranges: flags[k] bit 0 = the
+// candidate has a Fact, bit 1 = the Fact has firstGlobalFilterLevels, bit 2 = lastGlobalFilterLevels; first / last are the global
+// filter levels joined by NUL (level 0 = tenant id). keep[k] = 1 iff the candidate is in the returned collection.
+void orc_range_lookup(const uint8_t* tenant, int64_t tn, const uint8_t* topic, int64_t pn, int64_t n_cand, const uint8_t* flags,
+                      const uint8_t* first_blob, const int64_t* first_off, const uint8_t* last_blob, const int64_t* last_off, uint8_t* keep) {
+    TopicTrie trie(true);                                                          // TopicTrieNode.builder(true)   :71
+    Levels global{S(tenant, tn)};
+    for (auto& l : parse(S(topic, pn), false)) global.push_back(l);                // TopicUtil.parse(tenantId, topic, false)   :72
+    trie.add_topic(global, 0);
+    TopicFilterIterator it(trie);                                                   // :73-75
+    auto joined = [](const Levels& l) {                                             // fastJoin(NUL, levels)
+        std::string s;
+        for (size_t i = 0; i < l.size(); i++) {
+            if (i) s.push_back('\0');
+            s += l[i];
+        }
+        return s;
+    };
+    for (int64_t k = 0; k < n_cand; k++) keep[k] = 0;
+    for (int64_t k = 0; k < n_cand; k++) {                                          // :77
+        if (!(flags[k] & 1)) {                                                      // no Fact: conservatively included   :79-82
+            keep[k] = 1;
+            continue;
+        }
+        if ((flags[k] & 6) != 6) continue;                                          // range is empty   :84-87
+        const Levels first = parse(S(first_blob + first_off[k], first_off[k + 1] - first_off[k]), true);
+        const Levels last = parse(S(last_blob + last_off[k], last_off[k + 1] - last_off[k]), true);
+        it.seek(first);                                                             // :90
+        if (it.is_valid()) {                                                        // :91
+            const Levels key = it.key();
+            if (key == first || java_compare(joined(key), joined(last)) <= 0) keep[k] = 1;   // :93-98
+        } else {
+            break;                                                                  // :99-102
+        }
+    }
+}
+
 // seek(filter) -> serialised key levels, or -1 when the cursor is invalid
 int64_t orc_expansion_seek(const uint8_t* topics, const int64_t* topic_off, int64_t n, int32_t isGlobal,
                            const uint8_t* filter, int64_t fn, uint8_t* out, int64_t cap) {

@@ -40,6 +40,7 @@ def _load():
         "orc_route_matcher_from": (i64, [u8p, i64, u8p, i64]),
         "orc_receiver_url": (i64, [i32, u8p, i64, u8p, i64, u8p, i64]),
         "orc_tenant_begin_key": (i64, [u8p, i64, u8p, i64]),
+        "orc_range_lookup": (None, [u8p, i64, u8p, i64, i64, u8p, u8p, i64p, u8p, i64p, u8p]),
         "orc_retain_key": (i64, [u8p, i64, u8p, i64, u8p, i64]),
         "orc_retain_key_prefix": (i64, [u8p, i64, u8p, i64, u8p, i64]),
         "orc_level_hash_byte": (i32, [u8p, i64]),
@@ -487,3 +488,27 @@ def route_group_members_in_wire_order(value):
                 varint()
         out.append(key)
     return out
+
+
+# ------------------------------------------------------------------ dist-server range pruning
+def range_lookup(tenant, topic, candidates):
+    """TenantRangeLookupCache.lookup restated literally (oracle/capi.cc: orc_range_lookup). candidates: ordered list of None
+    (no Fact) or (first, last) global filter level lists (either may be None). Returns the kept candidate indices."""
+    flags, firsts, lasts = [], [], []
+    enc = lambda lv: b"\0".join(_b(x) for x in lv)
+    for c in candidates:
+        if c is None:
+            flags.append(0); firsts.append(b""); lasts.append(b"")
+        else:
+            first, last = c
+            flags.append(1 | (2 if first is not None else 0) | (4 if last is not None else 0))
+            firsts.append(enc(first) if first is not None else b"")
+            lasts.append(enc(last) if last is not None else b"")
+    fb, foff = blob(firsts)
+    lb, loff = blob(lasts)
+    keep = (C.c_uint8 * max(len(candidates), 1))()
+    fl = bytes(flags) + b"\0"
+    t, p = _b(tenant), _b(topic)
+    lib.orc_range_lookup(t, len(t), p, len(p), len(candidates), fl, fb.tobytes() + b"\0", foff, lb.tobytes() + b"\0", loff,
+                         C.cast(keep, C.c_char_p))
+    return [k for k in range(len(candidates)) if keep[k]]

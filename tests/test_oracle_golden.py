@@ -819,3 +819,11 @@ def test_retain_message_key_layout_and_tenant_parse():   # KVSchemaUtilTest.java
     # a retain key starts with the prefix of every filter that can match its topic by a plain prefix scan
     for tf in ["/a/b/c", "/a/b/+", "/a/+/+", "/+/b/c"]:
         assert k.startswith(O.retain_key_prefix("tenantA", tf))
+
+
+# ------------------------------------------------------------------ dist-server range pruning
+def test_tenant_range_lookup_cache_vectors():
+    """TenantRangeLookupCacheTest.java:109-330 through the oracle's literal restatement of TenantRangeLookupCache.lookup"""
+    from golden.range_lookup_vectors import T, VECTORS
+    for topic, cands, want in VECTORS:
+        assert O.range_lookup(T, topic, cands) == want, (topic, cands)
