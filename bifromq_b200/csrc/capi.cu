@@ -1394,7 +1394,9 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     // Large batches are cut into sub-batches that flow through three streams: all H2D copies on one, the kernels +
     // compaction + D2H of consecutive sub-batches alternating on two others, so the copy of sub-batch c+1 and the
     // result read-back of c-1 overlap the kernels of c (PCIe is full duplex; the copies dominate the host path).
-    int C = n >= (1 << 19) ? 8 : n >= (1 << 17) ? 4 : 1;   // more, smaller sub-batches shorten the un-overlapped tail (the last sub-batch's kernels + read-back)
+    // four sub-batches: eight were measured slower (2.45 ms vs 2.1 ms per 1M C4 topics): a 125k-topic sub-batch is less than one
+    // wave of tier-0 lanes, its kernel takes as long as a 250k one
+    int C = n >= (1 << 17) ? 4 : 1;
     CoreOut co;
     int64_t rbase = 0, tbase = 0;
     double kernel_ms = -1;
