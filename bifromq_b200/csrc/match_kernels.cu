@@ -1058,10 +1058,18 @@ void launch_match(const MatchParams& p, bool tier2, int n_warps_tier2, cudaStrea
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, match_topics_kernel<false>, WARPS_PER_CTA * 32, 0);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // occupancy is a property of the device / context: cached per device ordinal
+    static std::mutex occ_mu;
+    static int occ_of[64] = {0};
+    int ctas_per_sm;
+    {
+        std::lock_guard<std::mutex> g(occ_mu);
+        int& slot = occ_of[dev & 63];
+        if (slot == 0) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, match_topics_kernel<false>, WARPS_PER_CTA * 32, 0);
+            if (slot < 1) slot = 1;
+        }
+        ctas_per_sm = slot;
     }
     // persistent grid: a whole number of waves (SM count x resident CTAs per SM), grid-stride over topics
     int64_t ctas = (int64_t) sms * ctas_per_sm;
@@ -1132,7 +1140,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
                                     match_topics_lane_kernel<false, false, true>,  match_topics_lane_kernel<false, true, true>,
                                     match_topics_lane_kernel<true, false, true>,   match_topics_lane_kernel<true, true, true>};
     static std::mutex setup_mu;
-    static int ctas_of[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static int ctas_by_dev[64][8] = {};   // function attributes (the carve-out) and occupancy are per device: cached per ordinal
     static const int rootstep = getenv("BFQ_ROOTSTEP") ? atoi(getenv("BFQ_ROOTSTEP")) : 0;
     static const int prefetch = getenv("BFQ_PREFETCH") ? atoi(getenv("BFQ_PREFETCH")) : 1;
     static const int noalloc_forced = getenv("BFQ_NOALLOC") ? atoi(getenv("BFQ_NOALLOC")) : -1;
@@ -1141,6 +1149,7 @@ void launch_match_lanes(const MatchParams& p, cudaStream_t stream) {
     int ctas_per_sm;
     {
         std::lock_guard<std::mutex> g(setup_mu);
+        int* ctas_of = ctas_by_dev[dev & 63];
         if (ctas_of[variant] == 0) {
             // Shared memory and L1 share 256 KB per SM, and the kernel lives on L1 (topic bytes, top trie levels): with the
             // 228 KB carve-out (what 8 resident CTAs need) only 28 KB of L1 remain and the kernel runs 1.5x slower (measured).
