@@ -1012,6 +1012,12 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
     std::string err;
     nf.tenants.reserve(entries.size());
     sn->th.reserve(entries.size());
+    // the old snapshot's per-tenant fan-out tables may be filled in by a concurrent bfq_fanout_device: copy them under its lock
+    std::vector<Snapshot::TenantHost> old_th;
+    {
+        std::lock_guard<std::mutex> gf(old->fan_mu);
+        old_th = old->th;
+    }
     for (auto& e : entries) {
         if (e.plan < 0) {   // untouched: same region, ranks moved by the growth of the tenants before it
             TenantMeta m = of.tenants[(size_t) e.old_index];
@@ -1022,7 +1028,7 @@ int32_t commit_delta(bfq_index* h, const std::shared_ptr<Snapshot>& old, const s
             ppb += m.pp;
             pgb += m.pg;
             nf.tenants.push_back(std::move(m));
-            sn->th.push_back(old->th[(size_t) e.old_index]);
+            sn->th.push_back(old_th[(size_t) e.old_index]);
             continue;
         }
         Plan& pl = plans[(size_t) e.plan];
