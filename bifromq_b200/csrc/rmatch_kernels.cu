@@ -164,6 +164,38 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
         if (n_next > capF) overflow = true;
     };
 
+    // Visits every NODE of every frontier interval, 32 nodes per round, one per lane: the intervals of a block of 32 are
+    // flattened with a warp scan and each lane finds its (interval, offset) with a 5-step search over the scanned prefixes.
+    // (Round 1 gave each lane one INTERVAL and walked it sequentially: after a '+' level the frontier is ONE interval of
+    // hundreds of nodes, so one lane did hundreds of dependent probes while 31 idled.) fn(alive, node) is called by the whole
+    // warp in lock step: it may use warp collectives.
+    auto for_each_frontier_node = [&](auto&& fn) {
+        for (uint32_t base = 0; base < n_fr && !overflow; base += 32) {
+            const bool act = base + lane < n_fr;
+            const uint2 iv = act ? fr_cur[base + lane] : make_uint2(0u, 0u);
+            uint32_t inc = iv.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(RFULL, inc, o);
+                if (lane >= o) inc += y;
+            }
+            const uint32_t pre = inc - iv.y, tot = __shfl_sync(RFULL, inc, 31);
+            for (uint32_t t0 = 0; t0 < tot && !overflow; t0 += 32) {
+                const uint32_t g = t0 + lane;
+                int lo = 0, hi = 32;
+#pragma unroll
+                for (int it = 0; it < 5; it++) {   // largest lane whose exclusive prefix is <= g (prefixes are non-decreasing)
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t pm = __shfl_sync(RFULL, pre, mid);
+                    if (pm <= g) lo = mid;
+                    else hi = mid;
+                }
+                const uint32_t ix = __shfl_sync(RFULL, iv.x, lo), ip = __shfl_sync(RFULL, pre, lo);
+                fn(g < tot, ix + (g - ip));
+            }
+        }
+    };
+
     if (root >= 0) {
         if (lane == 0) fr_cur[0] = make_uint2((uint32_t) root, 1u);
         n_fr = 1;
@@ -250,82 +282,78 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
                         emit(split, SPACE_BFS | o0, o1 - o0);
                         emit(split, SPACE_BFS | o2, o3 - o2);
                     } else if (hash_next) {
-                        // "+/#": whole subtrees of all children; per frontier node one DFS range (minus own topic)
-                        for (uint32_t j = 0; __any_sync(RFULL, act && j < iv.y); j++) {
-                            const bool a2 = act && j < iv.y;
-                            RNode nd{};
-                            uint32_t own = 0;
-                            if (a2) {
-                                nd = load_node(p.nodes + iv.x + j);
-                                own = load_node(p.nodes + iv.x + j + 1).own_prefix - nd.own_prefix;
-                            }
-                            const uint32_t lo = nd.sub_begin + own;
-                            const bool sp = a2 && level == 0 && nd.sys_count > 0;
-                            RNode s0{}, s1{};
-                            if (sp) {
-                                s0 = load_node(p.nodes + nd.sys_begin);
-                                s1 = load_node(p.nodes + nd.sys_begin + nd.sys_count - 1);
-                            }
-                            emit(a2 && !sp, lo, nd.sub_end - lo);
-                            emit(sp, lo, s0.sub_begin - lo);
-                            emit(sp, s1.sub_end, nd.sub_end - s1.sub_end);
-                        }
+                        // "+/#": handled below, per frontier NODE
                     } else {
                         push(act && !split, cb, ce - cb);
                         push(split, cb, sb - cb);
                         push(split, se, ce - se);
                     }
                 }
+                if (hash_next && !last) {
+                    // "+/#": whole subtrees of all children; per frontier node one DFS range (minus its own topic)
+                    for_each_frontier_node([&](bool a2, uint32_t id) {
+                        RNode nd{};
+                        uint32_t own = 0;
+                        if (a2) {
+                            nd = load_node(p.nodes + id);
+                            own = load_node(p.nodes + id + 1).own_prefix - nd.own_prefix;
+                        }
+                        const uint32_t lo = nd.sub_begin + own;
+                        const bool sp = a2 && level == 0 && nd.sys_count > 0;
+                        RNode s0{}, s1{};
+                        if (sp) {
+                            s0 = load_node(p.nodes + nd.sys_begin);
+                            s1 = load_node(p.nodes + nd.sys_begin + nd.sys_count - 1);
+                        }
+                        emit(a2 && !sp, lo, nd.sub_end - lo);
+                        emit(sp, lo, s0.sub_begin - lo);
+                        emit(sp, s1.sub_end, nd.sub_end - s1.sub_end);
+                    });
+                }
                 if (last || hash_next) break;
             } else {
                 // exact level: probe every node of every frontier interval
                 const int nchunks = tlen <= (int) TOKEN_BYTES ? 1 : (tlen + (int) TOKEN_BYTES - 1) / (int) TOKEN_BYTES;
-                for (uint32_t base = 0; base < n_fr && !overflow; base += 32) {
-                    const bool act = base + lane < n_fr;
-                    const uint2 iv = act ? fr_cur[base + lane] : make_uint2(0u, 0u);
-                    for (uint32_t j = 0; __any_sync(RFULL, act && j < iv.y) && !overflow; j++) {
-                        bool alive = act && j < iv.y;
-                        uint32_t node = iv.x + j;
-                        for (int c = 0; c < nchunks; c++) {
-                            const int cpos = pos + c * (int) TOKEN_BYTES;
-                            const int cend = min(e, cpos + (int) TOKEN_BYTES);
-                            const uint32_t lenw = c == nchunks - 1 ? (uint32_t) tlen : (LEN_CONT | (uint32_t) c);
-                            __syncwarp();
-                            if (lane < (int) TOKEN_WORDS) {
-                                uint32_t v = 0;
+                for_each_frontier_node([&](bool alive, uint32_t node) {
+                    for (int c = 0; c < nchunks; c++) {
+                        const int cpos = pos + c * (int) TOKEN_BYTES;
+                        const int cend = min(e, cpos + (int) TOKEN_BYTES);
+                        const uint32_t lenw = c == nchunks - 1 ? (uint32_t) tlen : (LEN_CONT | (uint32_t) c);
+                        __syncwarp();
+                        if (lane < (int) TOKEN_WORDS) {
+                            uint32_t v = 0;
 #pragma unroll
-                                for (int b = 0; b < 4; b++) {
-                                    const int idx = cpos + lane * 4 + b;
-                                    if (idx < cend) v |= byte_at(idx) << (8 * b);
-                                }
-                                ws.keyw[lane] = v;
+                            for (int b = 0; b < 4; b++) {
+                                const int idx = cpos + lane * 4 + b;
+                                if (idx < cend) v |= byte_at(idx) << (8 * b);
                             }
-                            __syncwarp();
-                            uint32_t k[6];
-#pragma unroll
-                            for (int q = 0; q < 6; q++) k[q] = ws.keyw[q];
-                            const uint64_t tokh = token_hash(lenw, k);
-                            if (alive) {
-                                node = rprobe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh);
-                                alive = node != NONE;
-                            }
+                            ws.keyw[lane] = v;
                         }
-                        if (last) {
-                            uint32_t o0 = 0, o1 = 0;
-                            if (alive) {
-                                o0 = load_node(p.nodes + node).own_prefix;
-                                o1 = load_node(p.nodes + node + 1).own_prefix;
-                            }
-                            emit(alive, SPACE_BFS | o0, o1 - o0);
-                        } else if (hash_next) {
-                            RNode nd{};
-                            if (alive) nd = load_node(p.nodes + node);
-                            emit(alive, nd.sub_begin, nd.sub_end - nd.sub_begin);   // "x/#": x itself and everything below
-                        } else {
-                            push(alive, node, 1u);
+                        __syncwarp();
+                        uint32_t k[6];
+#pragma unroll
+                        for (int q = 0; q < 6; q++) k[q] = ws.keyw[q];
+                        const uint64_t tokh = token_hash(lenw, k);
+                        if (alive) {
+                            node = rprobe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh);
+                            alive = node != NONE;
                         }
                     }
-                }
+                    if (last) {
+                        uint32_t o0 = 0, o1 = 0;
+                        if (alive) {
+                            o0 = load_node(p.nodes + node).own_prefix;
+                            o1 = load_node(p.nodes + node + 1).own_prefix;
+                        }
+                        emit(alive, SPACE_BFS | o0, o1 - o0);
+                    } else if (hash_next) {
+                        RNode nd{};
+                        if (alive) nd = load_node(p.nodes + node);
+                        emit(alive, nd.sub_begin, nd.sub_end - nd.sub_begin);   // "x/#": x itself and everything below
+                    } else {
+                        push(alive, node, 1u);
+                    }
+                });
                 if (last || hash_next) break;
             }
             __syncwarp();
