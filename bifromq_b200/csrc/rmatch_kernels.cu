@@ -112,11 +112,16 @@ __device__ __forceinline__ RNode load_node(const RNode* n) {
     return r;
 }
 
-// (parent, lenw, k) -> child id, or NONE
+// (parent, lenw, k) -> child id, or NONE; *nd = the child's record (without its '$' run), *own_next = own_prefix of the node
+// behind it — both carried in the slot's payload half (see rebuild)
 __device__ __forceinline__ uint32_t rprobe(const Slot* slots, const uint4* tags, uint32_t n_blocks, uint32_t parent, uint32_t lenw,
-                                           const uint32_t (&k)[6], uint64_t tokh) {
+                                           const uint32_t (&k)[6], uint64_t tokh, RNode* nd, uint32_t* own_next) {
     uint32_t w[16], slot = 0;
-    return probe(slots, tags, n_blocks, parent, lenw, k, tokh, w, slot) ? w[W_PLUS] : NONE;
+    if (!probe(slots, tags, n_blocks, parent, lenw, k, tokh, w, slot)) return NONE;
+    nd->child_begin = w[9]; nd->child_count = w[10]; nd->sub_begin = w[11]; nd->sub_end = w[12];
+    nd->own_prefix = w[13]; nd->sys_begin = 0; nd->sys_count = 0; nd->pad = 0;
+    *own_next = w[14];
+    return w[W_PLUS];
 }
 
 template <bool kBig>
@@ -315,6 +320,8 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
                 // exact level: probe every node of every frontier interval
                 const int nchunks = tlen <= (int) TOKEN_BYTES ? 1 : (tlen + (int) TOKEN_BYTES - 1) / (int) TOKEN_BYTES;
                 for_each_frontier_node([&](bool alive, uint32_t node) {
+                    RNode cnd{};
+                    uint32_t own_next = 0;
                     for (int c = 0; c < nchunks; c++) {
                         const int cpos = pos + c * (int) TOKEN_BYTES;
                         const int cend = min(e, cpos + (int) TOKEN_BYTES);
@@ -335,21 +342,14 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
                         for (int q = 0; q < 6; q++) k[q] = ws.keyw[q];
                         const uint64_t tokh = token_hash(lenw, k);
                         if (alive) {
-                            node = rprobe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh);
+                            node = rprobe(p.slots, p.tags, p.n_blocks, node, lenw, k, tokh, &cnd, &own_next);
                             alive = node != NONE;
                         }
                     }
                     if (last) {
-                        uint32_t o0 = 0, o1 = 0;
-                        if (alive) {
-                            o0 = load_node(p.nodes + node).own_prefix;
-                            o1 = load_node(p.nodes + node + 1).own_prefix;
-                        }
-                        emit(alive, SPACE_BFS | o0, o1 - o0);
+                        emit(alive, SPACE_BFS | cnd.own_prefix, own_next - cnd.own_prefix);
                     } else if (hash_next) {
-                        RNode nd{};
-                        if (alive) nd = load_node(p.nodes + node);
-                        emit(alive, nd.sub_begin, nd.sub_end - nd.sub_begin);   // "x/#": x itself and everything below
+                        emit(alive, cnd.sub_begin, cnd.sub_end - cnd.sub_begin);   // "x/#": x itself and everything below
                     } else {
                         push(alive, node, 1u);
                     }
@@ -480,6 +480,7 @@ struct bfq_rindex {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] around all kernels of a match, [2,3] around rmatch_kernel
+    unsigned long long* h_small = nullptr;   // pinned scalars
     // staging: (tenant, topic) -> id ; id -> (tenant, topic)
     std::map<std::pair<std::string, std::string>, int64_t> staged;
     std::vector<std::pair<std::string, std::string>> by_id;   // id -> strings (tombstones keep their slot)
@@ -513,6 +514,7 @@ struct bfq_rindex {
         d_kept.release(); d_offsets.release(); d_counters.release(); d_ranges.release(); d_scratch.release();
         d_ord_keys.release(); d_ord_leader.release(); d_order.release(); d_hist.release(); d_ord_ctr.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (h_small) cudaFreeHost(h_small);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -674,7 +676,20 @@ int32_t rebuild(bfq_rindex* h) {
     table.init(edges.size());
     for (const Edge& e : edges) {
         const uint32_t s = table.place(e.parent, e.lenw, e.tok);
-        table.slots[s].w[W_PLUS] = e.child;
+        uint32_t* w = table.slots[s].w;
+        w[W_PLUS] = e.child;
+        if (e.child < VIRT_BASE) {
+            // the child's node record rides in the slot's payload half: an exact step is tag + slot, with no third dependent
+            // access for the record (words 9..14: child_begin, child_count, sub_begin, sub_end, own_prefix, own_prefix of the
+            // next node; the '$' run is only needed for tenant roots, which are never reached through a slot)
+            const RNode& r = rn[e.child];
+            w[9] = r.child_begin;
+            w[10] = r.child_count;
+            w[11] = r.sub_begin;
+            w[12] = r.sub_end;
+            w[13] = r.own_prefix;
+            w[14] = rn[e.child + 1].own_prefix;
+        }
     }
     SlotVec& slots = table.slots;
     // ---- upload
@@ -994,12 +1009,12 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     RCUDA_TRY(h->d_scan_tmp.reserve(tmp_bytes));
     cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_kept.p, h->d_offsets.p, (int) n, st);
     h->launches += 2;
-    std::vector<unsigned long long> hoff((size_t) n), hkept((size_t) n), htot((size_t) n);
-    RCUDA_TRY(cudaMemcpyAsync(hoff.data(), h->d_offsets.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
-    RCUDA_TRY(cudaMemcpyAsync(hkept.data(), h->d_kept.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
-    RCUDA_TRY(cudaMemcpyAsync(htot.data(), h->d_total.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+    // only the grand total is needed on the host before the expansion (to size the id buffer): two scalars, not the arrays
+    if (!h->h_small) RCUDA_TRY(cudaMallocHost(&h->h_small, 4 * sizeof(unsigned long long)));
+    RCUDA_TRY(cudaMemcpyAsync(h->h_small, h->d_offsets.p + (n - 1), 8, cudaMemcpyDeviceToHost, st));
+    RCUDA_TRY(cudaMemcpyAsync(h->h_small + 1, h->d_kept.p + (n - 1), 8, cudaMemcpyDeviceToHost, st));
     RCUDA_TRY(cudaStreamSynchronize(st));
-    const unsigned long long total_ids = hoff[(size_t) n - 1] + hkept[(size_t) n - 1];
+    const unsigned long long total_ids = h->h_small[0] + h->h_small[1];
     RCUDA_TRY(h->d_ids.reserve((size_t) std::max<unsigned long long>(total_ids, 1)));
     rexpand_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, st>>>(n, h->d_span_begin.p, h->d_span_count.p, h->d_ranges.p,
                                                                       h->d_offsets.p, h->d_kept.p, h->d_dfs_to_id.p,
@@ -1008,13 +1023,13 @@ int32_t bfq_rmatch(bfq_rindex* h, const uint8_t* tenants, const int64_t* tenant_
     RCUDA_TRY(cudaGetLastError());
     RCUDA_TRY(cudaEventRecord(h->ev[1], st));
     auto t2 = std::chrono::steady_clock::now();
+    // the result owns its arrays: offsets / totals / ids are read back straight into them (same 8-byte element types)
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offsets are copied without conversion");
     res->ids.resize((size_t) total_ids);
+    RCUDA_TRY(cudaMemcpyAsync(res->offsets.data(), h->d_offsets.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+    RCUDA_TRY(cudaMemcpyAsync(res->totals.data(), h->d_total.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
     if (total_ids) RCUDA_TRY(cudaMemcpyAsync(res->ids.data(), h->d_ids.p, (size_t) total_ids * 8, cudaMemcpyDeviceToHost, st));
     RCUDA_TRY(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < n; i++) {
-        res->offsets[(size_t) i] = (int64_t) hoff[(size_t) i];
-        res->totals[(size_t) i] = (int64_t) htot[(size_t) i];
-    }
     res->offsets[(size_t) n] = (int64_t) total_ids;
     auto t3 = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
