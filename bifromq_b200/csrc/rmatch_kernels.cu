@@ -398,7 +398,7 @@ __device__ __forceinline__ void rmatch_one(const RMatchParams& p, RWarpSmem& ws,
 }
 
 template <bool kBig>
-__global__ void __launch_bounds__(R_WARPS * 32) rmatch_kernel(const RMatchParams p) {
+__global__ void __launch_bounds__(R_WARPS * 32, 5) rmatch_kernel(const RMatchParams p) {
     __shared__ RWarpSmem sm[R_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     RWarpSmem& ws = sm[wid];
