@@ -388,6 +388,7 @@ def main_inverse(args, rank, world, local):
         k_ms.append(last.timings_ms["device_rmatch_kernel"])
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
+    idx.match_blobs(tenants, f_blob, f_off, f_tt, None)          # warm: the first unlimited call grows the id / range buffers
     unl = idx.match_blobs(tenants, f_blob, f_off, f_tt, None)
     if numa:
         try:
