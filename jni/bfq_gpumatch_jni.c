@@ -196,3 +196,86 @@ jlongArray JFN(rmatch)(JNIEnv* env, jclass cls, jlong h, jobject tenants, jobjec
     bfq_rresult_free(r);
     return out;
 }
+/* RetainStoreCoProc.load (bifromq-retain/bifromq-retain-store/src/main/java/org/apache/bifromq/retain/store/RetainStoreCoProc.java:
+ * 279-296): the raw KV keys of the range scan -> topic ids (-1 = not a retain key) */
+jlongArray JFN(rindexLoadKeys)(JNIEnv* env, jclass cls, jlong h, jobject keys, jobject keyOff, jlong n) {
+    (void) cls;
+    int64_t* ids = (int64_t*) malloc((size_t) (n > 0 ? n : 1) * sizeof(int64_t));
+    if (!ids) { throw_bfq(env, BFQ_E_NOMEM); return NULL; }
+    int32_t rc = bfq_rindex_load_keys(RIDX(h), ADDR(keys), ADDR(keyOff), n, ids);
+    if (rc != BFQ_OK) { free(ids); throw_bfq(env, rc); return NULL; }
+    jlongArray out = (*env)->NewLongArray(env, (jsize) n);
+    if (out) (*env)->SetLongArrayRegion(env, out, 0, (jsize) n, (const jlong*) ids);
+    free(ids);
+    return out;
+}
+/* {offsets[n + 1], keyOff[nKeys + 1], keyBlob}: the matched topics as the retain KV keys RetainStoreCoProc.match reads next (:177-188) */
+jobjectArray JFN(rmatchRetainKeys)(JNIEnv* env, jclass cls, jlong h, jobject tenants, jobject tenantOff, jint nTenants, jobject filters,
+                                   jobject filterOff, jobject filterTenant, jlong n, jlongArray limit) {
+    (void) cls;
+    jlong* lim = limit ? (*env)->GetLongArrayElements(env, limit, NULL) : NULL;
+    bfq_rresult* r = NULL;
+    int32_t rc = bfq_rmatch(RIDX(h), ADDR(tenants), ADDR(tenantOff), nTenants, ADDR(filters), ADDR(filterOff), ADDR(filterTenant), n,
+                            (const int64_t*) lim, &r);
+    if (lim) (*env)->ReleaseLongArrayElements(env, limit, lim, JNI_ABORT);
+    if (rc != BFQ_OK) { throw_bfq(env, rc); return NULL; }
+    int64_t n_ids = 0;
+    (void) bfq_rresult_ids(r, &n_ids);
+    const int64_t blob_len = bfq_rresult_retain_keys(RIDX(h), r, NULL, 0, NULL);
+    uint8_t* blob = blob_len >= 0 ? (uint8_t*) malloc((size_t) blob_len + 1) : NULL;
+    int64_t* key_off = blob ? (int64_t*) malloc((size_t) (n_ids + 1) * sizeof(int64_t)) : NULL;
+    if (!blob || !key_off) {
+        free(blob); free(key_off); bfq_rresult_free(r);
+        throw_bfq(env, blob_len < 0 ? (int32_t) blob_len : BFQ_E_NOMEM);
+        return NULL;
+    }
+    const int64_t got = bfq_rresult_retain_keys(RIDX(h), r, blob, blob_len, key_off);
+    jobjectArray out = NULL;
+    if (got == blob_len) {
+        jlongArray offs = (*env)->NewLongArray(env, (jsize) (n + 1));
+        jlongArray koff = (*env)->NewLongArray(env, (jsize) (n_ids + 1));
+        jbyteArray kb = (*env)->NewByteArray(env, (jsize) blob_len);
+        (*env)->SetLongArrayRegion(env, offs, 0, (jsize) (n + 1), (const jlong*) bfq_rresult_offsets(r));
+        (*env)->SetLongArrayRegion(env, koff, 0, (jsize) (n_ids + 1), (const jlong*) key_off);
+        (*env)->SetByteArrayRegion(env, kb, 0, (jsize) blob_len, (const jbyte*) blob);
+        out = (*env)->NewObjectArray(env, 3, (*env)->FindClass(env, "java/lang/Object"), NULL);
+        (*env)->SetObjectArrayElement(env, out, 0, offs);
+        (*env)->SetObjectArrayElement(env, out, 1, koff);
+        (*env)->SetObjectArrayElement(env, out, 2, kb);
+    } else {
+        throw_bfq(env, got < 0 ? (int32_t) got : BFQ_E_STATE);
+    }
+    free(blob); free(key_off); bfq_rresult_free(r);
+    return out;
+}
+
+/* ---------------------------------------------------------------- dist-server range pruning (TenantRangeLookupCache.lookup,
+ * bifromq-dist/bifromq-dist-server/src/main/java/org/apache/bifromq/dist/server/scheduler/TenantRangeLookupCache.java:70-106)
+ * keepOff[nTopics + 1] followed by one 0/1 flag per (topic, candidate range of its tenant) */
+jlongArray JFN(rangeLookup)(JNIEnv* env, jclass cls, jint device, jobject tenants, jobject tenantOff, jint nTenants, jobject topics,
+                            jobject topicOff, jobject topicTenant, jlong nTopics, jobject candOff, jobject candFlags,
+                            jobject firstBlob, jobject firstOff, jobject lastBlob, jobject lastOff) {
+    (void) cls;
+    const int64_t* coff = (const int64_t*) ADDR(candOff);
+    const int32_t* tt = (const int32_t*) ADDR(topicTenant);
+    if (!coff || (nTopics > 0 && !tt)) { throw_bfq(env, BFQ_E_INVALID); return NULL; }
+    int64_t total = 0;   /* rows are sized by the caller's own candidate table */
+    for (jlong i = 0; i < nTopics; i++) {
+        if (tt[i] < 0 || tt[i] >= nTenants) { throw_bfq(env, BFQ_E_INVALID); return NULL; }
+        total += coff[tt[i] + 1] - coff[tt[i]];
+    }
+    int64_t* all = (int64_t*) malloc((size_t) (nTopics + 1 + total) * sizeof(int64_t));   /* keepOff ++ widened flags */
+    uint8_t* keep = (uint8_t*) malloc((size_t) total + 1);
+    if (!all || !keep) { free(all); free(keep); throw_bfq(env, BFQ_E_NOMEM); return NULL; }
+    int32_t rc = bfq_range_lookup(device, ADDR(tenants), ADDR(tenantOff), nTenants, ADDR(topics), ADDR(topicOff), tt, nTopics, coff,
+                                  ADDR(candFlags), ADDR(firstBlob), ADDR(firstOff), ADDR(lastBlob), ADDR(lastOff), all, keep);
+    jlongArray out = NULL;
+    if (rc != BFQ_OK) {
+        throw_bfq(env, rc);
+    } else if ((out = (*env)->NewLongArray(env, (jsize) (nTopics + 1 + total))) != NULL) {
+        for (int64_t i = 0; i < total; i++) all[nTopics + 1 + i] = keep[i];
+        (*env)->SetLongArrayRegion(env, out, 0, (jsize) (nTopics + 1 + total), (const jlong*) all);
+    }
+    free(all); free(keep);
+    return out;
+}

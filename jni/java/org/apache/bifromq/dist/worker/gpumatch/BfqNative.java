@@ -50,4 +50,16 @@ final class BfqNative {
     static native void rindexCommit(long h);
     static native long[] rmatch(long h, ByteBuffer tenants, ByteBuffer tenantOff, int nTenants, ByteBuffer filters,
                                 ByteBuffer filterOff, ByteBuffer filterTenant, long n, long[] limit);   // offsets[n+1] ++ ids
+    // RetainStoreCoProc.load: feed the raw retain-store KV keys of the range scan (no TopicMessage parsing) -> ids, -1 = not a key
+    static native long[] rindexLoadKeys(long h, ByteBuffer keys, ByteBuffer keyOff, long n);
+    // RetainStoreCoProc.match: as rmatch, but the matched topics come back as the retain KV keys to reader.get():
+    // {long[] offsets[n+1] of filters -> key index, long[] keyOff[nKeys+1], byte[] keyBlob}
+    static native Object[] rmatchRetainKeys(long h, ByteBuffer tenants, ByteBuffer tenantOff, int nTenants, ByteBuffer filters,
+                                            ByteBuffer filterOff, ByteBuffer filterTenant, long n, long[] limit);
+
+    // ---- dist-server side: TenantRangeLookupCache.lookup for a whole batch -> keepOff[nTopics+1] ++ keep flags (one per candidate)
+    static native long[] rangeLookup(int deviceOrdinal, ByteBuffer tenants, ByteBuffer tenantOff, int nTenants, ByteBuffer topics,
+                                     ByteBuffer topicOff, ByteBuffer topicTenant, long nTopics, ByteBuffer candOff,
+                                     ByteBuffer candFlags, ByteBuffer firstBlob, ByteBuffer firstOff, ByteBuffer lastBlob,
+                                     ByteBuffer lastOff);
 }
