@@ -247,7 +247,7 @@ def oracle_for_sample(w, idx):
     return O, kv, w.tenants, (pb, poff), tt
 
 
-def run_cpu_baseline(w, args, mode_name, cached=False):
+def run_cpu_baseline(w, args, mode_name, cached=False, n_passes=5, n_warm=0):
     """times the oracle on the host cores over a bounded, unbiased sample; returns the cpu_baseline dict and the per-topic
     algorithmic-byte figures measured on the same sample.
     mode_name: "trie" = the oracle's per-topic filter-trie walk over the WHOLE batch (also the exact V / P / ranges counters);
@@ -287,9 +287,22 @@ def run_cpu_baseline(w, args, mode_name, cached=False):
     n_run = len(tt_run)
     # warm (also builds the oracle's trie outside the timed region)
     kv.match_blobs(tb, toff, pb, poff, tt_run, min(n_run, 256), 2 ** 31 - 1, 100, mode, singleton, cores)
-    # >= 5 timed passes, each repeated until it lasts >= 1 s of wall time; the MEDIAN pass is reported
+    if n_warm > 0 and not cached:
+        # the reference arm: bound the whole --steps K --warmup W run to ~3 minutes of matching by shrinking the sample (a
+        # prefix of a uniform random sample is one) if a pilot pass says K + W passes would take longer
+        kv.match_blobs(tb, toff, pb, poff, tt_run, n_run, 2 ** 31 - 1, 100, mode, singleton, cores)
+        pilot = kv.last_match_seconds
+        budget = 180.0
+        if pilot * (n_passes + n_warm) > budget and n_run > 10000:
+            n_run = max(10000, int(n_run * budget / (pilot * (n_passes + n_warm))))
+            n = n_run
+        n_warm -= 1
+    for _ in range(n_warm):   # --warmup W: whole passes of the sample, untimed
+        kv.match_blobs(tb, toff, pb, poff, tt_run, n_run, 2 ** 31 - 1, 100, mode, singleton, cores)
+    # n_passes timed passes (5 for the cpu_baseline leg, --steps K for the reference arm), each repeated until it lasts >= 1 s
+    # of wall time; the MEDIAN pass is reported
     passes, per_pass = [], []
-    for _ in range(5):
+    for _ in range(max(1, n_passes)):
         dt, reps = 0.0, 0
         while dt < 1.0 and reps < 64:
             out = kv.match_blobs(tb, toff, pb, poff, tt_run, n_run, 2 ** 31 - 1, 100, mode, singleton, cores)
@@ -302,10 +315,10 @@ def run_cpu_baseline(w, args, mode_name, cached=False):
     what = ("oracle filter-trie walk" if mode_name == "trie" else
             "literal TenantRouteMatcher.matchAll restatement, one call per topic (production shape)")
     res = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": "%s: %d topics (%s) against all %d routes; %s, std::thread x %d; median of 5 passes of >= 1 s (%.3f s per "
+           "sample": "%s: %d topics (%s) against all %d routes; %s, std::thread x %d; median of %d passes of >= 1 s (%.3f s per "
                      "batch, spread %.3f-%.3f) = %.0f core-seconds per batch%s"
                      % (w.config, n, "the whole batch" if n == w.n_topics else "uniform random sample without replacement", len(kv), what, cores,
-                        dt, min(passes), max(passes), dt * cores,
+                        len(passes), dt, min(passes), max(passes), dt * cores,
                         ("; a (tenant, topic) result cache in front: %d distinct pairs matched, %d repeats served as lookups" % (n_unique, n - n_unique)) if cached else "")}
     return res, stats, n, float(poff[-1] - poff[0]) if not cached else None
 
@@ -461,10 +474,11 @@ def main():
                               "note": "C++ restatement of the Java reference, not the JVM (no JDK in the image)"}, "cpu_baseline": base,
                               "e2e": {"value": v, "unit": "filters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
             return
-        base, _, n, _ = run_cpu_baseline(w, args, "reference")
-        cached, _, _, _ = run_cpu_baseline(w, args, "reference", cached=True)
+        # a step = one pass of the bounded sample (100k topics: seconds per pass on the box's cores); K timed, W untimed
+        base, _, n, _ = run_cpu_baseline(w, args, "reference", n_passes=args.steps, n_warm=args.warmup)
+        cached, _, _, _ = run_cpu_baseline(w, args, "reference", cached=True, n_passes=min(args.steps, 5))
         v = base["value"]
-        line = {"metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 5, "warmup": 1,
+        line = {"metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8/u32 (byte and integer work)", "data": "synthetic", "impl": "reference",
                 "config": {"workload": workload_name(args, w), "note": "C++ restatement of the Java reference, not the JVM (no JDK in the image)"},
