@@ -80,6 +80,48 @@ struct PinBuf {
     }
 };
 
+// Upload of a large PAGEABLE host array (the 2.3 GB record array of a 10M-filter index): cudaMemcpy stages such a copy through
+// the driver's own bounce buffer on one thread; here several threads each own a pinned bounce buffer and a stream and take
+// 8 MB pieces in turn (memcpy into the buffer, async DMA, wait), so the host-side copies run in parallel and overlap the DMA
+// of the other threads. BFQ_UPLOAD=plain falls back to one cudaMemcpy (experiment switch). Small arrays go the plain way.
+cudaError_t upload_pageable(void* dst, const void* src, size_t bytes, int device) {
+    constexpr size_t PIECE = 8u << 20;
+    static const bool plain = [] {
+        const char* e = getenv("BFQ_UPLOAD");
+        return e && strcmp(e, "plain") == 0;
+    }();
+    if (bytes == 0) return cudaSuccess;
+    if (plain || bytes < 4 * PIECE) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    const unsigned nthreads = (unsigned) std::min<size_t>(8, (bytes + PIECE - 1) / PIECE);
+    std::atomic<size_t> next{0};
+    std::atomic<int> first_error{(int) cudaSuccess};
+    auto worker = [&]() {
+        cudaError_t e = cudaSetDevice(device);
+        void* bounce = nullptr;
+        cudaStream_t st = nullptr;
+        if (e == cudaSuccess) e = cudaMallocHost(&bounce, PIECE);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        while (e == cudaSuccess && first_error.load() == (int) cudaSuccess) {
+            const size_t at = next.fetch_add(PIECE);
+            if (at >= bytes) break;
+            const size_t len = std::min(PIECE, bytes - at);
+            memcpy(bounce, (const uint8_t*) src + at, len);
+            e = cudaMemcpyAsync((uint8_t*) dst + at, bounce, len, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (e != cudaSuccess) {
+            int expected = (int) cudaSuccess;
+            first_error.compare_exchange_strong(expected, (int) e);
+        }
+        if (st) cudaStreamDestroy(st);
+        if (bounce) cudaFreeHost(bounce);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+    return (cudaError_t) first_error.load();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ snapshots
@@ -856,13 +898,24 @@ void publish(bfq_index* h, std::shared_ptr<Snapshot> sn) {
 // every tenant rebuilt on all host cores, everything uploaded: bfq_index_load, the first commit, and whenever the delta
 // path cannot be used
 int32_t commit_full(bfq_index* h) {
+    const bool trace = getenv("BFQ_COMMIT_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bfq full commit] %-38s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     h->staging.merge_all();
-    const KVBlob kv = h->staging.concat();
+    lap("merge staged deltas");
+    std::vector<const KVBlob*> parts;   // the staged per-tenant blobs themselves: no concatenated copy of the KV
+    for (auto& kvp : h->staging.tenants()) parts.push_back(kvp.second.base.get());
     auto sn = std::make_shared<Snapshot>();
     sn->device = h->device;
     FlatIndex& flat = sn->flat;
     std::string err;
-    if (!build_flat_index(kv, &flat, &err)) return fail(BFQ_E_INVALID, err);
+    if (!build_flat_index_parts(parts, &flat, &err)) return fail(BFQ_E_INVALID, err);
+    lap("build (host, all cores)");
     CUDA_TRY(sn->d_slots.reserve(flat.slots.size()));
     CUDA_TRY(sn->d_tags.reserve(flat.tags.size()));
     CUDA_TRY(sn->d_roots.reserve(std::max<size_t>(flat.roots.size(), 1)));
@@ -870,15 +923,16 @@ int32_t commit_full(bfq_index* h) {
     CUDA_TRY(sn->d_rkind.reserve(std::max<size_t>(flat.rkind.size(), 1)));
     CUDA_TRY(sn->d_pfxP.reserve(flat.pfx_persistent.size()));
     CUDA_TRY(sn->d_pfxG.reserve(flat.pfx_group.size()));
-    CUDA_TRY(cudaMemcpy(sn->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    CUDA_TRY(upload_pageable(sn->d_slots.p, flat.slots.data(), flat.slots.size() * sizeof(Slot), h->device));
     CUDA_TRY(cudaMemcpy(sn->d_tags.p, flat.tags.data(), flat.tags.size(), cudaMemcpyHostToDevice));
     if (!flat.roots.empty())
         CUDA_TRY(cudaMemcpy(sn->d_roots.p, flat.roots.data(), flat.roots.size() * sizeof(Slot), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(sn->d_segs.p, flat.segs.data(), flat.segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!flat.rkind.empty())
         CUDA_TRY(cudaMemcpy(sn->d_rkind.p, flat.rkind.data(), flat.rkind.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(sn->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(sn->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(upload_pageable(sn->d_pfxP.p, flat.pfx_persistent.data(), flat.pfx_persistent.size() * sizeof(uint32_t), h->device));
+    CUDA_TRY(upload_pageable(sn->d_pfxG.p, flat.pfx_group.data(), flat.pfx_group.size() * sizeof(uint32_t), h->device));
+    lap("device allocations + upload");
     // per-tenant host side: the staged blobs are shared (no second copy of the KV), the route kinds are sliced
     sn->th.resize(flat.tenants.size());
     {
@@ -905,9 +959,11 @@ int32_t commit_full(bfq_index* h) {
     flat.pfx_persistent.shrink_to_fit();
     flat.pfx_group.clear();
     flat.pfx_group.shrink_to_fit();
+    lap("host bookkeeping, release of the image");
     set_l2_window(h, sn.get());
     h->staging.clear_bulk_changed();
     publish(h, std::move(sn));
+    lap("publish (drops the old snapshot)");
     return BFQ_OK;
 }
 
@@ -1248,11 +1304,49 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
     if (!st.load(keys, key_off, vals, val_off, n, &err)) return fail(BFQ_E_INVALID, err);
-    const KVBlob snapshot = st.concat();
     const auto t1 = std::chrono::steady_clock::now();
+    // the production path: straight from the staged per-tenant blobs
+    std::vector<const KVBlob*> parts;
+    for (auto& kvp : st.tenants()) parts.push_back(kvp.second.base.get());
     FlatIndex flat;
-    if (!build_flat_index(snapshot, &flat, &err)) return fail(BFQ_E_INVALID, err);
+    if (!build_flat_index_parts(parts, &flat, &err)) return fail(BFQ_E_INVALID, err);
     const auto t2 = std::chrono::steady_clock::now();
+    // stats[16]: a checksum of everything the build hands to the device (records, tags, roots, segments, per-rank arrays):
+    // two builds of the same KV are the same image (tests compare the sorted-order and the hash-table trie construction);
+    // stats[17]: 1 if the build from ONE concatenated blob (boundary scan) gives the same image as the per-tenant one
+    auto image_sum_of = [](const FlatIndex& f) {
+        uint64_t image_sum = 0;
+        auto fold = [&](const void* p, size_t bytes) {
+            const uint8_t* b = (const uint8_t*) p;
+            uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+            size_t i = 0;
+            for (; i + 32 <= bytes; i += 32)
+                for (int k = 0; k < 4; k++) {
+                    uint64_t w;
+                    memcpy(&w, b + i + 8 * k, 8);
+                    h[k] = (h[k] ^ w) * 0x100000001B3ull + (h[k] >> 29);
+                }
+            for (; i < bytes; i++) h[0] = (h[0] ^ b[i]) * 0x100000001B3ull;
+            image_sum = fmix64(image_sum ^ fmix64(h[0] ^ fmix64(h[1] ^ fmix64(h[2] ^ fmix64(h[3] ^ bytes)))));
+        };
+        fold(f.slots.data(), (size_t) f.n_slots * sizeof(Slot));
+        fold(f.tags.data(), f.tags.size());
+        fold(f.roots.data(), f.roots.size() * sizeof(Slot));
+        fold(f.segs.data(), f.segs.size() * sizeof(uint32_t));
+        fold(f.rkind.data(), f.rkind.size());
+        fold(f.pfx_persistent.data(), f.pfx_persistent.size() * sizeof(uint32_t));
+        fold(f.pfx_group.data(), f.pfx_group.size() * sizeof(uint32_t));
+        return image_sum;
+    };
+    uint64_t image_sum = 0;
+    int64_t same_as_concat = -1;
+    if (n_stats > 16) image_sum = image_sum_of(flat);
+    if (n_stats > 17) {
+        const KVBlob snapshot = st.concat();
+        FlatIndex flat2;
+        if (!build_flat_index(snapshot, &flat2, &err)) return fail(BFQ_E_INVALID, err);
+        same_as_concat = image_sum_of(flat2) == image_sum && flat2.n_nodes == flat.n_nodes && flat2.tenants.size() == flat.tenants.size();
+    }
     // self-check: every placed node is found again from its parent's record the way the kernels look it up
     {
         EdgeTable t;
@@ -1291,6 +1385,8 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     for (int32_t i = 9; i < n_stats && i < 9 + 5; i++) stats[i] = flat.child_hist[i - 9];
     if (n_stats > 14) stats[14] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();   // staging
     if (n_stats > 15) stats[15] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();   // flatten
+    if (n_stats > 16) stats[16] = (int64_t) image_sum;
+    if (n_stats > 17) stats[17] = same_as_concat;
     return BFQ_OK;
 }
 
@@ -1403,6 +1499,13 @@ int32_t bfq_match(bfq_index* h, const uint8_t* tenants, const int64_t* tenant_of
     // four sub-batches: eight were measured slower (2.45 ms vs 2.1 ms per 1M C4 topics): a 125k-topic sub-batch is less than one
     // wave of tier-0 lanes, its kernel takes as long as a 250k one
     int C = n >= (1 << 17) ? 4 : 1;
+    {
+        static const int forced = [] {   // experiment switch BFQ_SUBBATCHES
+            const char* e = getenv("BFQ_SUBBATCHES");
+            return e ? std::min(std::max(atoi(e), 1), (int) MAX_CHUNKS) : 0;
+        }();
+        if (forced > 0 && n >= (1 << 17)) C = forced;
+    }
     CoreOut co;
     int64_t rbase = 0, tbase = 0;
     double kernel_ms = -1;

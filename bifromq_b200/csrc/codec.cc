@@ -43,7 +43,8 @@ bool decode_route_key(sv k, DecodedKey* out) {
         size_t nul = r.find('\0');
         sv id = r.substr(0, nul);
         out->kind = (id.size() == 1 && id[0] == '1') ? KIND_PERSISTENT : KIND_NORMAL;
-        if (out->kind == KIND_NORMAL && !id.empty()) {
+        const bool one_digit = id.size() == 1 && id[0] >= '0' && id[0] <= '9';   // the usual spelling: decided above
+        if (out->kind == KIND_NORMAL && !id.empty() && !one_digit) {
             // tolerate "+1" / "01" spellings Integer.parseInt would accept
             char* end = nullptr;
             std::string tmp(id);

@@ -76,6 +76,8 @@ struct FlatIndex {
 
 // Build the flat index from a sorted KV snapshot. Returns false and sets *err on undecodable input.
 bool build_flat_index(const KVBlob& kv, FlatIndex* out, std::string* err);
+// The same from per-tenant blobs (one tenant each, in key order, empty ones skipped): what bfq_index_commit's full build uses.
+bool build_flat_index_parts(const std::vector<const KVBlob*>& parts, FlatIndex* out, std::string* err);
 
 // Host staging area behind bfq_index_load / bfq_index_apply / bfq_index_commit, kept PER TENANT (tenants are independent key
 // ranges: a SUB / UNSUB touches one tenant, and bfq_index_commit's delta path rebuilds only the touched ones). A tenant's

@@ -286,3 +286,86 @@ def test_retain_key_codec_matches_the_oracle():
             f[-1] = "#"
         tf = "/".join(f)
         assert schema.retain_key_prefix(tenant, tf) == O.retain_key_prefix(tenant, tf), tf
+
+
+_BUILDER_AB_CHILD = r"""
+import sys, json, random
+import numpy as np
+sys.path.insert(0, %(root)r)
+from bifromq_b200 import _native as N, schema
+rng = random.Random(20260923)
+LONG = "L" * 24                                    # levels longer than one 24-byte token share chunk nodes
+names = ["", "a", "b", "ab", "a\x01", "\x01", "\x02x", "+", "zz", LONG + "p", LONG + "q", LONG + LONG + "r", LONG]
+pairs = {}
+for tenant in ("t", "t0", "u"):
+    for _ in range(1500):
+        depth = rng.randint(1, 5)
+        levels = [rng.choice(names) for _ in range(depth)]
+        if rng.random() < 0.25:
+            levels.append("#")
+        tf = "/".join(levels)
+        if tf.startswith("$") or tf == "":
+            continue
+        for _ in range(rng.randint(1, 4)):
+            kind = rng.random()
+            if kind < 0.15:
+                key = schema.route_key(tenant, "$share/g%%d/%%s" %% (rng.randint(0, 3), tf), "")
+                val = b"\x0a\x06\x0a\x02r1\x10\x01"
+            else:
+                # receiver urls starting with control bytes after the bucket byte: a parent's OWN keys then interleave with
+                # the subtree of its empty-named child (the bucket-byte quirk), the revisit the sorted builder must survive
+                url = schema.receiver_url(rng.randint(0, 1), "r%%d" %% rng.randint(0, 400), rng.choice(["d", "\x01d", "e"]))
+                key = schema.route_key(tenant, tf, url)
+                val = schema.incarnation_bytes(1)
+            pairs[key] = val
+pairs = sorted(pairs.items())
+keys = b"".join(k for k, _ in pairs); vals = b"".join(v for _, v in pairs)
+koff = np.zeros(len(pairs) + 1, np.int64); voff = np.zeros(len(pairs) + 1, np.int64)
+koff[1:] = np.cumsum([len(k) for k, _ in pairs]); voff[1:] = np.cumsum([len(v) for _, v in pairs])
+k = np.frombuffer(keys, np.uint8).copy(); v = np.frombuffer(vals, np.uint8).copy()
+st = np.zeros(18, np.int64)
+rc = N.lib.bfq_host_build_stats(k.ctypes.data, koff.ctypes.data, v.ctypes.data, voff.ctypes.data, len(pairs), st.ctypes.data, 18)
+print(json.dumps({"rc": int(rc), "stats": st[:14].tolist(), "sum": int(st[16]), "same_as_concat": int(st[17]), "n": len(pairs)}))
+"""
+
+
+def test_sorted_order_trie_construction_builds_the_same_image_as_the_hash_table_one():
+    """index_builder.cc builds a tenant's trie from the KV order alone (a child can only be its parent's most recent child) and
+    keeps the hash-table construction as the checked fallback (BFQ_BUILDER=hash forces it). Both must produce the same image,
+    byte for byte (stats[16] = checksum of records, tags, roots, segments and per-rank arrays) — on a key set with empty
+    levels, control bytes, '+', '#', shared-subscription keys and long levels sharing 24-byte chunks, where a parent's own keys
+    interleave with its empty-named child's subtree (the reference's bucket-byte quirk)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("sorted", "hash"):
+        env = dict(os.environ)
+        env.pop("BFQ_BUILDER", None)
+        if mode == "hash":
+            env["BFQ_BUILDER"] = "hash"
+        r = subprocess.run([sys.executable, "-c", _BUILDER_AB_CHILD % {"root": root}], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out[mode]["rc"] == 0 and out[mode]["n"] > 5000
+        # the full build straight from the staged per-tenant blobs (what bfq_index_commit runs) == the build from one
+        # concatenated blob with a tenant-boundary scan
+        assert out[mode]["same_as_concat"] == 1
+    assert out["sorted"]["stats"] == out["hash"]["stats"]
+    assert out["sorted"]["sum"] == out["hash"]["sum"] != 0
+    assert out["sorted"]["stats"][6] > 0 and out["sorted"]["stats"][7] > 0   # multi-segment filters and long-token chunks occur
+
+
+def test_staging_delta_merge_equals_a_sorted_map(tmp_path):
+    """Staging::merge_tenant (the host half of bfq_index_apply + bfq_index_commit's delta path) copies the runs of base keys
+    between two delta keys in bulk; tests/native/staging_merge_test.cc drives 200 rounds of random load / upsert / erase /
+    merge over several tenants (new and vanishing ones included) against a std::map."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "bifromq_b200", "csrc")
+    exe = str(tmp_path / "staging_merge_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + csrc, os.path.join(root, "tests", "native", "staging_merge_test.cc"),
+                           os.path.join(csrc, "index_builder.cc"), os.path.join(csrc, "codec.cc"), "-lpthread", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "merge ok" in out.stdout, out.stdout + out.stderr
