@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-replicate-hot", action="store_true", help="strong scaling: pure hash placement, no replicas of hot tenants")
     ap.add_argument("--retain-limit", type=int, default=10, help="C5: ids returned per filter (RetainMessageMatchLimit default 10; -1 = unlimited)")
     ap.add_argument("--exchange", default="ranges", choices=["ranges", "counts", "none"], help="N > 1: what the timed step all-gathers")
+    ap.add_argument("--exchange-lag", type=int, default=2, help="N > 1: matches enqueued ahead of the exchange being issued (pipeline depth)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="topics in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-pfanout", type=int, default=2 ** 31 - 1, help="Setting.MaxPersistentFanout (reference default INT_MAX)")
@@ -563,16 +564,23 @@ def main():
         else:
             res.release()
 
-    xs = torch.cuda.Stream(dev) if xch is not None else None   # the exchange runs on its own stream, one step behind the matching
-    pipe = {"pending": None, "gathered": None}
+    xs = torch.cuda.Stream(dev) if xch is not None else None   # the exchange runs on its own stream, AHEAD steps behind the matching
+    pipe = {"pending": [], "gathered": None}
+    AHEAD = max(1, args.exchange_lag)
 
     def pump(res_new, record):
-        """N > 1, software-pipelined: the match of step i is enqueued (no host sync) BEFORE the exchange of step i - 1 is issued,
-        so the exchange's one host synchronisation and its NCCL traffic overlap the next step's kernels. The exchange
-        (SURVEY.md 8e): every rank ends with every rank's per-topic counts (and ranges) — bfq_exchange_gather, NCCL inside
-        the library."""
-        pend = pipe["pending"]
-        if pend is not None:
+        """N > 1, software-pipelined: the exchange of step i - AHEAD is issued after the matches of steps i - AHEAD + 1 .. i have
+        been enqueued (no host sync in a match). The exchange has one host synchronisation (the ranks' range counts size the
+        payload all-gather) and its kernels — NCCL's need most of an SM each — only get SM room between two persistent
+        tier-0 grids: with ONE match queued behind it (round 2's first version) the device ran dry while the host sat in that
+        synchronisation, so step time was match + exchange; with two queued the exchange of step i - 2 slides in between
+        tier 0 of step i - 1 and tier 0 of step i while the queue stays fed. The exchange: every rank ends
+        with every rank's per-topic counts (and ranges) — bfq_exchange_gather, NCCL inside the library. res_new = None drains
+        one step."""
+        if res_new is not None:
+            pipe["pending"].append(res_new)
+        if pipe["pending"] and (res_new is None or len(pipe["pending"]) > AHEAD):
+            pend = pipe["pending"].pop(0)
             pend.wait()                      # waits for THAT match only (an event behind it), then reads its counters
             g = xch.gather(pend, ranges=args.exchange == "ranges", stream=xs.cuda_stream)
             gathered_info.update(topics=g.n_topics_total, ranges=g.n_ranges_total, bytes_received=g.bytes_received)
@@ -581,8 +589,11 @@ def main():
             pipe["gathered"] = pend
             if record:
                 kernel_ms.append(pend.tier0_ms)
-        pipe["pending"] = res_new
         return (res_new.n_launches + 4) if (res_new is not None and record) else 0
+
+    def drain(record):
+        while pipe["pending"]:
+            pump(None, record)
 
     inflight = []
     for _ in range(max(args.warmup, 3) + DEPTH):   # warm-up (also creates the workspaces the timed loop will reuse)
@@ -595,7 +606,7 @@ def main():
     while inflight:
         retire(inflight.pop(0), record=False)
     if xch is not None:
-        pump(None, False)
+        drain(False)
         xs.synchronize()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -610,7 +621,7 @@ def main():
         t_begin.record(stream)
         for i in range(args.steps):
             launches += pump(enqueue_device(), True)
-        pump(None, True)
+        drain(True)
         t_end.record(xs)
         xs.synchronize()
         torch.cuda.synchronize(dev)
@@ -698,7 +709,7 @@ def main():
                            "order": "inside the timed region: duplicate (tenant, topic) pairs are found with a device hash table and answered from their "
                                     "first occurrence (%d of %d topics distinct), the distinct ones are matched in locality order (own counting sort)" % (n_distinct, n),
                            "pipelining": ("steps are enqueued without host synchronisation (bfq_match_device_async), %d in flight; timed per step with CUDA events on the launching stream" % DEPTH) if xch is None else
-                                         "software pipeline of depth 2: the match of step i is enqueued before the exchange of step i-1 (own stream) is issued; the K steps are timed as a whole with CUDA events (first match -> last exchange complete); no L2 flush (index >> L2)",
+                                         ("software pipeline: the matches of steps i-%d+1 .. i are enqueued (no host sync) before the exchange of step i-%d (own stream, one host sync) is issued; the K steps are timed as a whole with CUDA events (first match -> last exchange complete); no L2 flush (index >> L2)" % (AHEAD, AHEAD)),
                            "host": ("rank pinned to NUMA node %d of its GPU (%d cpus) for the GPU legs" % (numa["node"], numa["cpus"])) if numa
                                    else "no NUMA pinning (topology not exposed or single node)",
                            "gen_s": round(t_gen, 1), "build_s": round(t_build, 1)},
