@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--no-replicate-hot", action="store_true", help="strong scaling: pure hash placement, no replicas of hot tenants")
     ap.add_argument("--retain-limit", type=int, default=10, help="C5: ids returned per filter (RetainMessageMatchLimit default 10; -1 = unlimited)")
     ap.add_argument("--exchange", default="ranges", choices=["ranges", "counts", "none"], help="N > 1: what the timed step all-gathers")
-    ap.add_argument("--exchange-lag", type=int, default=2, help="N > 1: matches enqueued ahead of the exchange being issued (pipeline depth)")
+    ap.add_argument("--exchange-lag", type=int, default=1,
+                    help="N > 1: matches enqueued ahead of the exchange being issued (2 was measured equal at N = 2: 0.604 vs 0.597 ms per step)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="topics in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-pfanout", type=int, default=2 ** 31 - 1, help="Setting.MaxPersistentFanout (reference default INT_MAX)")
@@ -570,13 +571,12 @@ def main():
 
     def pump(res_new, record):
         """N > 1, software-pipelined: the exchange of step i - AHEAD is issued after the matches of steps i - AHEAD + 1 .. i have
-        been enqueued (no host sync in a match). The exchange has one host synchronisation (the ranks' range counts size the
-        payload all-gather) and its kernels — NCCL's need most of an SM each — only get SM room between two persistent
-        tier-0 grids: with ONE match queued behind it (round 2's first version) the device ran dry while the host sat in that
-        synchronisation, so step time was match + exchange; with two queued the exchange of step i - 2 slides in between
-        tier 0 of step i - 1 and tier 0 of step i while the queue stays fed. The exchange: every rank ends
-        with every rank's per-topic counts (and ranges) — bfq_exchange_gather, NCCL inside the library. res_new = None drains
-        one step."""
+        been enqueued (no host sync in a match), so the exchange's one host synchronisation (the ranks' range counts size the
+        payload all-gather) and its NCCL traffic overlap the next step's kernels. AHEAD = 1 by default; 2 (one more match
+        queued while the host sits in that synchronisation) was measured equal at N = 2 — what the exchange adds to a step is
+        device work (compaction of the sparse ranges + the all-gather), not a starved queue. The exchange: every
+        rank ends with every rank's per-topic counts (and ranges) — bfq_exchange_gather, NCCL inside the library.
+        res_new = None drains one step."""
         if res_new is not None:
             pipe["pending"].append(res_new)
         if pipe["pending"] and (res_new is None or len(pipe["pending"]) > AHEAD):
