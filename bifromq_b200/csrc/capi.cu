@@ -1323,6 +1323,36 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
         if (!build_flat_index(snapshot, &flat2, &err)) return fail(BFQ_E_INVALID, err);
         same_as_concat = image_sum_of(flat2) == image_sum && flat2.n_nodes == flat.n_nodes && flat2.tenants.size() == flat.tenants.size();
     }
+    // stats[18]: tenants whose stand-alone image (build_tenant_image with the full build's bases — what a delta commit
+    // uploads for a touched tenant) equals their part of the full image byte for byte; -1 - index of the first that differs
+    int64_t tenant_images_equal = 0;
+    if (n_stats > 18) {
+        size_t ti = 0;
+        for (auto& kvp : st.tenants()) {
+            if (ti >= flat.tenants.size()) break;
+            const TenantMeta& m = flat.tenants[ti];
+            TenantImage img;
+            if (!build_tenant_image(*kvp.second.base, sv(m.tenant), m.ordinal, m.lo, m.region_base, m.seg_base, m.pp_base, m.pg_base, &img, &err))
+                return fail(BFQ_E_INVALID, err);
+            bool same = img.meta.big_edges == m.big_edges && img.meta.n_routes == m.n_routes;
+            if (same && m.big_edges == 0) {
+                same = img.meta.csr_slots == m.csr_slots && img.meta.seg_words == m.seg_words && img.meta.pp == m.pp && img.meta.pg == m.pg &&
+                       img.meta.tenant_nodes == m.tenant_nodes && img.meta.n_multi == m.n_multi &&
+                       memcmp(img.slots.data(), flat.slots.data() + m.region_base, (size_t) m.csr_slots * sizeof(Slot)) == 0 &&
+                       memcmp(&img.root, &flat.roots[m.ordinal], sizeof(Slot)) == 0 &&
+                       (m.seg_words == 0 || memcmp(img.segs.data(), flat.segs.data() + m.seg_base, (size_t) m.seg_words * 4) == 0) &&
+                       (m.n_routes == 0 || (memcmp(img.rkind.data(), flat.rkind.data() + m.lo, (size_t) m.n_routes) == 0 &&
+                                            memcmp(img.pfxP.data(), flat.pfx_persistent.data() + m.lo, (size_t) m.n_routes * 4) == 0 &&
+                                            memcmp(img.pfxG.data(), flat.pfx_group.data() + m.lo, (size_t) m.n_routes * 4) == 0));
+            }
+            if (!same) {
+                tenant_images_equal = -1 - (int64_t) ti;
+                break;
+            }
+            tenant_images_equal++;
+            ti++;
+        }
+    }
     // self-check: every placed node is found again from its parent's record the way the kernels look it up
     {
         EdgeTable t;
@@ -1363,6 +1393,7 @@ int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const 
     if (n_stats > 15) stats[15] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();   // flatten
     if (n_stats > 16) stats[16] = (int64_t) image_sum;
     if (n_stats > 17) stats[17] = same_as_concat;
+    if (n_stats > 18) stats[18] = tenant_images_equal;
     return BFQ_OK;
 }
 

@@ -1021,7 +1021,22 @@ bool build_tenant_image(const KVBlob& tkv, sv tenant, uint32_t ordinal, int64_t 
     tb.pp_base = pp_base;
     tb.pg_base = pg_base;
     out->slots.resize((size_t) tb.csr_slots);
-    fill_empty_slots(out->slots.data(), out->slots.size());
+    {   // uninitialised; filled (first-touched) by several threads when the tenant is large
+        const size_t total = out->slots.size(), piece = 1u << 16;
+        const unsigned nt = total >= (1u << 20) ? std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u) : 1u;
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            while (true) {
+                const size_t at = next.fetch_add(piece);
+                if (at >= total) break;
+                fill_empty_slots(out->slots.data() + at, std::min(piece, total - at));
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
     out->segs.assign((size_t) tb.seg_words, 0);
     tb.slots = out->slots.data();
     tb.slot_origin = region_base;

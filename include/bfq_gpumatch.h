@@ -104,7 +104,8 @@ int32_t bfq_index_last_kernel_ms(bfq_index* h, double* ms);
  * stats[0..7] = routes, tenants, trie nodes, hash slots, max nodes per depth, max nodes per tenant,
  * multi-segment filters, long-token chunks, 8 = tag-table blocks that overflowed, 9..13 = nodes with 0/1/2/3/>=4
  * exact children, 14 = staging microseconds, 15 = flatten microseconds, 16 = a checksum of the whole image the build would
- * upload, 17 = 1 if building from one concatenated KV blob gives that same image (used by CPU tests and to time the build). */
+ * upload, 17 = 1 if building from one concatenated KV blob gives that same image, 18 = tenants whose stand-alone image (what a delta
+ * commit builds for a touched tenant) equals their part of the full image (used by CPU tests and to time the build). */
 int32_t bfq_host_build_stats(const uint8_t* keys, const int64_t* key_off, const uint8_t* vals, const int64_t* val_off,
                              int64_t n, int64_t* stats, int32_t n_stats);
 

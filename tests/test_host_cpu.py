@@ -323,9 +323,10 @@ keys = b"".join(k for k, _ in pairs); vals = b"".join(v for _, v in pairs)
 koff = np.zeros(len(pairs) + 1, np.int64); voff = np.zeros(len(pairs) + 1, np.int64)
 koff[1:] = np.cumsum([len(k) for k, _ in pairs]); voff[1:] = np.cumsum([len(v) for _, v in pairs])
 k = np.frombuffer(keys, np.uint8).copy(); v = np.frombuffer(vals, np.uint8).copy()
-st = np.zeros(18, np.int64)
-rc = N.lib.bfq_host_build_stats(k.ctypes.data, koff.ctypes.data, v.ctypes.data, voff.ctypes.data, len(pairs), st.ctypes.data, 18)
-print(json.dumps({"rc": int(rc), "stats": st[:14].tolist(), "sum": int(st[16]), "same_as_concat": int(st[17]), "n": len(pairs)}))
+st = np.zeros(19, np.int64)
+rc = N.lib.bfq_host_build_stats(k.ctypes.data, koff.ctypes.data, v.ctypes.data, voff.ctypes.data, len(pairs), st.ctypes.data, 19)
+print(json.dumps({"rc": int(rc), "stats": st[:14].tolist(), "sum": int(st[16]), "same_as_concat": int(st[17]),
+                  "tenant_images_equal": int(st[18]), "n": len(pairs)}))
 """
 
 
@@ -352,6 +353,9 @@ def test_sorted_order_trie_construction_builds_the_same_image_as_the_hash_table_
         # the full build straight from the staged per-tenant blobs (what bfq_index_commit runs) == the build from one
         # concatenated blob with a tenant-boundary scan
         assert out[mode]["same_as_concat"] == 1
+        # the stand-alone image of every tenant (what a delta commit builds for a touched tenant, build_tenant_image) == its
+        # part of the full image
+        assert out[mode]["tenant_images_equal"] == out[mode]["stats"][1] == 3
     assert out["sorted"]["stats"] == out["hash"]["stats"]
     assert out["sorted"]["sum"] == out["hash"]["sum"] != 0
     assert out["sorted"]["stats"][6] > 0 and out["sorted"]["stats"][7] > 0   # multi-segment filters and long-token chunks occur
