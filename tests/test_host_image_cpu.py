@@ -190,3 +190,34 @@ def test_image_walk_after_staged_deltas_equals_oracle_of_the_final_kv(walker, tm
     assert off.tolist() == want.offsets.tolist() and ranks.tolist() == want.ranks.tolist()
     assert np.diff(off)[-2] == 1 and np.diff(off)[-1] == 0            # "#" matches everything but a '$' topic
     assert all(np.diff(off)[i] == 0 for i, t in enumerate(tt) if t == 1)   # nothing left under the vanished tenant
+
+
+@pytest.mark.parametrize("config,scale", [("C3", 0.02), ("C4", 0.02), ("C2", 0.05)])
+def test_image_walk_baseline_workloads_equal_oracle(walker, tmp_path, config, scale):
+    """the BASELINE generators (bench.py's own inputs) at a small scale: tens of thousands of filters, the whole topic batch"""
+    from bifromq_b200.workload import Workload
+    w = Workload(config, scale=scale)
+    n = min(w.n_topics, 20000)
+    tmp = str(tmp_path)
+    np.ascontiguousarray(w.keys).tofile(os.path.join(tmp, "keys.bin"))
+    np.ascontiguousarray(w.vals).tofile(os.path.join(tmp, "vals.bin"))
+    np.ascontiguousarray(w.key_off, dtype=np.int64).tofile(os.path.join(tmp, "koff.bin"))
+    np.ascontiguousarray(w.val_off, dtype=np.int64).tofile(os.path.join(tmp, "voff.bin"))
+    tb, toff = O.blob(w.tenants)
+    np.ascontiguousarray(tb).tofile(os.path.join(tmp, "tenants.bin"))
+    np.ascontiguousarray(toff, dtype=np.int64).tofile(os.path.join(tmp, "tenant_off.bin"))
+    poff = np.ascontiguousarray(w.topic_off[:n + 1], dtype=np.int64)
+    np.ascontiguousarray(w.topics[:int(poff[-1])]).tofile(os.path.join(tmp, "topics.bin"))
+    poff.tofile(os.path.join(tmp, "topic_off.bin"))
+    tt = np.ascontiguousarray(w.topic_tenant[:n], dtype=np.int32)
+    tt.tofile(os.path.join(tmp, "topic_tenant.bin"))
+    r = subprocess.run([walker, tmp], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    off = np.fromfile(os.path.join(tmp, "out_off.bin"), np.int64)
+    ranks = np.fromfile(os.path.join(tmp, "out_ranks.bin"), np.int64)
+    kv = O.KV()
+    kv.load(w.keys, w.key_off, w.vals, w.val_off)
+    kv.freeze()
+    want = kv.match_blobs(tb, toff, w.topics, poff, tt, n, INT_MAX, INT_MAX, O.MODE_TRIE, False, os.cpu_count() or 1)
+    assert np.array_equal(off, want.offsets) and np.array_equal(ranks, want.ranks)
+    assert len(ranks) > n // 4
