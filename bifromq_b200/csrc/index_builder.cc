@@ -432,6 +432,169 @@ bool insert_tenant_keys(const KVBlob& kv, TenantBuild& tb, std::vector<uint32_t>
     return true;
 }
 
+// The first level of the filter in a route key (the bytes up to the first NUL of the escaped filter), or false if undecodable.
+bool first_level_of_key(sv key, sv* level) {
+    DecodedKey d;
+    if (!decode_route_key(key, &d)) return false;
+    const size_t nul = d.escaped_filter.find('\0');
+    *level = nul == sv::npos ? d.escaped_filter : d.escaped_filter.substr(0, nul);
+    return true;
+}
+
+// Sorted-order construction of a LARGE tenant on several threads. The sorted key range is cut where the filter's first EDGE from
+// the root changes (the first level, or its first 24-byte chunk if it is longer than one token): the sub-tries under different
+// root children share nothing but the root, so every piece is built on its own (same
+// code, its own root), and the pieces are concatenated — piece after piece, each in its creation order — which is exactly the
+// numbering the one-thread construction gives (it creates the nodes in key order too), hence the same image
+// (tests compare it with the hash-table construction byte for byte). Returns 1 = built, 0 = not applicable or order
+// violation (the caller falls back to one thread), and leaves tb.err set on undecodable keys like the one-thread path.
+int insert_tenant_keys_parallel(const KVBlob& kv, TenantBuild& tb, std::vector<uint32_t>& depth_count, unsigned threads) {
+    const int64_t lo = tb.lo, hi = tb.hi, nkeys = hi - lo;
+    // ---- cut points
+    std::vector<int64_t> cuts{lo};
+    for (unsigned c = 1; c < threads; c++) {
+        int64_t r = lo + nkeys * (int64_t) c / (int64_t) threads;
+        if (r <= cuts.back()) continue;
+        sv prev, cur;
+        if (!first_level_of_key(kv.key(r - 1), &prev)) return 0;
+        while (r < hi) {
+            if (!first_level_of_key(kv.key(r), &cur)) return 0;
+            const int cmp = cur.compare(prev);
+            if (cmp < 0) return 0;   // not in level-wise order: the one-thread path decides what to do with it
+            // same child of the root? equal levels, or two levels longer than one token that share their first 24-byte chunk
+            // (they hang off the same continuation node)
+            const bool same_edge = cmp == 0 || (prev.size() > TOKEN_BYTES && cur.size() > TOKEN_BYTES &&
+                                                prev.substr(0, TOKEN_BYTES) == cur.substr(0, TOKEN_BYTES));
+            if (!same_edge) break;
+            prev = cur;
+            r++;
+        }
+        if (r < hi && r > cuts.back()) cuts.push_back(r);
+    }
+    cuts.push_back(hi);
+    const size_t P = cuts.size() - 1;
+    if (P < 2) return 0;
+    // ---- the pieces, each with the tenant's own output arrays (ranks are absolute; the prefix counts are rebased below)
+    std::vector<TenantBuild> piece(P);
+    std::vector<std::vector<uint32_t>> piece_depth(P);
+    std::vector<char> piece_ok(P, 1);
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            while (true) {
+                const size_t i = next.fetch_add(1);
+                if (i >= P) break;
+                TenantBuild& pb = piece[i];
+                pb.kv = tb.kv;
+                pb.lo = cuts[i];
+                pb.hi = cuts[i + 1];
+                pb.rank_off = tb.rank_off;
+                pb.index_off = tb.index_off;
+                pb.rkind = tb.rkind;
+                pb.pfxP = tb.pfxP;
+                pb.pfxG = tb.pfxG;
+                pb.b = Builder(true);
+                piece_ok[i] = insert_tenant_keys(kv, pb, piece_depth[i]) ? 1 : 0;
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < std::min<size_t>(threads, P); t++) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    for (size_t i = 0; i < P; i++) {
+        if (!piece[i].err.empty()) {
+            tb.err = piece[i].err;
+            return 1;   // reported like the one-thread path does
+        }
+        if (!piece_ok[i]) return 0;
+    }
+    // ---- concatenate: node 0 = the root, then piece after piece without their own roots
+    std::vector<size_t> node_off(P + 1, 1), multi_off(P + 1, 0);
+    std::vector<uint32_t> pp_base(P + 1, 0), pg_base(P + 1, 0);
+    int64_t n_cont_total = 0;
+    for (size_t i = 0; i < P; i++) {
+        n_cont_total += piece[i].b.n_cont;
+        node_off[i + 1] = node_off[i] + piece[i].b.nodes.size() - 1;
+        multi_off[i + 1] = multi_off[i] + piece[i].b.multi_lists.size();
+        pp_base[i + 1] = pp_base[i] + piece[i].pp;
+        pg_base[i + 1] = pg_base[i] + piece[i].pg;
+    }
+    if (node_off[P] >= 0x7FFFFFF0ull) return 0;
+    Builder& b = tb.b;
+    b = Builder(true);
+    b.nodes.resize(node_off[P]);
+    b.multi_lists.resize(multi_off[P]);
+    BNode root;
+    root.root_ordinal = 0;
+    int plus_owner = -1, hash_owner = -1;
+    for (size_t i = 0; i < P; i++) {
+        const BNode& r = piece[i].b.nodes[0];
+        root.flags |= r.flags;
+        if (r.plus != NONE) {
+            if (plus_owner >= 0) return 0;   // cannot happen when the cuts are first-level boundaries
+            plus_owner = (int) i;
+        }
+        if (r.hash.total > 0) {
+            if (hash_owner >= 0) return 0;
+            hash_owner = (int) i;
+        }
+        if (r.own.total > 0) return 0;   // no filter has zero levels
+    }
+    auto map_node = [&](size_t i, uint32_t local) { return local == NONE ? NONE : local == 0 ? 0u : (uint32_t) (node_off[i] + local - 1); };
+    auto map_target = [&](size_t i, Target t) {
+        if (t.multi >= 0) t.multi += (int32_t) multi_off[i];
+        return t;
+    };
+    if (plus_owner >= 0) root.plus = map_node((size_t) plus_owner, piece[(size_t) plus_owner].b.nodes[0].plus);
+    if (hash_owner >= 0) root.hash = map_target((size_t) hash_owner, piece[(size_t) hash_owner].b.nodes[0].hash);
+    b.nodes[0] = root;
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            while (true) {
+                const size_t i = next.fetch_add(1);
+                if (i >= P) break;
+                Builder& pb = piece[i].b;
+                for (size_t l = 1; l < pb.nodes.size(); l++) {
+                    BNode nd = pb.nodes[l];
+                    nd.parent = map_node(i, nd.parent);
+                    nd.plus = map_node(i, nd.plus);
+                    nd.last_child = NONE;
+                    nd.own = map_target(i, nd.own);
+                    nd.hash = map_target(i, nd.hash);
+                    b.nodes[node_off[i] + l - 1] = nd;
+                }
+                for (size_t m = 0; m < pb.multi_lists.size(); m++) b.multi_lists[multi_off[i] + m] = std::move(pb.multi_lists[m]);
+                // prefix counts were counted from the piece's first key: rebase to the tenant's
+                if (pp_base[i] || pg_base[i])
+                    for (int64_t r = piece[i].lo; r < piece[i].hi; r++) {
+                        tb.pfxP[(size_t) (r + tb.index_off)] += pp_base[i];
+                        tb.pfxG[(size_t) (r + tb.index_off)] += pg_base[i];
+                    }
+                pb = Builder(true);   // release the piece's nodes here, on this thread
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < std::min<size_t>(threads, P); t++) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    if (getenv("BFQ_BUILD_TRACE"))
+        fprintf(stderr, "[bfq build] tenant of %lld routes inserted as %zu pieces (%zu nodes)\n", (long long) nkeys, P, b.nodes.size());
+    tb.pp = pp_base[P];
+    tb.pg = pg_base[P];
+    tb.tenant_nodes = 0;
+    depth_count.clear();
+    b.n_cont = n_cont_total;
+    for (size_t i = 0; i < P; i++) {
+        tb.tenant_nodes += piece[i].tenant_nodes;
+        if (piece_depth[i].size() > depth_count.size()) depth_count.resize(piece_depth[i].size(), 0);
+        for (size_t k = 0; k < piece_depth[i].size(); k++) depth_count[k] += piece_depth[i][k];
+    }
+    return 1;
+}
+
 // phase B: the tenant's trie (sorted-order construction; hash-table construction if the keys turn out not to be in level-wise
 // order, or when BFQ_BUILDER=hash asks for it — both give the same node numbering, hence the same image: tests compare them),
 // then the plan of the child arrays
@@ -440,11 +603,27 @@ void build_tenant(const KVBlob& kv, TenantBuild& tb) {
         const char* e = getenv("BFQ_BUILDER");
         return e && strcmp(e, "hash") == 0;
     }();
+    // a tenant of >= 2^18 routes is inserted on several threads (experiment / test switches: BFQ_INSERT_PARALLEL_MIN,
+    // BFQ_INSERT_THREADS)
+    static const int64_t par_min = [] {
+        const char* e = getenv("BFQ_INSERT_PARALLEL_MIN");
+        return e ? std::max<int64_t>(2, atoll(e)) : (int64_t) 1 << 18;
+    }();
+    static const unsigned par_threads = [] {
+        const char* e = getenv("BFQ_INSERT_THREADS");
+        return e ? (unsigned) std::min(std::max(atoi(e), 1), 64) : std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    }();
     std::vector<uint32_t> depth_count;
     bool done = false;
     if (!force_table) {
-        tb.b = Builder(true);
-        done = insert_tenant_keys(kv, tb, depth_count);
+        if (par_threads > 1 && tb.hi - tb.lo >= par_min) done = insert_tenant_keys_parallel(kv, tb, depth_count, par_threads) == 1;
+        if (!done) {
+            tb.b = Builder(true);
+            tb.tenant_nodes = 0;
+            tb.err.clear();
+            depth_count.clear();
+            done = insert_tenant_keys(kv, tb, depth_count);
+        }
     }
     if (!done) {
         tb.b = Builder(false);

@@ -341,11 +341,15 @@ def test_sorted_order_trie_construction_builds_the_same_image_as_the_hash_table_
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    for mode in ("sorted", "hash"):
+    for mode in ("sorted", "hash", "pieces"):
         env = dict(os.environ)
-        env.pop("BFQ_BUILDER", None)
+        for k in ("BFQ_BUILDER", "BFQ_INSERT_PARALLEL_MIN", "BFQ_INSERT_THREADS"):
+            env.pop(k, None)
         if mode == "hash":
             env["BFQ_BUILDER"] = "hash"
+        if mode == "pieces":   # the several-thread insertion of large tenants, forced onto these small ones: cut at first-level
+            env["BFQ_INSERT_PARALLEL_MIN"] = "2"   # boundaries (the empty first level, '+', control bytes among them), pieces
+            env["BFQ_INSERT_THREADS"] = "5"        # concatenated
         r = subprocess.run([sys.executable, "-c", _BUILDER_AB_CHILD % {"root": root}], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
@@ -356,8 +360,8 @@ def test_sorted_order_trie_construction_builds_the_same_image_as_the_hash_table_
         # the stand-alone image of every tenant (what a delta commit builds for a touched tenant, build_tenant_image) == its
         # part of the full image
         assert out[mode]["tenant_images_equal"] == out[mode]["stats"][1] == 3
-    assert out["sorted"]["stats"] == out["hash"]["stats"]
-    assert out["sorted"]["sum"] == out["hash"]["sum"] != 0
+    assert out["sorted"]["stats"] == out["hash"]["stats"] == out["pieces"]["stats"]
+    assert out["sorted"]["sum"] == out["hash"]["sum"] == out["pieces"]["sum"] != 0
     assert out["sorted"]["stats"][6] > 0 and out["sorted"]["stats"][7] > 0   # multi-segment filters and long-token chunks occur
 
 

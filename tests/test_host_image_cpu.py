@@ -36,7 +36,10 @@ def _blob(items):
     return b"".join(items), off
 
 
-def walk(walker, tmp, pairs, tenants, topics, tt, deltas=()):
+PIECES = {"BFQ_INSERT_PARALLEL_MIN": "2", "BFQ_INSERT_THREADS": "6"}   # force the several-thread insertion of large tenants
+
+
+def walk(walker, tmp, pairs, tenants, topics, tt, deltas=(), env=None):
     """pairs: the KV handed to load (sorted); deltas: [("put", key, value) | ("del", key)] staged on top, like bfq_index_apply"""
     os.makedirs(tmp, exist_ok=True)
     kb, ko = _blob([k for k, _ in pairs])
@@ -53,7 +56,7 @@ def walk(walker, tmp, pairs, tenants, topics, tt, deltas=()):
             k = d[1]
             v = d[2] if d[0] == "put" else b""
             f.write(struct.pack("<BI", 1 if d[0] == "put" else 2, len(k)) + k + struct.pack("<I", len(v)) + v)
-    r = subprocess.run([walker, tmp], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([walker, tmp], capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout + r.stderr
     return np.fromfile(os.path.join(tmp, "out_off.bin"), np.int64), np.fromfile(os.path.join(tmp, "out_ranks.bin"), np.int64), r.stdout
 
@@ -108,8 +111,8 @@ def random_pairs(schema, rng, n_filters, vocab, depth):
     return pairs, tenants, topics, tt
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
-def test_image_walk_random_small_vocab_equals_oracle(walker, tmp_path, seed):
+@pytest.mark.parametrize("seed,env", [(1, None), (2, None), (3, None), (4, PIECES), (5, PIECES)])
+def test_image_walk_random_small_vocab_equals_oracle(walker, tmp_path, seed, env):
     from bifromq_b200 import schema
     rng = random.Random(seed)
     pairs, tenants, topics, tt = random_pairs(schema, rng, 700, ["a", "b", "c", "dd", "e1"], 5)
@@ -117,7 +120,7 @@ def test_image_walk_random_small_vocab_equals_oracle(walker, tmp_path, seed):
     # a tenant the index has never seen, mixed into the batch
     tenants = tenants + ["nobody"]
     tt = [3 if i % 11 == 0 else t for i, t in enumerate(tt)]
-    off, ranks, _ = walk(walker, str(tmp_path), pairs, tenants, topics, tt)
+    off, ranks, _ = walk(walker, str(tmp_path), pairs, tenants, topics, tt, env=env)
     want = oracle(pairs, tenants, topics, tt)
     assert off.tolist() == want.offsets.tolist() and ranks.tolist() == want.ranks.tolist()
     assert len(ranks) > 1000
@@ -153,7 +156,7 @@ def test_image_walk_wide_fanouts_long_levels_and_split_runs(walker, tmp_path):
     tt = [0] * len(topics)
     topics += ["dev00000/state", "dev02499/state", "dev02500/state", "dev00017"]
     tt += [1, 1, 1, 1]
-    off, ranks, log = walk(walker, str(tmp_path), pairs, tenants, topics, tt)
+    off, ranks, log = walk(walker, str(tmp_path), pairs, tenants, topics, tt, env=PIECES)
     want = oracle(pairs, tenants, topics, tt)
     assert off.tolist() == want.offsets.tolist() and ranks.tolist() == want.ranks.tolist()
     assert int(log.split(" tag blocks")[0].split()[-1]) > 64          # the global tag table was really used
