@@ -469,7 +469,8 @@ int insert_tenant_keys_parallel(const KVBlob& kv, TenantBuild& tb, std::vector<u
             prev = cur;
             r++;
         }
-        if (r < hi && r > cuts.back()) cuts.push_back(r);
+        if (r >= hi) break;   // the rest of the range hangs off one root child: no further cut exists (and no further scan)
+        if (r > cuts.back()) cuts.push_back(r);
     }
     cuts.push_back(hi);
     const size_t P = cuts.size() - 1;
